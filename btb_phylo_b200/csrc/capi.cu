@@ -1,0 +1,427 @@
+// C-ABI of libbtbphylo.so: error plumbing, distance stage (levels 1-3).  See include/btb_phylo.h.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "host_io.h"
+
+namespace btb {
+
+std::string &last_error() {
+    thread_local std::string e;
+    return e;
+}
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+int distance_tiles_popc(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, int,
+                        cudaStream_t);
+int distance_tiles_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, int,
+                        cudaStream_t);
+extern int g_umma_cta_group;
+
+int require_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(BTB_ENODEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(BTB_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    BTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(BTB_ENODEVICE, "device %d is sm_%d%d; libbtbphylo is built for sm_100a only", device, prop.major, prop.minor);
+    BTB_CUDA(cudaSetDevice(device));
+    return BTB_OK;
+}
+
+// engine choice for AUTO: the tensor-core engine whenever its one-hot operands fit in free HBM
+int pick_engine(int engine, int64_t n, int64_t len, int sigma, int64_t out_bytes) {
+    if (engine == BTB_ENGINE_POPC || engine == BTB_ENGINE_UMMA) return engine;
+    if (len == 0) return BTB_ENGINE_POPC;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return BTB_ENGINE_POPC;
+    const int64_t need = btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma) + out_bytes + n * len + (int64_t(1) << 30);
+    return need < int64_t(free_b) ? BTB_ENGINE_UMMA : BTB_ENGINE_POPC;
+}
+
+// rank r of `world` owns tiles [lo, hi) of the band order: equal counts, contiguous for L2 locality
+void tile_share(int64_t tiles, int rank, int world, int64_t &lo, int64_t &hi) {
+    lo = tiles * rank / world;
+    hi = tiles * (rank + 1) / world;
+}
+
+}  // namespace btb
+
+using namespace btb;
+
+extern "C" int btb_last_error(char *buf, size_t cap) {
+    const std::string &e = last_error();
+    if (buf && cap) {
+        size_t n = std::min(cap - 1, e.size());
+        memcpy(buf, e.data(), n);
+        buf[n] = 0;
+    }
+    return int(e.size());
+}
+
+extern "C" const char *btb_version(void) { return "btb-phylo-b200 0.1 (snp-sites 2.5.1 -c / snp-dists 0.8.2 semantics, sm_100a)"; }
+
+extern "C" int btb_device_count(int *count) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+    int ok = 0;
+    for (int d = 0; d < c; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    if (count) *count = ok;
+    return BTB_OK;
+}
+
+extern "C" int btb_set_option(const char *key, int value) {
+    if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
+    return fail(BTB_EINVAL, "unknown option");
+}
+
+extern "C" int64_t btb_dist_tile_count(int64_t n) { return n > 0 ? tile_count(n) : 0; }
+
+extern "C" int btb_dist_tile_coords(int64_t n, int64_t tile, int32_t *I, int32_t *J) {
+    if (n <= 0 || tile < 0 || tile >= tile_count(n)) return fail(BTB_EINVAL, "tile index out of range");
+    int i, j;
+    tile_coords(tiles_per_dim(n), tile, i, j);
+    if (I) *I = i;
+    if (J) *J = j;
+    return BTB_OK;
+}
+
+extern "C" int btb_distance_tiles(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
+                                  int64_t tile_lo, int64_t tile_hi, void *d_out, int out_elem_bytes,
+                                  int64_t out_ld, int out_mode, int mirror, void *stream) {
+    if (!d_operands || !d_out || n <= 0 || len < 0) return fail(BTB_EINVAL, "btb_distance_tiles: bad argument");
+    if (out_elem_bytes != 2 && out_elem_bytes != 4) return fail(BTB_EINVAL, "out_elem_bytes must be 2 or 4");
+    if (out_elem_bytes == 2 && len > 65535) return fail(BTB_EINVAL, "uint16 output needs len < 65536");
+    if (tile_lo < 0 || tile_hi > tile_count(n) || tile_lo > tile_hi) return fail(BTB_EINVAL, "tile range out of bounds");
+    if (out_mode == 0 && out_ld < n) return fail(BTB_EINVAL, "out_ld < n");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (engine == BTB_ENGINE_POPC)
+        return distance_tiles_popc(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s);
+    if (engine == BTB_ENGINE_UMMA)
+        return distance_tiles_umma(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s);
+    return fail(BTB_EINVAL, "btb_distance_tiles: engine must be POPC or UMMA");
+}
+
+// =============================================================================== level 2
+extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                                    int allchars, int keepcase, int engine, int device, int rank, int world,
+                                    void *out, int out_elem_bytes, int64_t out_ld) {
+    if (!seqs || !out || n <= 0 || len < 0 || row_stride < len || out_ld < n || world < 1 || rank < 0 || rank >= world)
+        return fail(BTB_EINVAL, "btb_dist_matrix_host: bad argument");
+    if (out_elem_bytes != 2 && out_elem_bytes != 4) return fail(BTB_EINVAL, "out_elem_bytes must be 2 or 4");
+    if (out_elem_bytes == 2 && len > 65535) return fail(BTB_EINVAL, "uint16 output needs len < 65536");
+    BTB_TRY(require_device(device));
+    cudaStream_t st;
+    BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = BTB_OK;
+    uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
+    const int64_t d_stride = (len + 15) / 16 * 16;
+    const int64_t d_ld = (n + 7) / 8 * 8;
+    auto cleanup = [&]() {
+        cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
+        cudaStreamDestroy(st);
+    };
+#define L2_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            rc = fail(BTB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                         \
+            cleanup();                                                                                    \
+            return rc;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+#define L2_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
+    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(std::max<int64_t>(1, n * d_stride))));
+    if (len > 0)
+        L2_CUDA(cudaMemcpy2DAsync(d_seqs, size_t(d_stride), seqs, size_t(row_stride), size_t(len), size_t(n),
+                                  cudaMemcpyHostToDevice, st));
+    uint8_t table[256];
+    int sigma = 4;
+    L2_TRY(btb_dist_alphabet(d_seqs, n, len, d_stride, allchars, keepcase, table, &sigma, st));
+    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * d_ld * out_elem_bytes)));
+    const int eng = pick_engine(engine, n, len, sigma, n * d_ld * out_elem_bytes);
+    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
+    L2_TRY(btb_dist_encode(eng, d_seqs, n, len, d_stride, table, sigma, d_ops, st));
+    int64_t lo, hi;
+    tile_share(tile_count(n), rank, world, lo, hi);
+    L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 0, 1, st));
+    const size_t eb = size_t(out_elem_bytes);
+    if (world == 1) {
+        L2_CUDA(cudaMemcpy2DAsync(out, size_t(out_ld) * eb, d_out, size_t(d_ld) * eb, size_t(n) * eb, size_t(n),
+                                  cudaMemcpyDeviceToHost, st));
+    } else {
+        // copy back the owned tiles and their mirrors, merging runs of tiles on one block row
+        const int64_t T = tiles_per_dim(n);
+        int64_t t = lo;
+        while (t < hi) {
+            int I, J, I2, J2;
+            tile_coords(T, t, I, J);
+            int64_t e = t + 1;
+            while (e < hi) { tile_coords(T, e, I2, J2); if (I2 != I || J2 != J + int(e - t)) break; ++e; }
+            const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + BTB_TILE);
+            const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + (e - t) * BTB_TILE);
+            char *ho = static_cast<char *>(out);
+            L2_CUDA(cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
+                                      size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, st));
+            L2_CUDA(cudaMemcpy2DAsync(ho + (c0 * out_ld + r0) * eb, size_t(out_ld) * eb, d_out + (c0 * d_ld + r0) * eb,
+                                      size_t(d_ld) * eb, size_t(r1 - r0) * eb, size_t(c1 - c0), cudaMemcpyDeviceToHost, st));
+            t = e;
+        }
+    }
+    L2_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+    return BTB_OK;
+#undef L2_CUDA
+#undef L2_TRY
+}
+
+// =============================================================================== level 1: snp-dists
+namespace {
+
+struct DenseFasta {
+    std::vector<std::string> names;
+    int64_t n = 0, len = 0, stride = 0;
+    uint8_t *rows = nullptr;          // pinned
+    ~DenseFasta() { if (rows) cudaFreeHost(rows); }
+};
+
+// File -> dense pinned rows.  Error texts follow snp-dists 0.8.2.
+int read_dense(const char *path, int threads, DenseFasta &df) {
+    FileBytes fb;
+    BTB_TRY(load_file(path, fb));
+    std::vector<FastaRecord> recs;
+    BTB_TRY(index_fasta(fb, recs, threads));
+    if (recs.empty()) return fail(BTB_EFORMAT, "ERROR: file contained no sequences");
+    if (int64_t(recs.size()) > BTB_MAX_SEQ)
+        return fail(BTB_EFORMAT, "ERROR: snp-dists can only handle %d sequences at most. Please change MAX_SEQ and recompile.", BTB_MAX_SEQ);
+    // the exact walk gives every record's length whatever its line layout
+    df.n = int64_t(recs.size());
+    df.len = walk_record(fb, recs[0], nullptr);
+    df.stride = std::max<int64_t>(16, (df.len + 15) / 16 * 16);
+    BTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&df.rows), size_t(df.n * df.stride)));
+    df.names.resize(recs.size());
+    std::vector<int64_t> lens(recs.size(), 0);
+    auto work = [&](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> tmp;
+        for (int64_t i = lo; i < hi; ++i) {
+            const FastaRecord &r = recs[size_t(i)];
+            df.names[size_t(i)] = r.name;
+            uint8_t *dst = df.rows + i * df.stride;
+            tmp.resize(r.raw_len + 1);
+            const int64_t l = walk_record(fb, r, tmp.data());
+            lens[size_t(i)] = l;
+            if (l != df.len) continue;
+            memcpy(dst, tmp.data(), size_t(l));
+            memset(dst + l, '.', size_t(df.stride - l));
+        }
+    };
+    threads = std::max(1, std::min<int>(threads, 64));
+    if (threads == 1 || df.n < 64) {
+        work(0, df.n);
+    } else {
+        std::vector<std::thread> pool;
+        const int64_t span = (df.n + threads - 1) / threads;
+        for (int t = 0; t < threads; ++t) {
+            int64_t lo = t * span, hi = std::min(df.n, lo + span);
+            if (lo < hi) pool.emplace_back(work, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    }
+    for (int64_t i = 0; i < df.n; ++i)
+        if (lens[size_t(i)] != df.len)
+            return fail(BTB_EFORMAT, "ERROR: sequence #%lld '%s' has length %lld but expected %lld", (long long)(i + 1),
+                        recs[size_t(i)].name.c_str(), (long long)lens[size_t(i)], (long long)df.len);
+    return BTB_OK;
+}
+
+}  // namespace
+
+extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n, int64_t row0,
+                                   int64_t row1, const char *const *names, char sep, int host_threads,
+                                   char *buf, size_t cap, size_t *written) {
+    if (!mat || !buf || !names || row0 < 0 || row1 < row0 || (elem_bytes != 2 && elem_bytes != 4))
+        return fail(BTB_EINVAL, "btb_format_csv_rows: bad argument");
+    const int64_t rows = row1 - row0;
+    const size_t per_cell = elem_bytes == 2 ? 6 : 11;
+    std::vector<size_t> off(size_t(rows) + 1, 0);
+    for (int64_t r = 0; r < rows; ++r)
+        off[size_t(r) + 1] = off[size_t(r)] + strlen(names[row0 + r]) + size_t(n) * per_cell + 1 + 8;
+    std::vector<size_t> used(size_t(rows), 0);
+    // format into generously spaced slots, then compact
+    std::vector<char> tmp;
+    const bool direct = off[size_t(rows)] <= cap;
+    char *work = buf;
+    if (!direct) { tmp.resize(off[size_t(rows)]); work = tmp.data(); }
+    auto job = [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; ++r) {
+            char *p = work + off[size_t(r)];
+            const size_t nl = strlen(names[row0 + r]);
+            memcpy(p, names[row0 + r], nl);
+            p += nl;
+            p += format_row(static_cast<const char *>(mat) + size_t(r) * size_t(ld) * size_t(elem_bytes), elem_bytes, n, sep, p);
+            *p++ = '\n';
+            used[size_t(r)] = size_t(p - (work + off[size_t(r)]));
+        }
+    };
+    const int threads = std::max(1, std::min<int>(host_threads, 64));
+    if (threads == 1 || rows < 2 * threads) {
+        job(0, rows);
+    } else {
+        std::vector<std::thread> pool;
+        const int64_t span = (rows + threads - 1) / threads;
+        for (int t = 0; t < threads; ++t) {
+            int64_t lo = t * span, hi = std::min(rows, lo + span);
+            if (lo < hi) pool.emplace_back(job, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    }
+    size_t total = 0;
+    for (int64_t r = 0; r < rows; ++r) total += used[size_t(r)];
+    if (total > cap) return fail(BTB_EINVAL, "btb_format_csv_rows: buffer too small (%zu needed)", total);
+    size_t w = 0;
+    for (int64_t r = 0; r < rows; ++r) {
+        memmove(buf + w, work + off[size_t(r)], used[size_t(r)]);
+        w += used[size_t(r)];
+    }
+    if (written) *written = w;
+    return BTB_OK;
+}
+
+extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
+                             char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
+                             int64_t *n_samples, int64_t *seq_len) {
+    if (!in_fasta || !out_path) return fail(BTB_EINVAL, "btb_snp_dists: NULL path");
+    const int threads = std::max(1, host_threads);
+    (void)n_gpus;   // one device per call for now; multi-rank drivers use btb_dist_matrix_host / level 3
+    if (!quiet) {
+        fprintf(stderr, "This is snp-dists 0.8.2\n");
+        fprintf(stderr, "Will use %d threads.\n", threads);
+    }
+    BTB_TRY(require_device(0));
+    DenseFasta df;
+    int rc = read_dense(in_fasta, threads, df);
+    if (rc != BTB_OK) { if (!quiet) fprintf(stderr, "%s\n", last_error().c_str()); return rc; }
+    if (!quiet) fprintf(stderr, "Read %lld sequences of length %lld\n", (long long)df.n, (long long)df.len);
+    if (n_samples) *n_samples = df.n;
+    if (seq_len) *seq_len = df.len;
+    const int64_t n = df.n, len = df.len;
+    const int eb = len < 65536 ? 2 : 4;
+    const int64_t ld = (n + 7) / 8 * 8;
+
+    cudaStream_t st, st2;
+    BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    BTB_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
+    char *h_stage[2] = {nullptr, nullptr};
+    FILE *fo = nullptr;
+    const bool to_stdout = !strcmp(out_path, "-") || !strcmp(out_path, "/dev/stdout");
+    std::string tmp_path = to_stdout ? std::string("/dev/stdout") : std::string(out_path) + ".tmp";
+    auto cleanup = [&]() {
+        cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
+        if (h_stage[0]) cudaFreeHost(h_stage[0]);
+        if (h_stage[1]) cudaFreeHost(h_stage[1]);
+        cudaStreamDestroy(st); cudaStreamDestroy(st2);
+        if (fo) { fclose(fo); if (!to_stdout) remove(tmp_path.c_str()); }
+    };
+#define L1_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            rc = fail(BTB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                         \
+            cleanup();                                                                                    \
+            return rc;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+#define L1_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)));
+    L1_CUDA(cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st));
+    uint8_t table[256];
+    int sigma = 4;
+    L1_TRY(btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st));
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)));
+    const int eng = pick_engine(engine, n, len, sigma, n * ld * eb);
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
+    L1_TRY(btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st));
+    L1_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, 0, tile_count(n), d_out, eb, ld, 0, 1, st));
+    L1_CUDA(cudaStreamSynchronize(st));
+
+    // ---- serialise: D2H row blocks (double-buffered) -> threads format -> ordered writes
+    fo = fopen(tmp_path.c_str(), "wb");
+    if (!fo) { rc = fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); cleanup(); return rc; }
+    setvbuf(fo, nullptr, _IOFBF, 1 << 22);
+    std::vector<const char *> name_ptr(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) name_ptr[size_t(i)] = df.names[size_t(i)].c_str();
+    if (!molten) {
+        std::string head = corner ? "snp-dists 0.8.2" : "";
+        for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
+        head.push_back('\n');
+        fwrite(head.data(), 1, head.size(), fo);
+    }
+    const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / std::max<int64_t>(1, ld * eb)));
+    L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[0]), size_t(block_rows * ld * eb)));
+    L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[1]), size_t(block_rows * ld * eb)));
+    size_t max_name = 0;
+    for (auto &s : df.names) max_name = std::max(max_name, s.size());
+    std::vector<char> text(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 16));
+    cudaEvent_t ev[2];
+    L1_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    L1_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    auto issue = [&](int64_t b) -> cudaError_t {
+        const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
+        cudaError_t e = cudaMemcpyAsync(h_stage[b & 1], d_out + size_t(r0 * ld * eb), size_t((r1 - r0) * ld * eb),
+                                        cudaMemcpyDeviceToHost, st2);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ev[b & 1], st2);
+    };
+    const int64_t blocks = (n + block_rows - 1) / block_rows;
+    L1_CUDA(issue(0));
+    for (int64_t b = 0; b < blocks; ++b) {
+        L1_CUDA(cudaEventSynchronize(ev[b & 1]));
+        if (b + 1 < blocks) L1_CUDA(issue(b + 1));
+        const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
+        if (!molten) {
+            size_t w = 0;
+            L1_TRY(btb_format_csv_rows(h_stage[b & 1], eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads,
+                                       text.data(), text.size(), &w));
+            if (fwrite(text.data(), 1, w, fo) != w) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
+        } else {
+            for (int64_t r = r0; r < r1; ++r)
+                for (int64_t i = 0; i < n; ++i) {
+                    const uint32_t v = eb == 2 ? reinterpret_cast<const uint16_t *>(h_stage[b & 1])[(r - r0) * ld + i]
+                                               : reinterpret_cast<const uint32_t *>(h_stage[b & 1])[(r - r0) * ld + i];
+                    fprintf(fo, "%s%c%s%c%u\n", df.names[size_t(r)].c_str(), sep, df.names[size_t(i)].c_str(), sep, v);
+                }
+        }
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
+    fo = nullptr;
+    if (!to_stdout && rename(tmp_path.c_str(), out_path) != 0) { rc = fail(BTB_EIO, "cannot rename to '%s'", out_path); cleanup(); return rc; }
+    cleanup();
+    return BTB_OK;
+#undef L1_CUDA
+#undef L1_TRY
+}

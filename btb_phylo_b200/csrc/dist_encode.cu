@@ -1,0 +1,275 @@
+// k4 operand preparation: SNP alignment bytes -> what the distance engines consume.
+//
+// Replaces the load loop of snp-dists 0.8.2 (toupper unless -k, non-ACGT -> '.'
+// unless -a), reached in the reference through btbphylo/phylogeny.py:149.  A 256-entry symbol table
+// carries those rules: table[byte] = code 0..sigma-1, or 0xFF for bytes that never count.
+//
+//   POPC engine : Q = ceil(log2 sigma) code bit-planes + 1 validity plane, 32 sites per word.
+//                 Bit order inside a row is a fixed permutation of the sites (a lane reads 4
+//                 consecutive bytes, a ballot gathers byte b of all lanes), identical for every
+//                 row -- a distance is a sum over sites, so any common order is exact.
+//   UMMA engine : K-major int8, sigma4 = roundup(sigma, 4) bytes per site:
+//                 A[i][site*sigma4 + b] = [valid and code == b]            (one-hot)
+//                 B[i][site*sigma4 + b] = [valid and code != b, b < sigma] (masked complement)
+//                 so that  sum_b A_i * B_j = [valid_i][valid_j][code_i != code_j]  = snp-dists' test.
+//
+// HBM-bound streaming kernels: algorithmic bytes = n*len read + operand bytes written.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace btb {
+
+// ------------------------------------------------------------------ alphabet scan (-a mode)
+__global__ void presence_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len,
+                                int64_t row_stride, uint32_t *__restrict__ present /*[8]*/) {
+    __shared__ uint32_t s_present[8];
+    if (threadIdx.x < 8) s_present[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+        const uint8_t *p = seqs + row * row_stride;
+        for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < len;
+             k += (int64_t)gridDim.x * blockDim.x) {
+            uint32_t b = p[k];
+            loc[b >> 5] |= 1u << (b & 31);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = loc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_present[i], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && s_present[threadIdx.x]) atomicOr(&present[threadIdx.x], s_present[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ POPC planes
+// One warp packs 1024 sites (32 words) of one row.  Lane l of iteration it reads the 4 bytes of
+// sites 128*it + 4*l .. +3; word 4*it + b holds, at bit l, site 128*it + 4*l + b.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256)
+encode_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                     const uint8_t *__restrict__ table_g, int q_planes, int64_t words,
+                     uint32_t *__restrict__ planes) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t blocks_per_row = words / 32 + (words % 32 != 0);
+    const int64_t row = warp / blocks_per_row;
+    if (row >= n) return;
+    const int64_t w0 = (warp % blocks_per_row) * 32;
+    const uint8_t *p = seqs + row * row_stride;
+    uint32_t keep[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // lane j keeps word w0 + j of every plane
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const int64_t site = (w0 + 4 * it) * 32 + 4 * lane;
+        uint32_t raw = 0x2e2e2e2eu;                    // '.' never counts under any table
+        if (ALIGNED && site + 3 < len) {
+            raw = *reinterpret_cast<const uint32_t *>(p + site);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (site + b < len) raw = (raw & ~(0xffu << (8 * b))) | (uint32_t(p[site + b]) << (8 * b));
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t code = table[(raw >> (8 * b)) & 0xff];
+            const bool valid = code != 0xff;
+            const int j = 4 * it + b;
+            const uint32_t v = __ballot_sync(0xffffffffu, valid);
+            if (lane == j) keep[8] = v;
+#pragma unroll
+            for (int pl = 0; pl < 8; ++pl) {
+                if (pl < q_planes) {                       // warp-uniform
+                    const uint32_t bits = __ballot_sync(0xffffffffu, valid && ((code >> pl) & 1));
+                    if (lane == j) keep[pl] = bits;
+                }
+            }
+        }
+    }
+    const int64_t w = w0 + lane;
+    if (w < words) {
+        const int64_t plane_stride = n * words;
+#pragma unroll
+        for (int pl = 0; pl < 8; ++pl)
+            if (pl < q_planes) planes[pl * plane_stride + row * words + w] = keep[pl];
+        planes[q_planes * plane_stride + row * words + w] = keep[8];
+    }
+}
+
+// ------------------------------------------------------------------ UMMA one-hot operands
+// One thread per 4 sites when sigma4 == 4 (a 16-byte store to A and to B); generic path per site.
+__global__ void __launch_bounds__(256)
+encode_onehot4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                      const uint8_t *__restrict__ table_g, int64_t kbytes,
+                      uint8_t *__restrict__ A, uint8_t *__restrict__ B, int aligned) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int64_t quads = kbytes / 16;                     // 4 sites -> 16 operand bytes
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+    const uint8_t *p = seqs + row * row_stride;
+    for (int64_t qd = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; qd < quads;
+         qd += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t site = qd * 4;
+        uint32_t raw = 0x2e2e2e2eu;
+        if (aligned && site + 3 < len) {
+            raw = *reinterpret_cast<const uint32_t *>(p + site);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (site + b < len) raw = (raw & ~(0xffu << (8 * b))) | (uint32_t(p[site + b]) << (8 * b));
+        }
+        uint4 a, c;
+        uint32_t *aw = &a.x, *cw = &c.x;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t code = table[(raw >> (8 * b)) & 0xff];
+            const uint32_t hot = code < 4 ? (1u << (8 * code)) : 0u;
+            aw[b] = hot;
+            cw[b] = code < 4 ? (0x01010101u ^ hot) : 0u;
+        }
+        *reinterpret_cast<uint4 *>(A + row * kbytes + qd * 16) = a;
+        *reinterpret_cast<uint4 *>(B + row * kbytes + qd * 16) = c;
+    }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+encode_onehot_generic_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len,
+                             int64_t row_stride, const uint8_t *__restrict__ table_g, int sigma,
+                             int sigma4, int64_t kbytes, uint8_t *__restrict__ A,
+                             uint8_t *__restrict__ B) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int wps = sigma4 / 4;                            // words per site
+    const int64_t total_words = kbytes / 4;
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+    const uint8_t *p = seqs + row * row_stride;
+    uint32_t *Aw = reinterpret_cast<uint32_t *>(A + row * kbytes);
+    uint32_t *Bw = reinterpret_cast<uint32_t *>(B + row * kbytes);
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total_words;
+         w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t site = w / wps;
+        const int sub = int(w % wps);
+        uint32_t hot = 0, comp = 0;
+        if (site < len) {
+            const uint32_t code = table[p[site]];
+            if (code != 0xff) {
+                if (int(code >> 2) == sub) hot = 1u << (8 * (code & 3));
+                uint32_t live = 0;                          // planes of this word that exist (< sigma)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (sub * 4 + b < sigma) live |= 1u << (8 * b);
+                comp = live ^ hot;
+            }
+        }
+        Aw[w] = hot;
+        Bw[w] = comp;
+    }
+    }
+}
+
+}  // namespace btb
+
+using namespace btb;
+
+// =============================================================================== C-ABI
+extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                                 int allchars, int keepcase, uint8_t table[256], int *sigma,
+                                 void *stream_) {
+    if (!table || !sigma) return fail(BTB_EINVAL, "btb_dist_alphabet: NULL output");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    for (int b = 0; b < 256; ++b) table[b] = 0xff;
+    auto up = [&](int b) { return (!keepcase && b >= 'a' && b <= 'z') ? b - 32 : b; };
+    if (!allchars) {
+        const char *acgt = "ACGT";
+        for (int b = 0; b < 256; ++b)
+            for (int c = 0; c < 4; ++c)
+                if (up(b) == acgt[c]) table[b] = uint8_t(c);
+        *sigma = 4;
+        return BTB_OK;
+    }
+    if (!d_seqs && n * len > 0) return fail(BTB_EINVAL, "btb_dist_alphabet: allchars needs the alignment");
+    uint32_t *d_present = nullptr;
+    uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n * len > 0) {
+        BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_present), sizeof(present), stream));
+        BTB_CUDA(cudaMemsetAsync(d_present, 0, sizeof(present), stream));
+        dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 2048));
+        presence_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_present);
+        BTB_CUDA(cudaGetLastError());
+        BTB_CUDA(cudaMemcpyAsync(present, d_present, sizeof(present), cudaMemcpyDeviceToHost, stream));
+        BTB_CUDA(cudaStreamSynchronize(stream));
+        BTB_CUDA(cudaFreeAsync(d_present, stream));
+    }
+    // symbols that occur after the load rules (upper-casing), '.' excluded, in byte order
+    bool occurs[256] = {false};
+    for (int b = 0; b < 256; ++b)
+        if (present[b >> 5] >> (b & 31) & 1) occurs[up(b)] = true;
+    occurs[int('.')] = false;
+    int code_of[256], s = 0;
+    for (int b = 0; b < 256; ++b) code_of[b] = occurs[b] ? s++ : -1;
+    if (s > 254) return fail(BTB_EINVAL, "alphabet too large");
+    for (int b = 0; b < 256; ++b) {
+        int u = up(b);
+        if (u != '.' && code_of[u] >= 0) table[b] = uint8_t(code_of[u]);
+    }
+    *sigma = s > 0 ? s : 1;
+    return BTB_OK;
+}
+
+extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma) {
+    if (engine == BTB_ENGINE_POPC) return (popc_code_planes(sigma) + 1) * n * popc_words(len) * 4;
+    if (engine == BTB_ENGINE_UMMA) return 2 * n * umma_k_bytes(len, sigma);
+    return -1;
+}
+
+extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int64_t len,
+                               int64_t row_stride, const uint8_t table[256], int sigma,
+                               void *d_operands, void *stream_) {
+    if (n <= 0 || len < 0 || !d_operands || !table) return fail(BTB_EINVAL, "btb_dist_encode: bad argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint8_t *d_table = nullptr;
+    BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_table), 256, stream));
+    BTB_CUDA(cudaMemcpyAsync(d_table, table, 256, cudaMemcpyHostToDevice, stream));
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_seqs) % 4 == 0) && (row_stride % 4 == 0);
+    if (engine == BTB_ENGINE_POPC) {
+        const int q = popc_code_planes(sigma);
+        if (q > 8) return fail(BTB_EINVAL, "alphabet too large for the POPC engine");
+        const int64_t words = popc_words(len);
+        const int64_t blocks_per_row = words / 32 + (words % 32 != 0);
+        const int64_t warps = n * blocks_per_row;
+        const unsigned grid = unsigned((warps + 7) / 8);
+        if (aligned)
+            encode_planes_kernel<true><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q,
+                                                                 words, static_cast<uint32_t *>(d_operands));
+        else
+            encode_planes_kernel<false><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q,
+                                                                  words, static_cast<uint32_t *>(d_operands));
+    } else if (engine == BTB_ENGINE_UMMA) {
+        const int64_t kb = umma_k_bytes(len, sigma);
+        uint8_t *A = static_cast<uint8_t *>(d_operands);
+        uint8_t *B = A + n * kb;
+        if (sigma4_of(sigma) == 4) {
+            dim3 grid((unsigned)std::min<int64_t>((kb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            encode_onehot4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, B,
+                                                            aligned ? 1 : 0);
+        } else {
+            dim3 grid((unsigned)std::min<int64_t>((kb / 4 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            encode_onehot_generic_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table,
+                                                                   sigma, sigma4_of(sigma), kb, A, B);
+        }
+    } else {
+        return fail(BTB_EINVAL, "btb_dist_encode: unknown engine %d", engine);
+    }
+    BTB_CUDA(cudaGetLastError());
+    BTB_CUDA(cudaFreeAsync(d_table, stream));
+    return BTB_OK;
+}

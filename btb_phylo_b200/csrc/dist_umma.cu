@@ -1,0 +1,454 @@
+// k4, UMMA engine: the SNP distance matrix as an exact int8 GEMM on the 5th-gen tensor cores.
+//
+// Replaces the O(N^2 L) byte-compare loop of snp-dists 0.8.2, reached in
+// the reference through btbphylo/phylogeny.py:149.  With the operands of dist_encode.cu,
+//     d(i,j) = sum_k A[i][k] * B[j][k]          (A one-hot, B masked complement, values 0/1)
+// which tcgen05.mma kind::i8 evaluates exactly with int32 accumulators in tensor memory.
+//
+// Kernel shape (sm_100a only):
+//   * persistent; one unit of work = one BTB_TILE x BTB_TILE tile of the upper triangle
+//     (CG = 2: a CTA pair, UMMA 256 x 256 x 32, each CTA holds 128 accumulator rows) or one
+//     128-row half of it (CG = 1: UMMA 128 x 256 x 32);
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, 128 K-bytes per stage),
+//     warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> direct + mirrored global stores);
+//   * smem ring of kStages stages with full/empty mbarriers; two TMEM accumulator stages so the
+//     epilogue of tile t overlaps the K loop of tile t+1.
+// Bound: tensor pipe.  ops = 2 * sigma4 * L * 256 * 256 per tile.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace btb {
+
+constexpr int kBlockK = 128;          // K bytes per pipeline stage = one 128B swizzle atom row
+constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
+constexpr int kThreads = 256;
+constexpr int kAccCols = 256;         // accumulator columns per stage (N of the MMA)
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    } else {
+        // both CTAs of the pair signal the leader's barrier: clear the peer bit of the address
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+    }
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+
+// D[tmem] (+)= A[smem] * B[smem], 8-bit integer operands, int32 accumulate
+template <int CG>
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+
+// tcgen05.commit: arrive on `bar` when every MMA issued so far by this thread has completed
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;      // the barrier at this offset in both CTAs of the pair
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"(mask) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row atoms of 1024 B.
+// (descriptor bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout type [61,64) with 2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t(1024 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+
+// instruction descriptor, kind::i8: D = S32 (2 at [4,6)), A/B = signed 8-bit (1 at [7,10) / [10,13)),
+// both K-major (0 at 15 / 16), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+struct UmmaParams {
+    int64_t n;            // sequences
+    int64_t k_blocks;     // K bytes / 128
+    int64_t tile_lo;      // first tile of this launch
+    int64_t units;        // work units in this launch (tiles for CG=2, half tiles for CG=1)
+    void *out;
+    int64_t ld;
+    int out_mode;         // 0 = n x n matrix, 1 = tile-packed
+    int mirror;
+};
+
+template <int CG>
+struct UmmaCfg {
+    static constexpr int kARows = 128;                               // A rows loaded per CTA per stage
+    static constexpr int kBRows = CG == 2 ? 128 : 256;               // B rows loaded per CTA per stage
+    static constexpr int kABytes = kARows * kBlockK;
+    static constexpr int kBBytes = kBRows * kBlockK;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = CG == 2 ? 6 : 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int CG, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const UmmaParams p) {
+    using Cfg = UmmaCfg<CG>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms (same offset in both CTAs of a pair)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool leader = cta_rank == 0;
+    const int64_t worker = CG == 2 ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t n_workers = CG == 2 ? gridDim.x / 2 : gridDim.x;
+    const int64_t T = tiles_per_dim(p.n);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), CG);          // one arrive per producer CTA (+ tx bytes)
+            mbar_init(empty_bar(s), 1);          // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);          // tcgen05.commit
+            mbar_init(tempty_bar(a), CG * 4);    // one arrive per epilogue warp of every CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // unit -> rows of A (m0), rows of B (n0)
+    auto unit_coords = [&](int64_t u, int64_t &m0, int64_t &n0, int &I, int &J, int &half) {
+        const int64_t tile = p.tile_lo + (CG == 2 ? u : u / 2);
+        half = CG == 2 ? int(cta_rank) : int(u & 1);
+        tile_coords(T, tile, I, J);
+        m0 = int64_t(I) * BTB_TILE + half * 128;
+        n0 = int64_t(J) * BTB_TILE;
+    };
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers) {
+                int64_t m0, n0; int I, J, half;
+                unit_coords(u, m0, n0, I, J, half);
+                const int64_t b_row = n0 + (CG == 2 ? int64_t(cta_rank) * 128 : 0);
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if constexpr (CG == 2) {
+                        if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                        else mbar_arrive_cluster(full_bar(stage), 0);
+                    } else {
+                        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    }
+                    tma_load_2d<CG>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), int(m0));
+                    tma_load_2d<CG>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), int(b_row));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (leader CTA)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(CG == 2 ? 256 : 128, kAccCols);
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t it = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+                const int acc = int(it & 1);
+                const uint32_t acc_phase = uint32_t(it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccCols;
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_i8<CG>(d_tmem, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
+                                    idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit<CG>(empty_bar(stage));
+                    if (kb == p.k_blocks - 1) umma_commit<CG>(tfull_bar(acc));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================================================================= epilogue
+        const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
+        OutT *out = static_cast<OutT *>(p.out);
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const int acc = int(it & 1);
+            const uint32_t acc_phase = uint32_t(it >> 1) & 1;
+            int64_t m0, n0; int I, J, half;
+            unit_coords(u, m0, n0, I, J, half);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int64_t row = m0 + quarter * 32 + lane;
+            const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
+            const int64_t tile_slot = CG == 2 ? u : u / 2;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kAccCols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols + c0), v);
+                const int64_t col = n0 + c0;
+                if (p.out_mode == 1) {
+                    OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
+                                (int64_t)(half * 128 + quarter * 32 + lane) * BTB_TILE + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[j] = (row < p.n && col + j < p.n) ? OutT(v[j]) : OutT(0);
+                } else {
+                    if (row < p.n) {
+                        OutT *dst = out + row * p.ld + col;
+                        if (col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                            // interior: 32 consecutive outputs of this row as 16-byte stores
+                            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                            if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
+                                                       v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col + j < p.n) dst[j] = OutT(v[j]);
+                        }
+                    }
+                    if (do_mirror && row < p.n) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+                else mbar_arrive_local(tempty_bar(acc));
+            }
+        }
+    }
+
+    // teardown: nobody leaves (or frees TMEM) while the partner may still signal or read
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn *fn) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        BTB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+        if (!sym || q != cudaDriverEntryPointSuccess) return fail(BTB_ECUDA, "cuTensorMapEncodeTiled not available");
+        cached = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    *fn = cached;
+    return BTB_OK;
+}
+
+// 2-D uint8 tensor [rows][kbytes], box = 128 K-bytes x box_rows rows, 128B swizzle, OOB rows read as 0
+static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int64_t kbytes, int box_rows) {
+    EncodeTiledFn enc;
+    BTB_TRY(get_encode_fn(&enc));
+    cuuint64_t dims[2] = {cuuint64_t(kbytes), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(kbytes)};
+    cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BTB_ECUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
+    return BTB_OK;
+}
+
+int g_umma_cta_group = 2;     // overridable for tests/benchmarks through btb_set_option
+
+template <int CG, typename OutT>
+static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
+    using Cfg = UmmaCfg<CG>;
+    auto kernel = dist_umma_kernel<CG, OutT>;
+    BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    int dev = 0, sms = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    int64_t ctas = CG == 2 ? std::min<int64_t>(sms / 2, p.units) * 2 : std::min<int64_t>(sms, p.units);
+    cfg.gridDim = dim3(unsigned(ctas));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p));
+    return BTB_OK;
+}
+
+int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigma, int64_t tile_lo,
+                        int64_t tile_hi, void *d_out, int out_elem_bytes, int64_t out_ld, int out_mode,
+                        int mirror, cudaStream_t stream) {
+    const int64_t tiles = tile_hi - tile_lo;
+    if (tiles <= 0) return BTB_OK;
+    const int64_t kb = umma_k_bytes(len, sigma);
+    const int cg = g_umma_cta_group == 1 ? 1 : 2;
+    const uint8_t *A = static_cast<const uint8_t *>(d_operands);
+    const uint8_t *B = A + n * kb;
+    if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
+    CUtensorMap ma, mb;
+    BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
+    BTB_TRY(make_operand_map(&mb, B, n, kb, cg == 2 ? 128 : 256));
+    UmmaParams p;
+    p.n = n;
+    p.k_blocks = kb / kBlockK;
+    p.tile_lo = tile_lo;
+    p.units = cg == 2 ? tiles : tiles * 2;
+    p.out = d_out;
+    p.ld = out_ld;
+    p.out_mode = out_mode;
+    p.mirror = mirror;
+    if (cg == 2)
+        return out_elem_bytes == 2 ? launch_umma<2, uint16_t>(ma, mb, p, stream) : launch_umma<2, uint32_t>(ma, mb, p, stream);
+    return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);
+}
+
+}  // namespace btb

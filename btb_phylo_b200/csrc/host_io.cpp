@@ -1,0 +1,274 @@
+// Host-side file framing: see host_io.h.  Parsing and printing only.
+#include "host_io.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "common.cuh"
+
+namespace btb {
+
+FileBytes::~FileBytes() {
+    if (map_base) munmap(map_base, map_size);
+}
+
+int load_file(const char *path, FileBytes &fb) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(BTB_EIO, "ERROR: Could not open filename '%s'", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        close(fd);
+        return fail(BTB_EIO, "ERROR: Could not open filename '%s'", path);
+    }
+    unsigned char magic[2] = {0, 0};
+    ssize_t got = pread(fd, magic, 2, 0);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {       // gzip: inflate through zlib
+        close(fd);
+        gzFile gz = gzopen(path, "rb");
+        if (!gz) return fail(BTB_EIO, "ERROR: Could not open filename '%s'", path);
+        gzbuffer(gz, 1 << 20);
+        size_t cap = size_t(st.st_size) * 4 + (1 << 20), len = 0;
+        fb.owned.resize(cap);
+        for (;;) {
+            if (len == cap) { cap *= 2; fb.owned.resize(cap); }
+            int r = gzread(gz, fb.owned.data() + len, unsigned(std::min<size_t>(cap - len, 1u << 30)));
+            if (r < 0) { gzclose(gz); return fail(BTB_EIO, "ERROR: cannot inflate '%s'", path); }
+            if (r == 0) break;
+            len += size_t(r);
+        }
+        gzclose(gz);
+        fb.owned.resize(len);
+        fb.data = fb.owned.data();
+        fb.size = len;
+        return BTB_OK;
+    }
+    fb.size = size_t(st.st_size);
+    if (fb.size) {
+        void *m = mmap(nullptr, fb.size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); return fail(BTB_EIO, "ERROR: cannot map '%s'", path); }
+        madvise(m, fb.size, MADV_SEQUENTIAL);
+        fb.map_base = m;
+        fb.map_size = fb.size;
+        fb.data = static_cast<const uint8_t *>(m);
+    }
+    close(fd);
+    return BTB_OK;
+}
+
+static inline bool is_space(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// positions in [lo, hi) holding `ch` as the first byte of a line
+static void line_start_hits(const uint8_t *d, size_t lo, size_t hi, uint8_t ch, std::vector<size_t> &out) {
+    size_t p = lo;
+    while (p < hi) {
+        const void *q = memchr(d + p, ch, hi - p);
+        if (!q) break;
+        size_t at = size_t(static_cast<const uint8_t *>(q) - d);
+        if (at == 0 || d[at - 1] == '\n') out.push_back(at);
+        p = at + 1;
+    }
+}
+
+static void describe_layout(const FileBytes &fb, FastaRecord &r) {
+    const uint8_t *d = fb.data + r.seq_off;
+    size_t R = r.raw_len;
+    while (R > 0 && (d[R - 1] == '\n' || d[R - 1] == '\r')) --R;       // trailing terminators / empty lines
+    r.regular = true;
+    r.eol = 1;
+    r.line_w = 0;
+    if (R == 0) { r.seq_len = 0; return; }
+    const void *nl = memchr(d, '\n', R);
+    if (!nl) { r.seq_len = int64_t(R); return; }                        // single line
+    size_t first = size_t(static_cast<const uint8_t *>(nl) - d);
+    if (first > 0 && d[first - 1] == '\r') { r.eol = 2; --first; }
+    if (first == 0 || first > size_t(INT32_MAX)) { r.regular = false; return; }
+    r.line_w = int32_t(first);
+    const size_t pitch = first + size_t(r.eol);
+    const size_t X = R + size_t(r.eol);
+    const size_t q = X / pitch, rem = X % pitch;
+    if (rem == 0) r.seq_len = int64_t(q * first);
+    else if (rem > size_t(r.eol)) r.seq_len = int64_t(q * first + rem - size_t(r.eol));
+    else r.regular = false;
+}
+
+int64_t walk_record(const FileBytes &fb, const FastaRecord &r, uint8_t *out) {
+    const uint8_t *d = fb.data + r.seq_off;
+    const size_t R = r.raw_len;
+    int64_t len = 0;
+    size_t p = 0;
+    while (p < R) {
+        if (d[p] == '\n') { ++p; continue; }                            // empty line
+        const void *nl = memchr(d + p, '\n', R - p);
+        size_t e = nl ? size_t(static_cast<const uint8_t *>(nl) - d) : R;
+        size_t n = e - p;
+        if (out) memcpy(out + len, d + p, n);
+        len += int64_t(n);
+        // one trailing CR per line is dropped (whole-string test, as the parser the tools share does)
+        if (len > 1 && d[e - 1] == '\r') --len;
+        p = e + 1;
+    }
+    return len;
+}
+
+int index_fasta(const FileBytes &fb, std::vector<FastaRecord> &recs, int threads) {
+    recs.clear();
+    const uint8_t *d = fb.data;
+    const size_t N = fb.size;
+    if (N == 0) return BTB_OK;
+    // first record: first '>' or '@' anywhere
+    const void *g = memchr(d, '>', N), *a = memchr(d, '@', N);
+    if (!g && !a) return BTB_OK;
+    size_t first = N;
+    if (g) first = std::min(first, size_t(static_cast<const uint8_t *>(g) - d));
+    if (a) first = std::min(first, size_t(static_cast<const uint8_t *>(a) - d));
+    // later records: '>' / '@' at the start of a line.  A '+' line start would open a FASTQ quality
+    // block; those files take the sequential walk below.
+    threads = std::max(1, std::min(threads, 64));
+    std::vector<std::vector<size_t>> part(size_t(threads) * 3);
+    {
+        std::vector<std::thread> pool;
+        const size_t lo0 = first + 1, span = (N - lo0 + size_t(threads) - 1) / size_t(threads);
+        for (int t = 0; t < threads; ++t) {
+            const size_t lo = lo0 + size_t(t) * span, hi = std::min(N, lo + span);
+            if (lo >= hi) continue;
+            auto job = [&, t, lo, hi] {
+                line_start_hits(d, lo, hi, '>', part[size_t(t) * 3 + 0]);
+                line_start_hits(d, lo, hi, '@', part[size_t(t) * 3 + 1]);
+                line_start_hits(d, lo, hi, '+', part[size_t(t) * 3 + 2]);
+            };
+            if (threads == 1) job(); else pool.emplace_back(job);
+        }
+        for (auto &th : pool) th.join();
+    }
+    std::vector<size_t> starts{first};
+    bool fastq = false;
+    for (int t = 0; t < threads; ++t) {
+        for (int k = 0; k < 2; ++k)
+            for (size_t at : part[size_t(t) * 3 + size_t(k)]) starts.push_back(at);
+        if (!part[size_t(t) * 3 + 2].empty()) fastq = true;
+    }
+    std::sort(starts.begin(), starts.end());
+
+    if (fastq) {
+        // sequential exact walk: record := marker line, sequence lines up to a line starting with
+        // '>', '@' or '+'; after '+': skip that line, then consume >= seq_len quality bytes.
+        size_t p = first;
+        while (p < N) {
+            FastaRecord r;
+            const void *nl = memchr(d + p, '\n', N - p);
+            size_t he = nl ? size_t(static_cast<const uint8_t *>(nl) - d) : N;
+            size_t ne = p + 1;
+            while (ne < he && !is_space(d[ne])) ++ne;
+            r.name.assign(reinterpret_cast<const char *>(d + p + 1), ne - p - 1);
+            r.seq_off = std::min(N, he + 1);
+            size_t q = r.seq_off;
+            while (q < N) {
+                if (d[q] == '>' || d[q] == '@' || d[q] == '+') break;
+                const void *l2 = memchr(d + q, '\n', N - q);
+                q = l2 ? size_t(static_cast<const uint8_t *>(l2) - d) + 1 : N;
+            }
+            r.raw_len = q - r.seq_off;
+            r.regular = false;
+            r.seq_len = walk_record(fb, r, nullptr);
+            recs.push_back(std::move(r));
+            if (q < N && d[q] == '+') {
+                const void *l2 = memchr(d + q, '\n', N - q);
+                q = l2 ? size_t(static_cast<const uint8_t *>(l2) - d) + 1 : N;
+                int64_t need = recs.back().seq_len, have = 0;
+                while (q < N && have < need) { if (d[q] != '\n' && d[q] != '\r') ++have; ++q; }
+                if (have > 0) {
+                    const void *l3 = memchr(d + q, '\n', N - q);
+                    q = l3 ? size_t(static_cast<const uint8_t *>(l3) - d) + 1 : N;
+                }
+                while (q < N && d[q] != '>' && d[q] != '@') ++q;     // scan to the next marker
+            }
+            p = q;
+        }
+        return BTB_OK;
+    }
+
+    recs.resize(starts.size());
+    auto fill = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            FastaRecord &r = recs[i];
+            const size_t p = starts[i], end = i + 1 < starts.size() ? starts[i + 1] : N;
+            const void *nl = memchr(d + p, '\n', end - p);
+            size_t he = nl ? size_t(static_cast<const uint8_t *>(nl) - d) : end;
+            size_t ne = p + 1;
+            while (ne < he && !is_space(d[ne])) ++ne;
+            r.name.assign(reinterpret_cast<const char *>(d + p + 1), ne - p - 1);
+            r.seq_off = std::min(end, he + 1);
+            r.raw_len = end - r.seq_off;
+            describe_layout(fb, r);
+        }
+    };
+    if (threads == 1 || starts.size() < 64) {
+        fill(0, starts.size());
+    } else {
+        std::vector<std::thread> pool;
+        const size_t span = (starts.size() + size_t(threads) - 1) / size_t(threads);
+        for (int t = 0; t < threads; ++t) {
+            size_t lo = size_t(t) * span, hi = std::min(starts.size(), lo + span);
+            if (lo < hi) pool.emplace_back(fill, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    }
+    return BTB_OK;
+}
+
+// ------------------------------------------------------------------------------ decimal output
+namespace {
+struct DigitLut {
+    char d[10000][4];
+    DigitLut() {
+        for (int v = 0; v < 10000; ++v) {
+            d[v][0] = char('0' + v / 1000);
+            d[v][1] = char('0' + v / 100 % 10);
+            d[v][2] = char('0' + v / 10 % 10);
+            d[v][3] = char('0' + v % 10);
+        }
+    }
+};
+const DigitLut kLut;
+
+inline char *put_u32(char *p, uint32_t v) {
+    if (v < 10000) {
+        const char *s = kLut.d[v];
+        const int skip = v < 10 ? 3 : v < 100 ? 2 : v < 1000 ? 1 : 0;
+        memcpy(p, s + skip, 4);                      // writes up to 4, advances by the real width
+        return p + (4 - skip);
+    }
+    if (v < 100000000u) {
+        const uint32_t hi = v / 10000, lo = v % 10000;
+        p = put_u32(p, hi);
+        memcpy(p, kLut.d[lo], 4);
+        return p + 4;
+    }
+    const uint32_t hi = v / 100000000u, rest = v % 100000000u;
+    p = put_u32(p, hi);
+    memcpy(p, kLut.d[rest / 10000], 4);
+    memcpy(p + 4, kLut.d[rest % 10000], 4);
+    return p + 8;
+}
+}  // namespace
+
+size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst) {
+    char *p = dst;
+    if (elem_bytes == 2) {
+        const uint16_t *r = static_cast<const uint16_t *>(row);
+        for (int64_t i = 0; i < n; ++i) { *p++ = sep; p = put_u32(p, r[i]); }
+    } else {
+        const uint32_t *r = static_cast<const uint32_t *>(row);
+        for (int64_t i = 0; i < n; ++i) { *p++ = sep; p = put_u32(p, r[i]); }
+    }
+    return size_t(p - dst);
+}
+
+}  // namespace btb

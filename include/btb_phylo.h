@@ -1,0 +1,175 @@
+/*
+ * btb_phylo.h -- C-ABI of the B200-native phylogeny hot path (libbtbphylo.so).
+ *
+ * The reference (APHA-CSU/btb-phylo) has no FFI: its phylogeny stage is two subprocess calls,
+ *     snp-sites <multi_fasta> -c -o <snps.fas>           btbphylo/phylogeny.py:133
+ *     snp-dists -c -j <T> <snps.fas> > <snps.csv>        btbphylo/phylogeny.py:149
+ * wrapped by snp_sites() (phylogeny.py:128-141) and build_snp_matrix() (phylogeny.py:144-150).
+ * The entry points below are what a binding for that path attaches to.  Level 1 replaces the two
+ * command lines one for one; level 2 is the same work on host buffers (no files); level 3 is
+ * the individual GPU stages on device pointers, used by the tests and by bench.py.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every function returns 0 on success or a
+ *     BTB_E* code, and btb_last_error() gives the text (thread-local);
+ *   - paths are NUL-terminated; buffers are caller-allocated; sizes are element counts unless
+ *     the name says bytes; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - `device` is a CUDA ordinal; level 1/2 calls pick device 0.. themselves from `n_gpus`;
+ *   - there is no CPU fallback: without a usable sm_100 device every compute call fails with
+ *     BTB_ENODEVICE.
+ */
+#ifndef BTB_PHYLO_H
+#define BTB_PHYLO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ---- */
+#define BTB_OK          0
+#define BTB_EINVAL      1   /* bad argument */
+#define BTB_EIO         2   /* cannot open / read / write a file (snp-dists "Could not open filename") */
+#define BTB_EFORMAT     3   /* unequal sequence lengths, no sequences, > BTB_MAX_SEQ sequences */
+#define BTB_ENOSNPS     4   /* snp-sites: "No SNPs were detected" (upstream exits 1, no output file) */
+#define BTB_ECUDA       5   /* a CUDA runtime/driver call failed */
+#define BTB_ENODEVICE   6   /* no sm_100 device visible */
+#define BTB_ENOMEM      7
+
+#define BTB_MAX_SEQ     100000      /* snp-dists 0.8.2 MAX_SEQ */
+
+/* distance engines: both are exact integer kernels for sm_100a */
+#define BTB_ENGINE_AUTO (-1)
+#define BTB_ENGINE_POPC   0   /* warp-tiled XOR/AND/POPC over bit-planes */
+#define BTB_ENGINE_UMMA   1   /* tcgen05 kind::i8 GEMM on one-hot int8 tiles, int32 accumulators in TMEM */
+
+/* side length of one scheduler tile of the distance matrix (rows == columns) */
+#define BTB_TILE        256
+
+int         btb_last_error(char *buf, size_t cap);       /* copies the message, returns its length */
+const char *btb_version(void);
+int         btb_device_count(int *count);                 /* number of usable sm_100 devices */
+/* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (default 2: CTA pairs, 256-row UMMA) */
+int         btb_set_option(const char *key, int value);
+
+/* =====================================================================================
+ * Level 1 -- file to file.  Replaces the two command lines.
+ * ===================================================================================== */
+
+/* snp-sites <in_fasta> [-c] -o <out_fasta>   (phylogeny.py:133).
+ * pure_mode = 1 is `-c` (the only mode btb-phylo uses).  Writes one unwrapped record per
+ * sample (phylogeny.py:136-140 and :158-160 rely on that).  BTB_ENOSNPS / BTB_EFORMAT mirror the
+ * upstream exit-1 cases; nothing is written then.  host_threads is the reference's -j. */
+int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode,
+                  int n_gpus, int host_threads,
+                  int64_t *n_samples, int64_t *genome_len, int64_t *n_snps);
+
+/* snp-dists [-a] [-k] [-m] [-c] [-b] [-q] -j T <in_fasta> > <out_path>   (phylogeny.py:149).
+ * sep is ',' for -c else '\t'; corner = 0 is -b; the three banner lines go to stderr unless
+ * quiet.  The file holds the full square, byte-identical with snp-dists 0.8.2. */
+int btb_snp_dists(const char *in_fasta, const char *out_path,
+                  int allchars, int keepcase, int molten, char sep, int corner, int quiet,
+                  int n_gpus, int host_threads, int engine,
+                  int64_t *n_samples, int64_t *seq_len);
+
+/* =====================================================================================
+ * Level 2 -- host buffers in, host buffers out (copies are inside the call).
+ * ===================================================================================== */
+
+/* Full n x n distance matrix of n sequences of `len` bytes (row i at seqs + i*row_stride).
+ * out is row-major with out_ld elements per row, out_elem_bytes = 2 (uint16, needs len < 65536)
+ * or 4 (uint32).  seqs/out may be pageable or pinned host memory.  Ranks of a multi-process
+ * job pass (rank, world) to compute only their share of upper-triangle tiles; cells of tiles
+ * the rank does not own are left untouched.  (world = 1: the whole matrix, both triangles.) */
+int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                         int allchars, int keepcase, int engine, int device,
+                         int rank, int world,
+                         void *out, int out_elem_bytes, int64_t out_ld);
+
+/* Variable columns of an n x G alignment held as dense rows: keep[k] = 1 where snp-sites keeps
+ * column k; returns their count in *n_snps.  snps_out (may be NULL) receives n rows of *n_snps
+ * upper-cased bytes, row stride snps_ld (>= number kept; call once with NULL to size it). */
+int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64_t row_stride,
+                     int pure_mode, int device,
+                     uint8_t *keep, int64_t *n_snps, uint8_t *snps_out, int64_t snps_ld);
+
+/* =====================================================================================
+ * Level 3 -- device pointers, asynchronous on `stream`.  (tests, bench.py, multi-rank drivers)
+ * ===================================================================================== */
+
+/* ---- extraction: k1 pack, k2 column mask, k3 compaction ---- */
+
+/* words of 32 columns per sample and plane, padded for 128-bit access */
+int64_t btb_plane_words(int64_t G);
+
+/* k1: text -> bit-planes.  Sample i's bases start at d_text + rec_off[i]; its lines are
+ * line_w[i] bases followed by eol[i] line-terminator bytes (line_w = 0: unwrapped).  Writes three
+ * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
+ * sample i at d_planes + ((p * n_total + first + i) * words).  d_flags[i] is OR-ed with 1 when a
+ * line terminator is not where the layout says (caller then re-stages that record unwrapped).
+ * unknown_mode = 1 additionally keeps a 4th plane: byte is one of N n - ? (snp-sites default mode). */
+int btb_pack_planes(const uint8_t *d_text, const int64_t *d_rec_off, const int32_t *d_line_w,
+                    const int32_t *d_eol, int64_t n_chunk, int64_t first, int64_t n_total,
+                    int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream);
+
+/* k2: per-column reduction over samples [0, n) -> 5 words per 32 columns in d_colstate:
+ * seenA, seenC, seenG, seenT, anyInvalid.  accumulate != 0 ORs into existing state. */
+int btb_column_mask(const uint32_t *d_planes, int64_t n, int64_t n_total, int64_t G,
+                    uint32_t *d_colstate, int accumulate, void *stream);
+
+/* k3a: column state -> keep bitmask (G bits) + ascending kept-column indices; *d_count gets L.
+ * d_idx must hold G entries (worst case).  pure_mode as in btb_snp_sites. */
+int btb_select_columns(const uint32_t *d_colstate, int64_t G, int pure_mode,
+                       uint32_t *d_keep, uint32_t *d_idx, uint32_t *d_count, void *stream);
+
+/* k3b: gather the kept columns of samples [first, first + n_chunk) as upper-case ASCII:
+ * d_snps[i * snps_ld + l] for l < L. */
+int btb_compact_columns(const uint32_t *d_planes, int64_t first, int64_t n_chunk, int64_t n_total,
+                        int64_t G, const uint32_t *d_idx, int64_t L,
+                        uint8_t *d_snps, int64_t snps_ld, void *stream);
+
+/* ---- distances: k4 ---- */
+
+/* Symbol table of the alignment: table[b] = code 0..sigma-1, or 0xFF when byte b never counts
+ * (everything but ACGT by default; only '.' with allchars).  Default mode needs no data pass
+ * (d_seqs may be NULL); allchars scans the alignment on the device and synchronises `stream`. */
+int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                      int allchars, int keepcase, uint8_t table[256], int *sigma, void *stream);
+
+/* bytes of operand storage the engine needs for this problem */
+int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma);
+
+/* alignment bytes -> engine operands (bit-planes for POPC; one-hot int8 A and masked-complement
+ * int8 B for UMMA) */
+int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                    const uint8_t table[256], int sigma, void *d_operands, void *stream);
+
+/* number of BTB_TILE x BTB_TILE tiles in the upper triangle (diagonal included) */
+int64_t btb_dist_tile_count(int64_t n);
+/* tile index -> (block row I, block column J), I <= J; the order is L2-friendly bands */
+int btb_dist_tile_coords(int64_t n, int64_t tile, int32_t *I, int32_t *J);
+
+/* operands -> distances for tiles [tile_lo, tile_hi).
+ * out_mode 0: d_out is the n x n matrix (out_ld elements per row); the tile and, when mirror != 0,
+ *             its transpose are written.
+ * out_mode 1: d_out is tile-packed: tile t at d_out + (t - tile_lo) * BTB_TILE * BTB_TILE elements,
+ *             row-major inside the tile (cells beyond n are zero). */
+int btb_distance_tiles(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
+                       int64_t tile_lo, int64_t tile_hi,
+                       void *d_out, int out_elem_bytes, int64_t out_ld, int out_mode, int mirror,
+                       void *stream);
+
+/* ---- serialisation: k5 ---- */
+
+/* Formats rows [row0, row1) of a host matrix as snp-dists prints them (name SEP d SEP d ... \n)
+ * into buf (cap bytes) using host_threads threads; *written gets the byte count. */
+int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n,
+                        int64_t row0, int64_t row1, const char *const *names, char sep,
+                        int host_threads, char *buf, size_t cap, size_t *written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTB_PHYLO_H */
