@@ -22,14 +22,16 @@ SIGNATURES = {
     "btb_version": (ctypes.c_char_p, []),
     "btb_device_count": (c_int, [ctypes.POINTER(c_int)]),
     "btb_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "btb_query": (c_int, [ctypes.c_char_p, p_i64]),
     "btb_snp_sites": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int, p_i64, p_i64, p_i64]),
     "btb_snp_dists": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int, ctypes.c_char, c_int, c_int,
                               c_int, c_int, c_int, p_i64, p_i64]),
     "btb_dist_matrix_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_vp, c_int, c_i64]),
+    "btb_release_workspace": (c_int, []),
     "btb_extract_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, p_i64, c_vp, c_i64]),
     "btb_plane_words": (c_i64, [c_i64]),
-    "btb_pack_planes": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "btb_pack_planes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "btb_column_mask": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "btb_select_columns": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "btb_compact_columns": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -31,6 +32,7 @@ int distance_tiles_popc(const void *, int64_t, int64_t, int, int64_t, int64_t, v
 int distance_tiles_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, int,
                         cudaStream_t);
 extern int g_umma_cta_group;
+int umma_max_active_clusters(int cg, int *out);
 
 int require_device(int device) {
     int count = 0;
@@ -48,14 +50,14 @@ int require_device(int device) {
     return BTB_OK;
 }
 
-// engine choice for AUTO: the tensor-core engine whenever its one-hot operands fit in free HBM
-int pick_engine(int engine, int64_t n, int64_t len, int sigma, int64_t out_bytes) {
+// engine choice for AUTO: the tensor-core engine whenever the HBM it still has to allocate
+// (`extra_bytes`: its one-hot operands plus whatever else the caller has not allocated yet) is free
+int pick_engine(int engine, int64_t len, int64_t extra_bytes) {
     if (engine == BTB_ENGINE_POPC || engine == BTB_ENGINE_UMMA) return engine;
     if (len == 0) return BTB_ENGINE_POPC;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return BTB_ENGINE_POPC;
-    const int64_t need = btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma) + out_bytes + n * len + (int64_t(1) << 30);
-    return need < int64_t(free_b) ? BTB_ENGINE_UMMA : BTB_ENGINE_POPC;
+    return extra_bytes + (int64_t(1) << 30) < int64_t(free_b) ? BTB_ENGINE_UMMA : BTB_ENGINE_POPC;
 }
 
 // rank r of `world` owns tiles [lo, hi) of the band order: equal counts, contiguous for L2 locality
@@ -97,6 +99,15 @@ extern "C" int btb_set_option(const char *key, int value) {
     return fail(BTB_EINVAL, "unknown option");
 }
 
+extern "C" int btb_query(const char *key, int64_t *value) {
+    if (!key || !value) return fail(BTB_EINVAL, "btb_query: NULL argument");
+    int v = 0;
+    if (!strcmp(key, "umma_max_active_clusters_cg2")) { BTB_TRY(umma_max_active_clusters(2, &v)); *value = v; return BTB_OK; }
+    if (!strcmp(key, "umma_max_active_clusters_cg1")) { BTB_TRY(umma_max_active_clusters(1, &v)); *value = v; return BTB_OK; }
+    if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
+    return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
+}
+
 extern "C" int64_t btb_dist_tile_count(int64_t n) { return n > 0 ? tile_count(n) : 0; }
 
 extern "C" int btb_dist_tile_coords(int64_t n, int64_t tile, int32_t *I, int32_t *J) {
@@ -125,6 +136,44 @@ extern "C" int btb_distance_tiles(int engine, const void *d_operands, int64_t n,
 }
 
 // =============================================================================== level 2
+namespace {
+// Device buffers of btb_dist_matrix_host are kept between calls (one set per device): a weekly
+// production run calls once, a benchmark loop many times; cudaMalloc of ~20 GB is not free.
+struct Workspace {
+    void *p[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+    cudaStream_t st = nullptr;
+    int ensure(int k, size_t bytes, void **out) {
+        bytes = std::max<size_t>(bytes, 16);
+        if (cap[k] < bytes) {
+            if (p[k]) cudaFree(p[k]);
+            p[k] = nullptr; cap[k] = 0;
+            BTB_CUDA(cudaMalloc(&p[k], bytes));
+            cap[k] = bytes;
+        }
+        *out = p[k];
+        return BTB_OK;
+    }
+    void release() {
+        for (int k = 0; k < 3; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
+};
+Workspace g_ws[16];
+std::mutex g_ws_mutex;
+}  // namespace
+
+extern "C" int btb_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 16; ++d)
+        if (g_ws[d].p[0] || g_ws[d].p[1] || g_ws[d].p[2] || g_ws[d].st) { cudaSetDevice(d); g_ws[d].release(); }
+    cudaSetDevice(cur);
+    return BTB_OK;
+}
+
 extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
                                     int allchars, int keepcase, int engine, int device, int rank, int world,
                                     void *out, int out_elem_bytes, int64_t out_ld) {
@@ -133,16 +182,16 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
     if (out_elem_bytes != 2 && out_elem_bytes != 4) return fail(BTB_EINVAL, "out_elem_bytes must be 2 or 4");
     if (out_elem_bytes == 2 && len > 65535) return fail(BTB_EINVAL, "uint16 output needs len < 65536");
     BTB_TRY(require_device(device));
-    cudaStream_t st;
-    BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (device >= 16) return fail(BTB_EINVAL, "device ordinal too large");
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace &ws = g_ws[device];
+    if (!ws.st) BTB_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+    cudaStream_t st = ws.st;
     int rc = BTB_OK;
     uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
     const int64_t d_stride = (len + 15) / 16 * 16;
     const int64_t d_ld = (n + 7) / 8 * 8;
-    auto cleanup = [&]() {
-        cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
-        cudaStreamDestroy(st);
-    };
+    auto cleanup = [&]() {};
 #define L2_CUDA(call)                                                                                     \
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
@@ -153,16 +202,16 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         }                                                                                                 \
     } while (0)
 #define L2_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
-    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(std::max<int64_t>(1, n * d_stride))));
+    L2_TRY(ws.ensure(0, size_t(std::max<int64_t>(1, n * d_stride)), reinterpret_cast<void **>(&d_seqs)));
     if (len > 0)
         L2_CUDA(cudaMemcpy2DAsync(d_seqs, size_t(d_stride), seqs, size_t(row_stride), size_t(len), size_t(n),
                                   cudaMemcpyHostToDevice, st));
     uint8_t table[256];
     int sigma = 4;
     L2_TRY(btb_dist_alphabet(d_seqs, n, len, d_stride, allchars, keepcase, table, &sigma, st));
-    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * d_ld * out_elem_bytes)));
-    const int eng = pick_engine(engine, n, len, sigma, n * d_ld * out_elem_bytes);
-    L2_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
+    L2_TRY(ws.ensure(2, size_t(n * d_ld * out_elem_bytes), reinterpret_cast<void **>(&d_out)));
+    const int eng = pick_engine(engine, len, std::max<int64_t>(0, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma) - int64_t(ws.cap[1])));
+    L2_TRY(ws.ensure(1, size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma))), reinterpret_cast<void **>(&d_ops)));
     L2_TRY(btb_dist_encode(eng, d_seqs, n, len, d_stride, table, sigma, d_ops, st));
     int64_t lo, hi;
     tile_share(tile_count(n), rank, world, lo, hi);
@@ -361,7 +410,7 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     int sigma = 4;
     L1_TRY(btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st));
     L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)));
-    const int eng = pick_engine(engine, n, len, sigma, n * ld * eb);
+    const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
     L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
     L1_TRY(btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st));
     L1_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, 0, tile_count(n), d_out, eb, ld, 0, 1, st));

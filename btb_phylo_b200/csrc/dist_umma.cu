@@ -397,7 +397,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
     return BTB_OK;
 }
 
-int g_umma_cta_group = 2;     // overridable for tests/benchmarks through btb_set_option
+int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
 template <int CG, typename OutT>
 static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
@@ -421,6 +421,29 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p));
+    return BTB_OK;
+}
+
+// how many CTA pairs of the CG = 2 kernel the device can keep resident at once
+int umma_max_active_clusters(int cg, int *out) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(cg == 2 ? 148 : 148);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = cg == 2 ? UmmaCfg<2>::kSmemBytes : UmmaCfg<1>::kSmemBytes;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cg == 2) {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_kernel<2, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<2>::kSmemBytes));
+        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_kernel<2, uint16_t>, &cfg));
+    } else {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_kernel<1, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
+        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_kernel<1, uint16_t>, &cfg));
+    }
     return BTB_OK;
 }
 

@@ -1,0 +1,317 @@
+// Levels 1 and 2 of the extraction stage: btb_snp_sites (file -> file) and btb_extract_host
+// (host rows -> keep mask + SNP rows).  Host code only stages bytes and frames records; every
+// per-base decision is taken by the kernels in extract.cu.
+//
+// Reference call site: btbphylo/phylogeny.py:133  `snp-sites <multi_fasta> -c -o <snps.fas>`.
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "host_io.h"
+
+namespace btb {
+int require_device(int device);
+}
+using namespace btb;
+
+namespace {
+
+struct DeviceBuf {
+    void *p = nullptr;
+    ~DeviceBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        BTB_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        return BTB_OK;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+struct PinnedBuf {
+    void *p = nullptr;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    int alloc(size_t bytes) {
+        BTB_CUDA(cudaMallocHost(&p, std::max<size_t>(bytes, 16)));
+        return BTB_OK;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+    int create() { BTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return BTB_OK; }
+};
+
+void parallel_for(int64_t n, int threads, const std::function<void(int64_t, int64_t)> &fn) {
+    threads = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), n)));
+    if (threads == 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    const int64_t span = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        const int64_t lo = t * span, hi = std::min(n, lo + span);
+        if (lo < hi) pool.emplace_back(fn, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+}
+
+// After all samples are packed: reduce, select, gather.  Leaves L in *L_out, the kept-column
+// indices in d_idx, the keep bitmask in d_keep.
+int reduce_and_select(const uint32_t *d_planes, int64_t n, int64_t G, int pure_mode, uint32_t *d_state,
+                      uint32_t *d_keep, uint32_t *d_idx, uint32_t *d_count, int64_t *L_out, cudaStream_t st) {
+    BTB_TRY(btb_column_mask(d_planes, n, n, G, d_state, 0, st));
+    BTB_TRY(btb_select_columns(d_state, G, pure_mode, d_keep, d_idx, d_count, st));
+    uint32_t L = 0;
+    BTB_CUDA(cudaMemcpyAsync(&L, d_count, 4, cudaMemcpyDeviceToHost, st));
+    BTB_CUDA(cudaStreamSynchronize(st));
+    *L_out = L;
+    return BTB_OK;
+}
+
+}  // namespace
+
+// =============================================================================== level 2
+extern "C" int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64_t row_stride, int pure_mode,
+                                int device, uint8_t *keep, int64_t *n_snps, uint8_t *snps_out, int64_t snps_ld) {
+    if (!seqs || n <= 0 || G <= 0 || row_stride < G || !n_snps) return fail(BTB_EINVAL, "btb_extract_host: bad argument");
+    if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
+    BTB_TRY(require_device(device));
+    Stream st;
+    BTB_TRY(st.create());
+    const int64_t words = btb_plane_words(G);
+    DeviceBuf planes, state, keepw, idx, count, text, off, lw, el, flags, snps;
+    BTB_TRY(planes.alloc(size_t(3 * n * words * 4)));
+    BTB_TRY(state.alloc(size_t(5 * words * 4)));
+    BTB_TRY(keepw.alloc(size_t(words * 4)));
+    BTB_TRY(idx.alloc(size_t(words * 32 * 4)));
+    BTB_TRY(count.alloc(16));
+    // dense rows = unwrapped records; stage them in chunks of <= 256 MB
+    const int64_t d_stride = (G + 15) / 16 * 16;
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(256) << 20) / d_stride));
+    BTB_TRY(text.alloc(size_t(chunk_rows * d_stride + 16)));
+    BTB_TRY(off.alloc(size_t(chunk_rows * 8)));
+    BTB_TRY(lw.alloc(size_t(chunk_rows * 4)));
+    BTB_TRY(el.alloc(size_t(chunk_rows * 4)));
+    BTB_TRY(flags.alloc(size_t(n * 4)));
+    BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(n * 4), st.s));
+    BTB_CUDA(cudaMemsetAsync(lw.p, 0, size_t(chunk_rows * 4), st.s));
+    BTB_CUDA(cudaMemsetAsync(el.p, 0, size_t(chunk_rows * 4), st.s));
+    std::vector<int64_t> h_off(static_cast<size_t>(chunk_rows));
+    for (int64_t r = 0; r < chunk_rows; ++r) h_off[size_t(r)] = r * d_stride;
+    BTB_CUDA(cudaMemcpyAsync(off.p, h_off.data(), size_t(chunk_rows * 8), cudaMemcpyHostToDevice, st.s));
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const int64_t rows = std::min(chunk_rows, n - r0);
+        BTB_CUDA(cudaMemcpy2DAsync(text.p, size_t(d_stride), seqs + r0 * row_stride, size_t(row_stride), size_t(G),
+                                   size_t(rows), cudaMemcpyHostToDevice, st.s));
+        BTB_TRY(btb_pack_planes(text.as<uint8_t>(), rows * d_stride, off.as<int64_t>(), lw.as<int32_t>(),
+                                el.as<int32_t>(), rows, r0, n, G, planes.as<uint32_t>(), flags.as<int32_t>() + r0, st.s));
+    }
+    int64_t L = 0;
+    BTB_TRY(reduce_and_select(planes.as<uint32_t>(), n, G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(),
+                              idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
+    *n_snps = L;
+    if (keep) {
+        std::vector<uint32_t> hk(static_cast<size_t>(words));
+        BTB_CUDA(cudaMemcpy(hk.data(), keepw.p, size_t(words * 4), cudaMemcpyDeviceToHost));
+        for (int64_t c = 0; c < G; ++c) keep[c] = uint8_t((hk[size_t(c >> 5)] >> (c & 31)) & 1u);
+    }
+    if (snps_out && L > 0) {
+        if (snps_ld < L) return fail(BTB_EINVAL, "btb_extract_host: snps_ld < number of SNPs (%lld)", (long long)L);
+        const int64_t ld = (L + 15) / 16 * 16;
+        BTB_TRY(snps.alloc(size_t(n * ld)));
+        BTB_TRY(btb_compact_columns(planes.as<uint32_t>(), 0, n, n, G, idx.as<uint32_t>(), L, snps.as<uint8_t>(), ld, st.s));
+        BTB_CUDA(cudaMemcpy2DAsync(snps_out, size_t(snps_ld), snps.p, size_t(ld), size_t(L), size_t(n),
+                                   cudaMemcpyDeviceToHost, st.s));
+        BTB_CUDA(cudaStreamSynchronize(st.s));
+    }
+    return BTB_OK;
+}
+
+// =============================================================================== level 1
+extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode, int n_gpus,
+                             int host_threads, int64_t *n_samples, int64_t *genome_len, int64_t *n_snps) {
+    if (!in_fasta || !out_fasta) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
+    if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
+    (void)n_gpus;
+    const int threads = std::max(1, host_threads);
+    BTB_TRY(require_device(0));
+    FileBytes fb;
+    BTB_TRY(load_file(in_fasta, fb));
+    std::vector<FastaRecord> recs;
+    BTB_TRY(index_fasta(fb, recs, threads));
+    const int64_t n = int64_t(recs.size());
+    if (n == 0) {
+        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
+        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
+    }
+    // Records the GPU cannot address with (line width, terminator length) go through the exact walk.
+    auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 8); };
+    for (auto &r : recs)
+        if (needs_walk(r)) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
+    const int64_t G = recs[0].seq_len;
+    auto unequal = [&](const FastaRecord &r) {
+        fprintf(stderr, "Alignment %s contains sequences of unequal length. Expected length is %i but got %i in sequence %s\n\n",
+                in_fasta, int(G), int(r.seq_len), r.name.c_str());
+        return fail(BTB_EFORMAT, "Alignment %s contains sequences of unequal length. Expected length is %i but got %i in sequence %s",
+                    in_fasta, int(G), int(r.seq_len), r.name.c_str());
+    };
+    for (auto &r : recs)
+        if (r.seq_len != G) return unequal(r);
+    if (n_samples) *n_samples = n;
+    if (genome_len) *genome_len = G;
+    if (G == 0) {
+        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
+        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
+    }
+
+    Stream st, st2;
+    BTB_TRY(st.create());
+    BTB_TRY(st2.create());
+    const int64_t words = btb_plane_words(G);
+    DeviceBuf planes, state, keepw, idx, count, flags, d_off, d_lw, d_el, d_text[2], snps;
+    BTB_TRY(planes.alloc(size_t(3 * n * words * 4)));
+    BTB_TRY(state.alloc(size_t(5 * words * 4)));
+    BTB_TRY(keepw.alloc(size_t(words * 4)));
+    BTB_TRY(idx.alloc(size_t(words * 32 * 4)));
+    BTB_TRY(count.alloc(16));
+    BTB_TRY(flags.alloc(size_t(n * 4)));
+    BTB_TRY(d_off.alloc(size_t(n * 8)));
+    BTB_TRY(d_lw.alloc(size_t(n * 4)));
+    BTB_TRY(d_el.alloc(size_t(n * 4)));
+    BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(n * 4), st.s));
+
+    // ---- chunks of consecutive records, each staged as one byte range of the file ------------
+    size_t max_rec = 0;
+    for (auto &r : recs) max_rec = std::max(max_rec, r.raw_len + 64);
+    const size_t chunk_cap = std::max<size_t>(size_t(256) << 20, max_rec + (size_t(G) + 64));
+    PinnedBuf h_text[2];
+    BTB_TRY(h_text[0].alloc(chunk_cap + 64));
+    BTB_TRY(h_text[1].alloc(chunk_cap + 64));
+    BTB_TRY(d_text[0].alloc(chunk_cap + 64));
+    BTB_TRY(d_text[1].alloc(chunk_cap + 64));
+    std::vector<int64_t> h_off(static_cast<size_t>(n));
+    std::vector<int32_t> h_lw(static_cast<size_t>(n)), h_el(static_cast<size_t>(n));
+    cudaEvent_t done[2];
+    BTB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    BTB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    bool used[2] = {false, false};
+
+    // stage records [i0, i1) into buffer b; `force_walk` re-stages with the exact walk (unwrapped)
+    auto run_chunk = [&](int b, int64_t i0, int64_t i1, bool force_walk) -> int {
+        if (used[b]) BTB_CUDA(cudaEventSynchronize(done[b]));
+        uint8_t *dst = h_text[b].as<uint8_t>();
+        // layout pass (serial, cheap): where each record lands in the staging buffer
+        size_t pos = 0;
+        std::vector<size_t> at(static_cast<size_t>(i1 - i0));
+        for (int64_t i = i0; i < i1; ++i) {
+            const FastaRecord &r = recs[size_t(i)];
+            const bool walk = force_walk || !r.regular;
+            at[size_t(i - i0)] = pos;
+            h_off[size_t(i)] = int64_t(pos);
+            h_lw[size_t(i)] = walk ? 0 : r.line_w;
+            h_el[size_t(i)] = walk ? 0 : r.eol;
+            pos += walk ? size_t(G) : r.raw_len;
+            pos = (pos + 15) & ~size_t(15);
+        }
+        const size_t total = pos;
+        parallel_for(i1 - i0, threads, [&](int64_t lo, int64_t hi) {
+            for (int64_t k = lo; k < hi; ++k) {
+                const FastaRecord &r = recs[size_t(i0 + k)];
+                if (force_walk || !r.regular) walk_record(fb, r, dst + at[size_t(k)]);
+                else memcpy(dst + at[size_t(k)], fb.data + r.seq_off, r.raw_len);
+            }
+        });
+        BTB_CUDA(cudaMemcpyAsync(d_text[b].p, dst, total + 16, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + i0, h_off.data() + i0, size_t(i1 - i0) * 8, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_lw.as<int32_t>() + i0, h_lw.data() + i0, size_t(i1 - i0) * 4, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_el.as<int32_t>() + i0, h_el.data() + i0, size_t(i1 - i0) * 4, cudaMemcpyHostToDevice, st.s));
+        BTB_TRY(btb_pack_planes(d_text[b].as<uint8_t>(), int64_t(total), d_off.as<int64_t>() + i0, d_lw.as<int32_t>() + i0,
+                                d_el.as<int32_t>() + i0, i1 - i0, i0, n, G, planes.as<uint32_t>(),
+                                flags.as<int32_t>() + i0, st.s));
+        BTB_CUDA(cudaEventRecord(done[b], st.s));
+        used[b] = true;
+        return BTB_OK;
+    };
+    auto chunk_end = [&](int64_t i0, bool force_walk) {
+        size_t bytes = 0;
+        int64_t i = i0;
+        while (i < n) {
+            const FastaRecord &r = recs[size_t(i)];
+            const size_t need = ((force_walk || !r.regular) ? size_t(G) : r.raw_len) + 16;
+            if (i > i0 && bytes + need > chunk_cap) break;
+            bytes += need;
+            ++i;
+        }
+        return i;
+    };
+    int b = 0;
+    for (int64_t i0 = 0; i0 < n;) {
+        const int64_t i1 = chunk_end(i0, false);
+        int rc = run_chunk(b, i0, i1, false);
+        if (rc != BTB_OK) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return rc; }
+        b ^= 1;
+        i0 = i1;
+    }
+    // records whose terminators were not where their first line promised: exact walk, pack again
+    std::vector<int32_t> h_flags(static_cast<size_t>(n));
+    BTB_CUDA(cudaMemcpyAsync(h_flags.data(), flags.p, size_t(n * 4), cudaMemcpyDeviceToHost, st.s));
+    BTB_CUDA(cudaStreamSynchronize(st.s));
+    for (int64_t i = 0; i < n; ++i) {
+        if (!h_flags[size_t(i)]) continue;
+        FastaRecord &r = recs[size_t(i)];
+        r.seq_len = walk_record(fb, r, nullptr);
+        r.regular = false;
+        if (r.seq_len != G) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return unequal(r); }
+        int rc = run_chunk(b, i, i + 1, true);
+        if (rc != BTB_OK) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return rc; }
+        b ^= 1;
+    }
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+
+    int64_t L = 0;
+    BTB_TRY(reduce_and_select(planes.as<uint32_t>(), n, G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(),
+                              idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
+    if (n_snps) *n_snps = L;
+    if (L == 0) {
+        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
+        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
+    }
+    // ---- gather + write: >name\n + L bases + \n per sample, one line per sequence -------------
+    const int64_t ld = (L + 15) / 16 * 16;
+    const int64_t block = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(128) << 20) / ld));
+    BTB_TRY(snps.alloc(size_t(block * ld)));
+    PinnedBuf h_snps;
+    BTB_TRY(h_snps.alloc(size_t(block * ld)));
+    std::string tmp_path = std::string(out_fasta) + ".tmp";
+    FILE *fo = fopen(tmp_path.c_str(), "wb");
+    if (!fo) return fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str());
+    setvbuf(fo, nullptr, _IOFBF, 1 << 22);
+    std::vector<char> text;
+    int rc = BTB_OK;
+    for (int64_t r0 = 0; r0 < n && rc == BTB_OK; r0 += block) {
+        const int64_t rows = std::min(block, n - r0);
+        rc = btb_compact_columns(planes.as<uint32_t>(), r0, rows, n, G, idx.as<uint32_t>(), L, snps.as<uint8_t>(), ld, st.s);
+        if (rc != BTB_OK) break;
+        if (cudaMemcpyAsync(h_snps.p, snps.p, size_t(rows * ld), cudaMemcpyDeviceToHost, st.s) != cudaSuccess ||
+            cudaStreamSynchronize(st.s) != cudaSuccess) { rc = fail(BTB_ECUDA, "copying SNP rows back failed"); break; }
+        size_t need = 0;
+        for (int64_t r = 0; r < rows; ++r) need += recs[size_t(r0 + r)].name.size() + size_t(L) + 3;
+        text.resize(need);
+        char *p = text.data();
+        for (int64_t r = 0; r < rows; ++r) {
+            const std::string &nm = recs[size_t(r0 + r)].name;
+            *p++ = '>';
+            memcpy(p, nm.data(), nm.size()); p += nm.size();
+            *p++ = '\n';
+            memcpy(p, h_snps.as<char>() + r * ld, size_t(L)); p += L;
+            *p++ = '\n';
+        }
+        if (fwrite(text.data(), 1, size_t(p - text.data()), fo) != size_t(p - text.data())) rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str());
+    }
+    if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
+    if (rc == BTB_OK && rename(tmp_path.c_str(), out_fasta) != 0) rc = fail(BTB_EIO, "cannot rename to '%s'", out_fasta);
+    if (rc != BTB_OK) remove(tmp_path.c_str());
+    return rc;
+}

@@ -1,0 +1,64 @@
+"""Host-side logic of the multi-GPU distance stage: which upper-triangle
+tiles a rank owns and how the per-rank tile-packed results become one symmetric matrix for the
+CSV writer.  There is no collective on the compute path: operands are replicated, tiles are
+independent, results are gathered on the host.  Pure numpy so that it is testable with gloo on
+CPU; the tiles themselves come from btb_distance_tiles (out_mode 1) on each rank's GPU."""
+import numpy as np
+
+TILE = 256
+BAND = 8          # must match kBand in csrc/common.cuh
+
+
+def tiles_per_dim(n):
+    return (n + TILE - 1) // TILE
+
+
+def tile_count(n):
+    t = tiles_per_dim(n)
+    return t * (t + 1) // 2
+
+
+def tile_coords(n, idx):
+    """Same band order as csrc/common.cuh tile_coords (checked against the library in tests)."""
+    T = tiles_per_dim(n)
+    c0 = 0
+    while c0 < T:
+        c1 = min(c0 + BAND, T)
+        w = c1 - c0
+        rect = c0 * w
+        tri = w * (w + 1) // 2
+        if idx < rect:
+            return idx // w, c0 + idx % w
+        idx -= rect
+        if idx < tri:
+            for r in range(w):
+                if idx < w - r:
+                    return c0 + r, c0 + r + idx
+                idx -= w - r
+        idx -= tri
+        c0 = c1
+    raise IndexError("tile index out of range")
+
+
+def tile_share(n, rank, world):
+    """Tiles [lo, hi) owned by `rank`: equal counts (+-1), contiguous in band order."""
+    t = tile_count(n)
+    return t * rank // world, t * (rank + 1) // world
+
+
+def assemble(n, shares, packed, out=None):
+    """shares: list of (lo, hi); packed: list of arrays [(hi-lo), TILE, TILE] in the same order.
+    Returns the full symmetric n x n matrix (both triangles)."""
+    dtype = packed[0].dtype
+    if out is None:
+        out = np.zeros((n, n), dtype=dtype)
+    for (lo, hi), tiles in zip(shares, packed):
+        for t in range(lo, hi):
+            I, J = tile_coords(n, t)
+            r0, c0 = I * TILE, J * TILE
+            r1, c1 = min(n, r0 + TILE), min(n, c0 + TILE)
+            blk = tiles[t - lo][: r1 - r0, : c1 - c0]
+            out[r0:r1, c0:c1] = blk
+            if I != J:
+                out[c0:c1, r0:r1] = blk.T
+    return out

@@ -53,6 +53,8 @@ const char *btb_version(void);
 int         btb_device_count(int *count);                 /* number of usable sm_100 devices */
 /* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (default 2: CTA pairs, 256-row UMMA) */
 int         btb_set_option(const char *key, int value);
+/* introspection: "umma_cta_group", "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
+int         btb_query(const char *key, int64_t *value);
 
 /* =====================================================================================
  * Level 1 -- file to file.  Replaces the two command lines.
@@ -88,6 +90,9 @@ int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t ro
                          int rank, int world,
                          void *out, int out_elem_bytes, int64_t out_ld);
 
+/* btb_dist_matrix_host keeps its device buffers between calls; this frees them. */
+int btb_release_workspace(void);
+
 /* Variable columns of an n x G alignment held as dense rows: keep[k] = 1 where snp-sites keeps
  * column k; returns their count in *n_snps.  snps_out (may be NULL) receives n rows of *n_snps
  * upper-cased bytes, row stride snps_ld (>= number kept; call once with NULL to size it). */
@@ -104,15 +109,15 @@ int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64_t row_stri
 /* words of 32 columns per sample and plane, padded for 128-bit access */
 int64_t btb_plane_words(int64_t G);
 
-/* k1: text -> bit-planes.  Sample i's bases start at d_text + rec_off[i]; its lines are
- * line_w[i] bases followed by eol[i] line-terminator bytes (line_w = 0: unwrapped).  Writes three
+/* k1: text -> bit-planes.  d_text holds text_bytes bytes of FASTA text (allocation padded to a
+ * 16-byte boundary).  Sample i's bases start at d_text + rec_off[i]; its lines are line_w[i] bases
+ * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 8).  Writes three
  * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
  * sample i at d_planes + ((p * n_total + first + i) * words).  d_flags[i] is OR-ed with 1 when a
- * line terminator is not where the layout says (caller then re-stages that record unwrapped).
- * unknown_mode = 1 additionally keeps a 4th plane: byte is one of N n - ? (snp-sites default mode). */
-int btb_pack_planes(const uint8_t *d_text, const int64_t *d_rec_off, const int32_t *d_line_w,
-                    const int32_t *d_eol, int64_t n_chunk, int64_t first, int64_t n_total,
-                    int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream);
+ * line terminator is not where the layout says (the caller then re-stages that record unwrapped). */
+int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
+                    const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
+                    int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream);
 
 /* k2: per-column reduction over samples [0, n) -> 5 words per 32 columns in d_colstate:
  * seenA, seenC, seenG, seenT, anyInvalid.  accumulate != 0 ORs into existing state. */

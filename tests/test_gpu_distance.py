@@ -1,0 +1,125 @@
+"""GPU (-m gpu): the distance stage (k4) through the C-ABI against the CPU oracle, bit-exact.
+Both engines (POPC bit-planes, tcgen05 kind::i8 GEMM with CTA pairs and single CTAs), default and
+-a / -k modes, ragged sizes, tile-packed output, rank shares, uint16 / uint32 output."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from btb_phylo_b200 import multirank, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+ENGINES = [("popc", 0, 0), ("umma_pair", 1, 2), ("umma_single", 1, 1)]
+
+
+def to_device(seqs):
+    n, L = seqs.shape
+    stride = max(16, (L + 15) // 16 * 16)
+    host = np.full((n, stride), ord("."), dtype=np.uint8)
+    host[:, :L] = seqs
+    return torch.from_numpy(host).cuda()
+
+
+def gpu_matrix(capi, seqs, engine, cg, allchars=False, keepcase=False, out_dtype=None):
+    from btb_phylo_b200 import device
+    if cg:
+        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+    plan = device.DistancePlan(to_device(seqs), length=seqs.shape[1], allchars=allchars, keepcase=keepcase,
+                               engine=engine, out_dtype=out_dtype)
+    plan.encode()
+    out = plan.alloc_matrix()
+    plan.compute(out)
+    torch.cuda.synchronize()
+    return plan, out[:, : seqs.shape[0]].cpu().numpy().astype(np.int64)
+
+
+@pytest.mark.parametrize("name,engine,cg", ENGINES)
+@pytest.mark.parametrize("n,L", [(1, 1), (2, 7), (4, 831), (255, 33), (256, 128), (257, 129), (700, 1000), (1300, 4097)])
+def test_default_mode_bit_exact(capi, oracle, name, engine, cg, n, L):
+    seqs = synth.snp_alignment(n, L, seed=n + L, heavy_n=0.15, lower=0.02)
+    _, got = gpu_matrix(capi, seqs, engine, cg)
+    want = oracle.snp_dists_rows(seqs, threads=8).astype(np.int64)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("name,engine,cg", ENGINES)
+@pytest.mark.parametrize("allchars,keepcase", [(True, False), (False, True), (True, True)])
+def test_allchars_and_keepcase_modes(capi, oracle, name, engine, cg, allchars, keepcase):
+    seqs = synth.snp_alignment(530, 2049, seed=21, heavy_n=0.25, iupac=0.01, lower=0.03)
+    seqs[5, 100:140] = ord(".")           # a literal '.' never counts, even with -a
+    plan, got = gpu_matrix(capi, seqs, engine, cg, allchars=allchars, keepcase=keepcase)
+    want = oracle.snp_dists_rows(seqs, allchars=allchars, keepcase=keepcase, threads=8).astype(np.int64)
+    assert (got == want).all()
+    if allchars:
+        assert plan.sigma > 4
+
+
+def test_golden_c1_matrix(capi, oracle):
+    from tests.conftest import golden
+    lines = golden("c1_snps.fas").split(b"\n")
+    seqs = np.stack([np.frombuffer(lines[2 * i + 1], dtype=np.uint8) for i in range(4)])
+    want = np.array([[int(v) for v in row.split(b",")[1:]] for row in golden("c1_snps.csv").split(b"\n")[1:5]])
+    for _, engine, cg in ENGINES:
+        _, got = gpu_matrix(capi, seqs, engine, cg)
+        assert (got == want).all()
+
+
+@pytest.mark.parametrize("name,engine,cg", ENGINES)
+def test_tile_packed_rank_shares_assemble(capi, oracle, name, engine, cg):
+    """world = 3: each rank computes its contiguous tile range into tile-packed storage; the host
+    assembly equals the single-GPU matrix and the oracle (multi-GPU = same bytes as 1 GPU)."""
+    from btb_phylo_b200 import device
+    n, L = 1100, 700
+    seqs = synth.snp_alignment(n, L, seed=8, heavy_n=0.1)
+    if cg:
+        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+    plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
+    plan.encode()
+    shares, packed = [], []
+    for r in range(3):
+        lo, hi = multirank.tile_share(n, r, 3)
+        tiles = plan.alloc_tiles(lo, hi)
+        plan.compute(tiles, lo, hi, packed=True)
+        torch.cuda.synchronize()
+        shares.append((lo, hi))
+        packed.append(tiles.cpu().numpy().astype(np.uint32))
+    mat = multirank.assemble(n, shares, packed)
+    assert (mat == oracle.snp_dists_rows(seqs, threads=8)).all()
+
+
+def test_uint32_output_and_long_rows(capi, oracle):
+    seqs = synth.snp_alignment(300, 70001, seed=2, heavy_n=0.05)
+    for _, engine, cg in ENGINES:
+        plan, got = gpu_matrix(capi, seqs, engine, cg)
+        assert plan.out_dtype == torch.uint32
+        assert (got == oracle.snp_dists_rows(seqs, threads=8)).all()
+
+
+def test_level2_host_call(capi, oracle):
+    from btb_phylo_b200 import device
+    seqs = synth.snp_alignment(777, 831, seed=5, heavy_n=0.2, lower=0.01)
+    want = oracle.snp_dists_rows(seqs, threads=8)
+    for engine in (capi.ENGINE_AUTO, capi.ENGINE_POPC, capi.ENGINE_UMMA):
+        assert (device.distance_matrix_host(seqs, engine=engine) == want).all()
+        assert (device.distance_matrix_host(seqs, engine=engine, dtype=np.uint16) == want).all()
+    # two ranks fill disjoint tile sets of the same host matrix
+    out = np.zeros((777, 777), dtype=np.uint32)
+    device.distance_matrix_host(seqs, rank=0, world=2, out=out)
+    assert not (out == want).all()
+    device.distance_matrix_host(seqs, rank=1, world=2, out=out)
+    assert (out == want).all()
+
+
+def test_properties_at_scale(capi, oracle):
+    """8192 x 30000 (BASELINE config 4 shape, cut to 8192 rows): symmetry, zero diagonal, engines
+    agree everywhere, sampled rows equal the oracle."""
+    n, L = 8192, 30000
+    seqs = synth.snp_alignment(n, L, seed=4)
+    _, a = gpu_matrix(capi, seqs, 1, 2)
+    _, b = gpu_matrix(capi, seqs, 0, 0)
+    assert (a == a.T).all() and (np.diag(a) == 0).all() and (a == b).all()
+    for r in (0, 1, 4097, 8191):
+        assert (a[r] == oracle.snp_dists_rows(seqs, threads=8, row0=r, row1=r + 1)[0]).all()
+    assert a.max() < L

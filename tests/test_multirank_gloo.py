@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the N>1 path of the distance stage is tile sharding with no
+data-path collective -- each rank produces its tile-packed share, the host gathers.  Here the
+per-rank tiles come from the oracle (no GPU in this container); the sharding, the gather and the
+max-over-ranks timing reduction that bench.py uses are the code under test."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, L, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from btb_phylo_b200 import multirank, synth
+    from oracle import oracle
+    seqs = synth.snp_alignment(n, L, seed=11, heavy_n=0.1)          # operands replicated on every rank
+    lo, hi = multirank.tile_share(n, rank, world)
+    full = oracle.snp_dists_rows(seqs, threads=2)
+    tiles = np.zeros((hi - lo, 256, 256), dtype=np.uint32)
+    for t in range(lo, hi):                                          # stands in for btb_distance_tiles(out_mode=1)
+        I, J = multirank.tile_coords(n, t)
+        blk = full[I * 256:(I + 1) * 256, J * 256:(J + 1) * 256]
+        tiles[t - lo, : blk.shape[0], : blk.shape[1]] = blk
+    # host gather (what the CSV writer consumes) + bench-style max-over-ranks time
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, tiles))
+    ms = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    pairs = torch.tensor([float(sum(1 for t in range(lo, hi)))], dtype=torch.float64)
+    dist.all_reduce(pairs, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        shares = [(g[0], g[1]) for g in gathered]
+        mat = multirank.assemble(n, shares, [g[2] for g in gathered])
+        ret["equal"] = bool((mat == full).all())
+        ret["max_ms"] = float(ms.item())
+        ret["tiles"] = float(pairs.item())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_sharding_assembles_full_matrix():
+    n, L, world = 700, 150, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, L, ret), nprocs=world, join=True)
+    from btb_phylo_b200 import multirank
+    assert ret["equal"] and ret["max_ms"] == 11.0 and ret["tiles"] == multirank.tile_count(n)
