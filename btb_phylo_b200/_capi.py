@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "libbtbphylo.so")
 
 ENGINE_AUTO, ENGINE_POPC, ENGINE_UMMA = -1, 0, 1
 TILE = 256
+SIGMA_DENSE4 = -4
 OK, EINVAL, EIO, EFORMAT, ENOSNPS, ECUDA, ENODEVICE, ENOMEM = range(8)
 
 c_i64 = ctypes.c_int64

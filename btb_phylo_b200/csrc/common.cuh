@@ -62,7 +62,9 @@ __host__ __device__ inline void tile_coords(int64_t T, int64_t idx, int &I, int 
 }
 
 // ---- operand layouts of the two distance engines (see dist_encode.cu) -----------------------
+__host__ __device__ inline bool sigma_dense(int sigma) { return sigma == BTB_SIGMA_DENSE4; }
 __host__ __device__ inline int popc_code_planes(int sigma) {
+    if (sigma_dense(sigma)) return 2;
     int q = 1;
     while ((1 << q) < sigma) ++q;
     return q;
@@ -73,7 +75,7 @@ __host__ __device__ inline int64_t popc_words(int64_t len) {      // words per r
 }
 __host__ __device__ inline int sigma4_of(int sigma) { return sigma <= 4 ? 4 : (sigma + 3) / 4 * 4; }
 __host__ __device__ inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple of 128
-    int64_t k = len * sigma4_of(sigma);
+    int64_t k = len * (sigma_dense(sigma) ? 3 : sigma4_of(sigma));
     return (k + 127) / 128 * 128;
 }
 

@@ -12,6 +12,11 @@
 //                 A[i][site*sigma4 + b] = [valid and code == b]            (one-hot)
 //                 B[i][site*sigma4 + b] = [valid and code != b, b < sigma] (masked complement)
 //                 so that  sum_b A_i * B_j = [valid_i][valid_j][code_i != code_j]  = snp-dists' test.
+//   dense (BTB_SIGMA_DENSE4: <= 4 symbols, nothing ignored -- every snp-sites -c output):
+//                 UMMA: one operand, 3 bytes per site, the +-1 vertices of a regular simplex
+//                 (1,1,1) (1,-1,-1) (-1,1,-1) (-1,-1,1): dot = 3 on a match, -1 on a mismatch, so
+//                 d = (3 len - dot) / 4 with 25 % fewer MMAs and half the operand bytes;
+//                 POPC: the validity plane is dropped.
 //
 // HBM-bound streaming kernels: algorithmic bytes = n*len read + operand bytes written.
 #include <algorithm>
@@ -52,7 +57,7 @@ __global__ void presence_kernel(const uint8_t *__restrict__ seqs, int64_t n, int
 template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 encode_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
-                     const uint8_t *__restrict__ table_g, int q_planes, int64_t words,
+                     const uint8_t *__restrict__ table_g, int q_planes, int has_valid, int64_t words,
                      uint32_t *__restrict__ planes) {
     __shared__ uint8_t table[256];
     table[threadIdx.x] = table_g[threadIdx.x];
@@ -68,7 +73,7 @@ encode_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, i
 #pragma unroll 1
     for (int it = 0; it < 8; ++it) {
         const int64_t site = (w0 + 4 * it) * 32 + 4 * lane;
-        uint32_t raw = 0x2e2e2e2eu;                    // '.' never counts under any table
+        uint32_t raw = 0x2e2e2e2eu;                    // '.' never counts under any table (dense: code 0 everywhere)
         if (ALIGNED && site + 3 < len) {
             raw = *reinterpret_cast<const uint32_t *>(p + site);
         } else {
@@ -98,7 +103,7 @@ encode_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, i
 #pragma unroll
         for (int pl = 0; pl < 8; ++pl)
             if (pl < q_planes) planes[pl * plane_stride + row * words + w] = keep[pl];
-        planes[q_planes * plane_stride + row * words + w] = keep[8];
+        if (has_valid) planes[q_planes * plane_stride + row * words + w] = keep[8];
     }
 }
 
@@ -176,6 +181,45 @@ encode_onehot_generic_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_
     }
 }
 
+// dense simplex operand: one thread per 4 sites -> 12 bytes
+__global__ void __launch_bounds__(256)
+encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                      const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int64_t groups = kbytes / 12 + (kbytes % 12 != 0);
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+        const uint8_t *p = seqs + row * row_stride;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(A + row * kbytes);
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t site = g * 4;
+            uint32_t raw = 0x2e2e2e2eu;
+            if (aligned && site + 3 < len) {
+                raw = *reinterpret_cast<const uint32_t *>(p + site);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (site + b < len) raw = (raw & ~(0xffu << (8 * b))) | (uint32_t(p[site + b]) << (8 * b));
+            }
+            uint32_t t[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t code = table[(raw >> (8 * b)) & 0xff];
+                // bytes (x, y, z) of the simplex vertex, little endian; sites beyond len -> 0
+                t[b] = code == 0 ? 0x010101u : code == 1 ? 0xFFFF01u : code == 2 ? 0xFF01FFu : code == 3 ? 0x01FFFFu : 0u;
+            }
+            const uint32_t w0 = t[0] | (t[1] << 24), w1 = (t[1] >> 8) | (t[2] << 16), w2 = (t[2] >> 16) | (t[3] << 8);
+            const int64_t wi = g * 3;
+            const int64_t total = kbytes / 4;
+            if (wi < total) dst[wi] = w0;
+            if (wi + 1 < total) dst[wi + 1] = w1;
+            if (wi + 2 < total) dst[wi + 2] = w2;
+        }
+    }
+}
+
 }  // namespace btb
 
 using namespace btb;
@@ -188,18 +232,11 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     for (int b = 0; b < 256; ++b) table[b] = 0xff;
     auto up = [&](int b) { return (!keepcase && b >= 'a' && b <= 'z') ? b - 32 : b; };
-    if (!allchars) {
-        const char *acgt = "ACGT";
-        for (int b = 0; b < 256; ++b)
-            for (int c = 0; c < 4; ++c)
-                if (up(b) == acgt[c]) table[b] = uint8_t(c);
-        *sigma = 4;
-        return BTB_OK;
-    }
-    if (!d_seqs && n * len > 0) return fail(BTB_EINVAL, "btb_dist_alphabet: allchars needs the alignment");
     uint32_t *d_present = nullptr;
     uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (n * len > 0) {
+    const bool scan = d_seqs && n * len > 0;
+    if (allchars && !d_seqs && n * len > 0) return fail(BTB_EINVAL, "btb_dist_alphabet: allchars needs the alignment");
+    if (scan) {
         BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_present), sizeof(present), stream));
         BTB_CUDA(cudaMemsetAsync(d_present, 0, sizeof(present), stream));
         dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 2048));
@@ -209,25 +246,39 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
         BTB_CUDA(cudaStreamSynchronize(stream));
         BTB_CUDA(cudaFreeAsync(d_present, stream));
     }
-    // symbols that occur after the load rules (upper-casing), '.' excluded, in byte order
-    bool occurs[256] = {false};
-    for (int b = 0; b < 256; ++b)
-        if (present[b >> 5] >> (b & 31) & 1) occurs[up(b)] = true;
-    occurs[int('.')] = false;
-    int code_of[256], s = 0;
-    for (int b = 0; b < 256; ++b) code_of[b] = occurs[b] ? s++ : -1;
-    if (s > 254) return fail(BTB_EINVAL, "alphabet too large");
-    for (int b = 0; b < 256; ++b) {
-        int u = up(b);
-        if (u != '.' && code_of[u] >= 0) table[b] = uint8_t(code_of[u]);
+    int s = 0;
+    if (!allchars) {
+        const char *acgt = "ACGT";
+        for (int b = 0; b < 256; ++b)
+            for (int c = 0; c < 4; ++c)
+                if (up(b) == acgt[c]) table[b] = uint8_t(c);
+        s = 4;
+    } else {
+        // symbols that occur after the load rules (upper-casing), '.' excluded, in byte order
+        bool occurs[256] = {false};
+        for (int b = 0; b < 256; ++b)
+            if (present[b >> 5] >> (b & 31) & 1) occurs[up(b)] = true;
+        occurs[int('.')] = false;
+        int code_of[256];
+        for (int b = 0; b < 256; ++b) code_of[b] = occurs[b] ? s++ : -1;
+        if (s > 254) return fail(BTB_EINVAL, "alphabet too large");
+        for (int b = 0; b < 256; ++b) {
+            int u = up(b);
+            if (u != '.' && code_of[u] >= 0) table[b] = uint8_t(code_of[u]);
+        }
+        if (s == 0) s = 1;
     }
-    *sigma = s > 0 ? s : 1;
+    // dense: nothing that occurs is ignored, and at most four symbols
+    bool dense = scan && s <= 4;
+    for (int b = 0; b < 256 && dense; ++b)
+        if ((present[b >> 5] >> (b & 31) & 1) && table[b] == 0xff) dense = false;
+    *sigma = dense ? BTB_SIGMA_DENSE4 : s;
     return BTB_OK;
 }
 
 extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma) {
-    if (engine == BTB_ENGINE_POPC) return (popc_code_planes(sigma) + 1) * n * popc_words(len) * 4;
-    if (engine == BTB_ENGINE_UMMA) return 2 * n * umma_k_bytes(len, sigma);
+    if (engine == BTB_ENGINE_POPC) return (popc_code_planes(sigma) + (sigma_dense(sigma) ? 0 : 1)) * n * popc_words(len) * 4;
+    if (engine == BTB_ENGINE_UMMA) return (sigma_dense(sigma) ? 1 : 2) * n * umma_k_bytes(len, sigma);
     return -1;
 }
 
@@ -248,16 +299,19 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         const int64_t warps = n * blocks_per_row;
         const unsigned grid = unsigned((warps + 7) / 8);
         if (aligned)
-            encode_planes_kernel<true><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q,
+            encode_planes_kernel<true><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q, sigma_dense(sigma) ? 0 : 1,
                                                                  words, static_cast<uint32_t *>(d_operands));
         else
-            encode_planes_kernel<false><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q,
+            encode_planes_kernel<false><<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, q, sigma_dense(sigma) ? 0 : 1,
                                                                   words, static_cast<uint32_t *>(d_operands));
     } else if (engine == BTB_ENGINE_UMMA) {
         const int64_t kb = umma_k_bytes(len, sigma);
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
-        if (sigma4_of(sigma) == 4) {
+        if (sigma_dense(sigma)) {
+            dim3 grid((unsigned)std::min<int64_t>((kb / 12 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            encode_simplex_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0);
+        } else if (sigma4_of(sigma) == 4) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             encode_onehot4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, B,
                                                             aligned ? 1 : 0);

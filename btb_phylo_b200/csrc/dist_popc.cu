@@ -41,16 +41,16 @@ __device__ __forceinline__ void store_tile_from_smem(const uint32_t *s_acc /*[12
     }
 }
 
-template <int Q, int kKC, typename OutT>
+template <int Q, int kKC, bool HASV, typename OutT>
 __global__ void __launch_bounds__(256)
 dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, int64_t tile_lo,
                  OutT *__restrict__ out, int64_t ld, int out_mode, int mirror) {
-    constexpr int P = Q + 1;                                // code planes + validity
+    constexpr int P = Q + (HASV ? 1 : 0);                   // code planes (+ validity unless dense)
     constexpr int kStride = kKC + 1;                        // odd: conflict-free column-row reads
     extern __shared__ uint32_t smem[];
     constexpr int kOperand = P * kPT * kStride;             // words of one operand in one stage
-    uint32_t *sA[2] = {smem, smem + 2 * kOperand};
-    uint32_t *sB[2] = {smem + kOperand, smem + 3 * kOperand};
+    auto sA = [&](int buf) { return smem + (2 * buf) * kOperand; };
+    auto sB = [&](int buf) { return smem + (2 * buf + 1) * kOperand; };
 
     const int64_t T = tiles_per_dim(n);
     const int64_t tile = tile_lo + blockIdx.x / 4;
@@ -73,8 +73,8 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
         for (int e = threadIdx.x; e < P * kPT * kKC; e += 256) {
             const int k = e & (kKC - 1), r = (e / kKC) & (kPT - 1), p = e / (kKC * kPT);
             const int64_t ra = row0 + r, rb = col0 + r;
-            uint32_t *da = &sA[buf][(p * kPT + r) * kStride + k];
-            uint32_t *db = &sB[buf][(p * kPT + r) * kStride + k];
+            uint32_t *da = &sA(buf)[(p * kPT + r) * kStride + k];
+            uint32_t *db = &sB(buf)[(p * kPT + r) * kStride + k];
             if (ra < n) {
                 const uint32_t *src = planes + p * plane_stride + ra * words + w0 + k;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(da)), "l"(src));
@@ -88,7 +88,7 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
     };
 
     const int64_t chunks = words / kKC;
-    if (row0 < n && col0 < n) {
+    if (row0 < n && col0 < n && chunks > 0) {
         stage(0, 0);
         for (int64_t ch = 0; ch < chunks; ++ch) {
             const int buf = int(ch & 1);
@@ -99,8 +99,8 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
                 asm volatile("cp.async.wait_group 0;");
             }
             __syncthreads();
-            const uint32_t *a = sA[buf] + (ty * 8) * kStride;
-            const uint32_t *b = sB[buf] + tx * kStride;
+            const uint32_t *a = sA(buf) + (ty * 8) * kStride;
+            const uint32_t *b = sB(buf) + tx * kStride;
 #pragma unroll 2
             for (int k = 0; k < kKC; ++k) {
                 uint32_t av[P][8], bv[P][8];
@@ -118,7 +118,7 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
                         uint32_t d = av[0][r] ^ bv[0][c];
 #pragma unroll
                         for (int q = 1; q < Q; ++q) d |= av[q][r] ^ bv[q][c];
-                        d &= av[Q][r] & bv[Q][c];
+                        if constexpr (HASV) d &= av[Q][r] & bv[Q][c];
                         acc[r][c] += __popc(d);
                     }
             }
@@ -136,16 +136,16 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
                                mirror && I != J);
 }
 
-template <int Q, typename OutT>
+template <int Q, bool HASV, typename OutT>
 static int launch_popc(const uint32_t *planes, int64_t n, int64_t words, int64_t tile_lo, int64_t tiles,
                        void *out, int64_t ld, int out_mode, int mirror, cudaStream_t stream) {
-    constexpr int P = Q + 1;
+    constexpr int P = Q + (HASV ? 1 : 0);
     constexpr int kKC = P <= 5 ? 16 : 8;                    // staged words per chunk: keep 4 buffers < 227 KB
     size_t smem = size_t(4) * P * kPT * (kKC + 1) * 4;
     const size_t epi = size_t(kPT) * 129 * 4;
     if (smem < epi) smem = epi;
-    BTB_CUDA(cudaFuncSetAttribute(dist_popc_kernel<Q, kKC, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dist_popc_kernel<Q, kKC, OutT><<<unsigned(tiles * 4), 256, smem, stream>>>(
+    BTB_CUDA(cudaFuncSetAttribute(dist_popc_kernel<Q, kKC, HASV, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dist_popc_kernel<Q, kKC, HASV, OutT><<<unsigned(tiles * 4), 256, smem, stream>>>(
         planes, n, words, tile_lo, static_cast<OutT *>(out), ld, out_mode, mirror);
     BTB_CUDA(cudaGetLastError());
     return BTB_OK;
@@ -162,8 +162,12 @@ int distance_tiles_popc(const void *d_operands, int64_t n, int64_t len, int sigm
 #define BTB_POPC_CASE(QQ)                                                                             \
     case QQ:                                                                                          \
         return out_elem_bytes == 2                                                                    \
-                   ? launch_popc<QQ, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream) \
-                   : launch_popc<QQ, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream);
+                   ? launch_popc<QQ, true, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream) \
+                   : launch_popc<QQ, true, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream);
+    if (sigma_dense(sigma))
+        return out_elem_bytes == 2
+                   ? launch_popc<2, false, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream)
+                   : launch_popc<2, false, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream);
     switch (q) {
         BTB_POPC_CASE(1)
         BTB_POPC_CASE(2)

@@ -3,6 +3,7 @@
 // Replaces the O(N^2 L) byte-compare loop of snp-dists 0.8.2, reached in
 // the reference through btbphylo/phylogeny.py:149.  With the operands of dist_encode.cu,
 //     d(i,j) = sum_k A[i][k] * B[j][k]          (A one-hot, B masked complement, values 0/1)
+// or, for dense alignments (one +-1 simplex operand X),  d(i,j) = (3 len - sum_k X[i][k] X[j][k]) / 4,
 // which tcgen05.mma kind::i8 evaluates exactly with int32 accumulators in tensor memory.
 //
 // Kernel shape (sm_100a only):
@@ -18,6 +19,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -172,6 +175,9 @@ struct UmmaParams {
     int64_t ld;
     int out_mode;         // 0 = n x n matrix, 1 = tile-packed
     int mirror;
+    int dense;            // simplex operands: distance = (bias - dot) >> 2
+    int32_t bias;         // 3 * len
+    unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
 template <int CG>
@@ -210,6 +216,13 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int64_t n_workers = CG == 2 ? gridDim.x / 2 : gridDim.x;
     const int64_t T = tiles_per_dim(p.n);
 
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t; uint32_t sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.dbg[blockIdx.x * 4 + 0] = t;
+        p.dbg[blockIdx.x * 4 + 2] = sm;
+    }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -313,6 +326,10 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int c0 = 0; c0 < kAccCols; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols + c0), v);
+                if (p.dense) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> 2;
+                }
                 const int64_t col = n0 + c0;
                 if (p.out_mode == 1) {
                     OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
@@ -361,6 +378,12 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_before();
     if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[blockIdx.x * 4 + 1] = t;
+        p.dbg[blockIdx.x * 4 + 3] = (unsigned long long)((p.units - worker + n_workers - 1) / n_workers);
+    }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -420,7 +443,27 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p));
+    UmmaParams q = p;
+    unsigned long long *d_dbg = nullptr;
+    const bool debug = getenv("BTB_UMMA_DEBUG") != nullptr;
+    if (debug) {
+        BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_dbg), size_t(ctas) * 32));
+        BTB_CUDA(cudaMemset(d_dbg, 0, size_t(ctas) * 32));
+        q.dbg = d_dbg;
+    }
+    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, q));
+    if (debug) {
+        BTB_CUDA(cudaStreamSynchronize(stream));
+        std::vector<unsigned long long> h(size_t(ctas) * 4);
+        BTB_CUDA(cudaMemcpy(h.data(), d_dbg, size_t(ctas) * 32, cudaMemcpyDeviceToHost));
+        cudaFree(d_dbg);
+        unsigned long long t0 = ~0ull;
+        for (int64_t c = 0; c < ctas; ++c) t0 = std::min(t0, h[size_t(c) * 4]);
+        fprintf(stderr, "[umma debug] CG=%d ctas=%lld units=%lld k_blocks=%lld\n", CG, (long long)ctas, (long long)p.units, (long long)p.k_blocks);
+        for (int64_t c = 0; c < ctas; ++c)
+            fprintf(stderr, "[umma debug] cta %3lld sm %3llu start %9.1f us end %9.1f us units %llu\n", (long long)c, h[size_t(c) * 4 + 2],
+                    (h[size_t(c) * 4] - t0) * 1e-3, (h[size_t(c) * 4 + 1] - t0) * 1e-3, h[size_t(c) * 4 + 3]);
+    }
     return BTB_OK;
 }
 
@@ -455,7 +498,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const int64_t kb = umma_k_bytes(len, sigma);
     const int cg = g_umma_cta_group == 1 ? 1 : 2;
     const uint8_t *A = static_cast<const uint8_t *>(d_operands);
-    const uint8_t *B = A + n * kb;
+    const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
     BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
@@ -469,6 +512,9 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.ld = out_ld;
     p.out_mode = out_mode;
     p.mirror = mirror;
+    p.dbg = nullptr;
+    p.dense = sigma_dense(sigma) ? 1 : 0;
+    p.bias = int32_t(3 * len);
     if (cg == 2)
         return out_elem_bytes == 2 ? launch_umma<2, uint16_t>(ma, mb, p, stream) : launch_umma<2, uint32_t>(ma, mb, p, stream);
     return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);

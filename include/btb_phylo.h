@@ -45,6 +45,12 @@ extern "C" {
 #define BTB_ENGINE_POPC   0   /* warp-tiled XOR/AND/POPC over bit-planes */
 #define BTB_ENGINE_UMMA   1   /* tcgen05 kind::i8 GEMM on one-hot int8 tiles, int32 accumulators in TMEM */
 
+/* `sigma` (number of symbol planes) takes this value when the alignment is "dense": at most four
+ * distinct symbols and no byte that is ignored anywhere (always true for what snp-sites -c writes).
+ * The engines then use their compact encodings: UMMA a 3-byte +-1 simplex code per site and a
+ * single operand (d = (3 len - dot) / 4), POPC two code planes without a validity plane. */
+#define BTB_SIGMA_DENSE4 (-4)
+
 /* side length of one scheduler tile of the distance matrix (rows == columns) */
 #define BTB_TILE        256
 
@@ -138,8 +144,10 @@ int btb_compact_columns(const uint32_t *d_planes, int64_t first, int64_t n_chunk
 /* ---- distances: k4 ---- */
 
 /* Symbol table of the alignment: table[b] = code 0..sigma-1, or 0xFF when byte b never counts
- * (everything but ACGT by default; only '.' with allchars).  Default mode needs no data pass
- * (d_seqs may be NULL); allchars scans the alignment on the device and synchronises `stream`. */
+ * (everything but ACGT by default; only '.' with allchars).  With d_seqs the alignment is scanned
+ * on the device (synchronises `stream`): allchars needs that to learn the alphabet, and either
+ * mode reports *sigma = BTB_SIGMA_DENSE4 when every byte present counts and sigma <= 4.
+ * Default mode with d_seqs == NULL skips the scan and returns sigma = 4. */
 int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
                       int allchars, int keepcase, uint8_t table[256], int *sigma, void *stream);
 

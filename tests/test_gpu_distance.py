@@ -56,6 +56,22 @@ def test_allchars_and_keepcase_modes(capi, oracle, name, engine, cg, allchars, k
         assert plan.sigma > 4
 
 
+@pytest.mark.parametrize("name,engine,cg", ENGINES)
+@pytest.mark.parametrize("n,L,allchars", [(3, 5, False), (300, 1000, False), (513, 4099, False), (513, 4099, True), (1500, 30000, False)])
+def test_dense_alignments_use_compact_encodings(capi, oracle, name, engine, cg, n, L, allchars):
+    """No ignored byte anywhere (what snp-sites -c always writes): UMMA switches to the +-1 simplex
+    operand (d = (3L - dot)/4), POPC drops the validity plane.  Same integers."""
+    seqs = synth.snp_alignment(n, L, seed=n * 7 + L, lower=0.0 if allchars else 0.02)
+    plan, got = gpu_matrix(capi, seqs, engine, cg, allchars=allchars)
+    assert plan.sigma == capi.SIGMA_DENSE4
+    assert (got == oracle.snp_dists_rows(seqs, allchars=allchars, threads=8)).all()
+    # one ignored byte switches the general encodings back on
+    seqs[n // 2, L // 2] = ord("N")
+    plan, got = gpu_matrix(capi, seqs, engine, cg, allchars=False)
+    assert plan.sigma == 4
+    assert (got == oracle.snp_dists_rows(seqs, threads=8)).all()
+
+
 def test_golden_c1_matrix(capi, oracle):
     from tests.conftest import golden
     lines = golden("c1_snps.fas").split(b"\n")

@@ -101,6 +101,9 @@ def main():
         try:
             r = subprocess.run([sys.executable, __file__, "--child", json.dumps(cfg)], capture_output=True, text=True,
                                timeout=cfg.get("timeout", 240))
+            if r.stderr.strip():
+                with open(os.path.join(ROOT, "gpurun_out", "probe_stderr.log"), "a") as ef:
+                    ef.write("==== %s\n%s\n" % (json.dumps(cfg), r.stderr[-200000:]))
             lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             msg = lines[-1] if lines else "NO RESULT rc=%d\n%s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-3000:])
         except subprocess.TimeoutExpired as e:
