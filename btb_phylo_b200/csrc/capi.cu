@@ -96,6 +96,7 @@ extern "C" int btb_device_count(int *count) {
 
 extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
+    if (key && !strcmp(key, "umma_dense_simplex")) { g_umma_dense_simplex = value ? 1 : 0; return BTB_OK; }
     return fail(BTB_EINVAL, "unknown option");
 }
 
@@ -142,7 +143,8 @@ namespace {
 struct Workspace {
     void *p[3] = {nullptr, nullptr, nullptr};
     size_t cap[3] = {0, 0, 0};
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev = nullptr;
     int ensure(int k, size_t bytes, void **out) {
         bytes = std::max<size_t>(bytes, 16);
         if (cap[k] < bytes) {
@@ -157,7 +159,10 @@ struct Workspace {
     void release() {
         for (int k = 0; k < 3; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
         if (st) cudaStreamDestroy(st);
-        st = nullptr;
+        if (st2) cudaStreamDestroy(st2);
+        if (ev) cudaEventDestroy(ev);
+        st = st2 = nullptr;
+        ev = nullptr;
     }
 };
 Workspace g_ws[16];
@@ -169,7 +174,7 @@ extern "C" int btb_release_workspace(void) {
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 16; ++d)
-        if (g_ws[d].p[0] || g_ws[d].p[1] || g_ws[d].p[2] || g_ws[d].st) { cudaSetDevice(d); g_ws[d].release(); }
+        if (g_ws[d].p[0] || g_ws[d].p[1] || g_ws[d].p[2] || g_ws[d].st || g_ws[d].st2) { cudaSetDevice(d); g_ws[d].release(); }
     cudaSetDevice(cur);
     return BTB_OK;
 }
@@ -213,24 +218,39 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
     const int eng = pick_engine(engine, len, std::max<int64_t>(0, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma) - int64_t(ws.cap[1])));
     L2_TRY(ws.ensure(1, size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma))), reinterpret_cast<void **>(&d_ops)));
     L2_TRY(btb_dist_encode(eng, d_seqs, n, len, d_stride, table, sigma, d_ops, st));
-    int64_t lo, hi;
-    tile_share(tile_count(n), rank, world, lo, hi);
-    L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 0, 1, st));
     const size_t eb = size_t(out_elem_bytes);
+    const int64_t T = tiles_per_dim(n);
     if (world == 1) {
-        L2_CUDA(cudaMemcpy2DAsync(out, size_t(out_ld) * eb, d_out, size_t(d_ld) * eb, size_t(n) * eb, size_t(n),
-                                  cudaMemcpyDeviceToHost, st));
+        // one launch per band of block rows; a finished band's matrix rows are final (row-band tile
+        // order + mirrored writes), so their copy to the host overlaps the next bands' GEMM
+        if (!ws.st2) L2_CUDA(cudaStreamCreateWithFlags(&ws.st2, cudaStreamNonBlocking));
+        if (!ws.ev) L2_CUDA(cudaEventCreateWithFlags(&ws.ev, cudaEventDisableTiming));
+        int64_t first = 0;
+        for (int64_t r0 = 0; r0 < T; r0 += kBand) {
+            const int64_t w = std::min<int64_t>(kBand, T - r0), cnt = band_tiles(T, r0, w);
+            L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, first, first + cnt, d_out, out_elem_bytes, d_ld, 0, 1, st));
+            L2_CUDA(cudaEventRecord(ws.ev, st));
+            L2_CUDA(cudaStreamWaitEvent(ws.st2, ws.ev, 0));
+            const int64_t row0 = r0 * BTB_TILE, row1 = std::min<int64_t>(n, (r0 + w) * BTB_TILE);
+            L2_CUDA(cudaMemcpy2DAsync(static_cast<char *>(out) + size_t(row0 * out_ld) * eb, size_t(out_ld) * eb,
+                                      d_out + size_t(row0 * d_ld) * eb, size_t(d_ld) * eb, size_t(n) * eb,
+                                      size_t(row1 - row0), cudaMemcpyDeviceToHost, ws.st2));
+            first += cnt;
+        }
+        L2_CUDA(cudaStreamSynchronize(ws.st2));
     } else {
-        // copy back the owned tiles and their mirrors, merging runs of tiles on one block row
-        const int64_t T = tiles_per_dim(n);
+        int64_t lo, hi;
+        tile_share(tile_count(n), rank, world, lo, hi);
+        L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 0, 1, st));
+        // copy back the owned tiles and their mirrors, merging runs of tiles in one block column
         int64_t t = lo;
         while (t < hi) {
             int I, J, I2, J2;
             tile_coords(T, t, I, J);
             int64_t e = t + 1;
-            while (e < hi) { tile_coords(T, e, I2, J2); if (I2 != I || J2 != J + int(e - t)) break; ++e; }
-            const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + BTB_TILE);
-            const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + (e - t) * BTB_TILE);
+            while (e < hi) { tile_coords(T, e, I2, J2); if (J2 != J || I2 != I + int(e - t)) break; ++e; }
+            const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + (e - t) * BTB_TILE);
+            const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + BTB_TILE);
             char *ho = static_cast<char *>(out);
             L2_CUDA(cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
                                       size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, st));

@@ -29,10 +29,14 @@ int fail(int code, const char *fmt, ...);
     } while (0)
 
 // ---- upper-triangle tile order ------------------------------------------------------------
-// Tiles are BTB_TILE x BTB_TILE blocks (I, J) with I <= J.  They are numbered band by band:
-// a band is kBand consecutive block columns; inside a band the order is row-major (I ascending,
-// then J).  74 CTA pairs working on consecutive indices therefore touch ~kBand column panels
-// and ~10 row panels at a time, which is what keeps the operand panels L2-resident.
+// Tiles are BTB_TILE x BTB_TILE blocks (I, J) with I <= J.  They are numbered band by band: a
+// band is kBand consecutive block ROWS; inside a band the order is column-major (J ascending,
+// then I).  Two properties follow:
+//   * 74-148 CTAs working on consecutive indices touch the band's <= kBand row panels plus ~10-19
+//     column panels at a time, which keeps the operand panels L2-resident;
+//   * with mirrored writes, every matrix row of a band is final as soon as the band is done (its
+//     left part was written by the mirrors of earlier bands), so finished row bands can be copied
+//     to the host and formatted while later bands are still being computed.
 constexpr int kBand = 8;
 
 __host__ __device__ inline int64_t tiles_per_dim(int64_t n) { return (n + BTB_TILE - 1) / BTB_TILE; }
@@ -42,23 +46,34 @@ __host__ __device__ inline int64_t tile_count(int64_t n) {
     return t * (t + 1) / 2;
 }
 
+// tiles in the band of block rows [r0, r0 + w)
+__host__ __device__ inline int64_t band_tiles(int64_t T, int64_t r0, int64_t w) {
+    return w * (w + 1) / 2 + (T - r0 - w) * w;
+}
+
 __host__ __device__ inline void tile_coords(int64_t T, int64_t idx, int &I, int &J) {
-    for (int64_t c0 = 0; c0 < T; c0 += kBand) {
-        int64_t c1 = c0 + kBand < T ? c0 + kBand : T;
-        int64_t w = c1 - c0;
-        int64_t rect = c0 * w;                 // rows above the band's diagonal block: w tiles each
-        int64_t tri = w * (w + 1) / 2;         // the band's diagonal block
-        if (idx < rect) { I = int(idx / w); J = int(c0 + idx % w); return; }
-        idx -= rect;
+    for (int64_t r0 = 0; r0 < T; r0 += kBand) {
+        const int64_t w = r0 + kBand < T ? kBand : T - r0;
+        const int64_t tri = w * (w + 1) / 2;            // the band's diagonal block: column r0+c holds c+1 tiles
         if (idx < tri) {
-            for (int64_t r = 0; r < w; ++r) {  // row c0 + r holds w - r tiles
-                if (idx < w - r) { I = int(c0 + r); J = int(c0 + r + idx); return; }
-                idx -= w - r;
+            for (int64_t c = 0; c < w; ++c) {
+                if (idx < c + 1) { I = int(r0 + idx); J = int(r0 + c); return; }
+                idx -= c + 1;
             }
         }
         idx -= tri;
+        const int64_t rect = (T - r0 - w) * w;          // columns right of the diagonal block: w tiles each
+        if (idx < rect) { I = int(r0 + idx % w); J = int(r0 + w + idx / w); return; }
+        idx -= rect;
     }
     I = J = -1;
+}
+
+// first tile index of the band that starts at block row r0 (r0 a multiple of kBand)
+__host__ __device__ inline int64_t band_first_tile(int64_t T, int64_t r0) {
+    int64_t idx = 0;
+    for (int64_t b = 0; b < r0; b += kBand) idx += band_tiles(T, b, b + kBand < T ? kBand : T - b);
+    return idx;
 }
 
 // ---- operand layouts of the two distance engines (see dist_encode.cu) -----------------------
@@ -74,8 +89,14 @@ __host__ __device__ inline int64_t popc_words(int64_t len) {      // words per r
     return (w + 15) / 16 * 16;
 }
 __host__ __device__ inline int sigma4_of(int sigma) { return sigma <= 4 ? 4 : (sigma + 3) / 4 * 4; }
-__host__ __device__ inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple of 128
-    int64_t k = len * (sigma_dense(sigma) ? 3 : sigma4_of(sigma));
+// dense UMMA operand: 0 = one-hot, single operand (d = len - matches); 1 = +-1 simplex, 3 bytes per
+// site (d = (3 len - dot) / 4).  The simplex code needs 25 % fewer MMAs but its dense +-1 data
+// drives the tensor pipe into the 1 kW power cap (measured: SM clock 1950 -> 1470 MHz), so the
+// sparse one-hot code is the default.  btb_set_option("umma_dense_simplex", 0|1).
+extern int g_umma_dense_simplex;
+inline int umma_bytes_per_site(int sigma) { return sigma_dense(sigma) ? (g_umma_dense_simplex ? 3 : 4) : sigma4_of(sigma); }
+inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple of 128
+    int64_t k = len * umma_bytes_per_site(sigma);
     return (k + 127) / 128 * 128;
 }
 

@@ -140,7 +140,7 @@ encode_onehot4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
             cw[b] = code < 4 ? (0x01010101u ^ hot) : 0u;
         }
         *reinterpret_cast<uint4 *>(A + row * kbytes + qd * 16) = a;
-        *reinterpret_cast<uint4 *>(B + row * kbytes + qd * 16) = c;
+        if (B) *reinterpret_cast<uint4 *>(B + row * kbytes + qd * 16) = c;
     }
     }
 }
@@ -308,13 +308,13 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         const int64_t kb = umma_k_bytes(len, sigma);
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
-        if (sigma_dense(sigma)) {
+        if (sigma_dense(sigma) && g_umma_dense_simplex) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 12 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             encode_simplex_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0);
-        } else if (sigma4_of(sigma) == 4) {
+        } else if (sigma_dense(sigma) || sigma4_of(sigma) == 4) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
-            encode_onehot4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, B,
-                                                            aligned ? 1 : 0);
+            encode_onehot4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A,
+                                                            sigma_dense(sigma) ? nullptr : B, aligned ? 1 : 0);
         } else {
             dim3 grid((unsigned)std::min<int64_t>((kb / 4 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             encode_onehot_generic_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table,

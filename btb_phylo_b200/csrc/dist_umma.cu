@@ -175,8 +175,8 @@ struct UmmaParams {
     int64_t ld;
     int out_mode;         // 0 = n x n matrix, 1 = tile-packed
     int mirror;
-    int dense;            // simplex operands: distance = (bias - dot) >> 2
-    int32_t bias;         // 3 * len
+    int dense;            // 0: out = acc; 1: out = bias - acc (one-hot matches); 2: out = (bias - acc) >> 2 (simplex)
+    int32_t bias;         // len or 3 * len
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
@@ -328,7 +328,7 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols + c0), v);
                 if (p.dense) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> 2;
+                    for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
                 }
                 const int64_t col = n0 + c0;
                 if (p.out_mode == 1) {
@@ -420,6 +420,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
     return BTB_OK;
 }
 
+int g_umma_dense_simplex = 0;
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
 template <int CG, typename OutT>
@@ -513,8 +514,8 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.out_mode = out_mode;
     p.mirror = mirror;
     p.dbg = nullptr;
-    p.dense = sigma_dense(sigma) ? 1 : 0;
-    p.bias = int32_t(3 * len);
+    p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex ? 2 : 1) : 0;
+    p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     if (cg == 2)
         return out_elem_bytes == 2 ? launch_umma<2, uint16_t>(ma, mb, p, stream) : launch_umma<2, uint32_t>(ma, mb, p, stream);
     return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);

@@ -19,24 +19,23 @@ def tile_count(n):
 
 
 def tile_coords(n, idx):
-    """Same band order as csrc/common.cuh tile_coords (checked against the library in tests)."""
+    """Same row-band order as csrc/common.cuh tile_coords (checked against the library in tests)."""
     T = tiles_per_dim(n)
-    c0 = 0
-    while c0 < T:
-        c1 = min(c0 + BAND, T)
-        w = c1 - c0
-        rect = c0 * w
+    r0 = 0
+    while r0 < T:
+        w = min(BAND, T - r0)
         tri = w * (w + 1) // 2
-        if idx < rect:
-            return idx // w, c0 + idx % w
-        idx -= rect
         if idx < tri:
-            for r in range(w):
-                if idx < w - r:
-                    return c0 + r, c0 + r + idx
-                idx -= w - r
+            for c in range(w):
+                if idx < c + 1:
+                    return r0 + idx, r0 + c
+                idx -= c + 1
         idx -= tri
-        c0 = c1
+        rect = (T - r0 - w) * w
+        if idx < rect:
+            return r0 + idx % w, r0 + w + idx // w
+        idx -= rect
+        r0 += w
     raise IndexError("tile index out of range")
 
 

@@ -47,8 +47,9 @@ extern "C" {
 
 /* `sigma` (number of symbol planes) takes this value when the alignment is "dense": at most four
  * distinct symbols and no byte that is ignored anywhere (always true for what snp-sites -c writes).
- * The engines then use their compact encodings: UMMA a 3-byte +-1 simplex code per site and a
- * single operand (d = (3 len - dot) / 4), POPC two code planes without a validity plane. */
+ * The engines then use their compact encodings: UMMA a single one-hot operand (d = len - matches;
+ * optionally a 3-byte +-1 simplex code, d = (3 len - dot) / 4), POPC two code planes without a
+ * validity plane. */
 #define BTB_SIGMA_DENSE4 (-4)
 
 /* side length of one scheduler tile of the distance matrix (rows == columns) */
@@ -57,7 +58,8 @@ extern "C" {
 int         btb_last_error(char *buf, size_t cap);       /* copies the message, returns its length */
 const char *btb_version(void);
 int         btb_device_count(int *count);                 /* number of usable sm_100 devices */
-/* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (default 2: CTA pairs, 256-row UMMA) */
+/* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (single CTA 128x256 UMMA | CTA pair 256x256);
+ * "umma_dense_simplex" = 0 | 1 (dense alignments: one-hot single operand | 3-byte +-1 simplex code) */
 int         btb_set_option(const char *key, int value);
 /* introspection: "umma_cta_group", "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
 int         btb_query(const char *key, int64_t *value);
