@@ -184,7 +184,8 @@ encode_onehot_generic_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_
 // dense simplex operand: one thread per 4 sites -> 12 bytes
 __global__ void __launch_bounds__(256)
 encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
-                      const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned) {
+                      const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned,
+                      int tetra01, int32_t *__restrict__ rowsum) {
     __shared__ uint8_t table[256];
     table[threadIdx.x] = table_g[threadIdx.x];
     __syncthreads();
@@ -192,6 +193,7 @@ encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
     for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
         const uint8_t *p = seqs + row * row_stride;
         uint32_t *dst = reinterpret_cast<uint32_t *>(A + row * kbytes);
+        int nonzero = 0;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
              g += (int64_t)gridDim.x * blockDim.x) {
             const int64_t site = g * 4;
@@ -208,7 +210,12 @@ encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
             for (int b = 0; b < 4; ++b) {
                 const uint32_t code = table[(raw >> (8 * b)) & 0xff];
                 // bytes (x, y, z) of the simplex vertex, little endian; sites beyond len -> 0
-                t[b] = code == 0 ? 0x010101u : code == 1 ? 0xFFFF01u : code == 2 ? 0xFF01FFu : code == 3 ? 0x01FFFFu : 0u;
+                if (tetra01) {
+                    t[b] = code == 1 ? 0x000101u : code == 2 ? 0x010001u : code == 3 ? 0x010100u : 0u;
+                    nonzero += (code >= 1 && code <= 3);
+                } else {
+                    t[b] = code == 0 ? 0x010101u : code == 1 ? 0xFFFF01u : code == 2 ? 0xFF01FFu : code == 3 ? 0x01FFFFu : 0u;
+                }
             }
             const uint32_t w0 = t[0] | (t[1] << 24), w1 = (t[1] >> 8) | (t[2] << 16), w2 = (t[2] >> 16) | (t[3] << 8);
             const int64_t wi = g * 3;
@@ -216,6 +223,11 @@ encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
             if (wi < total) dst[wi] = w0;
             if (wi + 1 < total) dst[wi + 1] = w1;
             if (wi + 2 < total) dst[wi + 2] = w2;
+        }
+        if (tetra01) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nonzero += __shfl_xor_sync(0xffffffffu, nonzero, o);
+            if ((threadIdx.x & 31) == 0 && nonzero) atomicAdd(&rowsum[row], nonzero);
         }
     }
 }
@@ -278,7 +290,7 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
 
 extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma) {
     if (engine == BTB_ENGINE_POPC) return (popc_code_planes(sigma) + (sigma_dense(sigma) ? 0 : 1)) * n * popc_words(len) * 4;
-    if (engine == BTB_ENGINE_UMMA) return (sigma_dense(sigma) ? 1 : 2) * n * umma_k_bytes(len, sigma);
+    if (engine == BTB_ENGINE_UMMA) return (sigma_dense(sigma) ? 1 : 2) * n * umma_k_bytes(len, sigma) + n * 4;
     return -1;
 }
 
@@ -310,7 +322,10 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         uint8_t *B = A + n * kb;
         if (sigma_dense(sigma) && g_umma_dense_simplex) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 12 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
-            encode_simplex_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0);
+            int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
+            if (g_umma_dense_simplex == 2) BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));
+            encode_simplex_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0,
+                                                            g_umma_dense_simplex == 2 ? 1 : 0, rowsum);
         } else if (sigma_dense(sigma) || sigma4_of(sigma) == 4) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             encode_onehot4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A,

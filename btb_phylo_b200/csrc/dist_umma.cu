@@ -70,6 +70,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// one lane of a converged warp; the compiler knows the guarded region is single-lane, so the
+// uniform-datapath instructions inside (UTMALDG, UTCIMMA, UTCBAR) need no per-lane election loops
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -135,6 +146,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     }
 }
 
+// CTA-pair MMA, arrival on the leader's barrier only (no multicast)
+__device__ __forceinline__ void umma_commit_leader(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -177,25 +193,31 @@ struct UmmaParams {
     int mirror;
     int dense;            // 0: out = acc; 1: out = bias - acc (one-hot matches); 2: out = (bias - acc) >> 2 (simplex)
     int32_t bias;         // len or 3 * len
+    const int32_t *rowsum; // dense == 3: c_i, out = c_row + c_col - acc
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
-template <int CG>
+// ATOMS = 128-byte K atoms per pipeline stage (one tcgen05.commit per stage: more atoms = fewer
+// commits); RELAY (CG = 2 only) = the leader's producer forwards the stage release to the peer
+// CTA with a remote mbarrier arrive instead of a multicast commit from the MMA thread.
+template <int CG, int ATOMS = 1, bool RELAY = false>
 struct UmmaCfg {
     static constexpr int kARows = 128;                               // A rows loaded per CTA per stage
     static constexpr int kBRows = CG == 2 ? 128 : 256;               // B rows loaded per CTA per stage
-    static constexpr int kABytes = kARows * kBlockK;
-    static constexpr int kBBytes = kBRows * kBlockK;
+    static constexpr int kAAtom = kARows * kBlockK;
+    static constexpr int kBAtom = kBRows * kBlockK;
+    static constexpr int kABytes = kAAtom * ATOMS;
+    static constexpr int kBBytes = kBAtom * ATOMS;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = CG == 2 ? 6 : 4;
+    static constexpr int kStages = (CG == 2 ? 6 : 4) / ATOMS;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int CG, typename OutT>
+template <int CG, typename OutT, int ATOMS = 1, bool RELAY = false>
 __global__ void __launch_bounds__(kThreads, 1)
 dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const UmmaParams p) {
-    using Cfg = UmmaCfg<CG>;
+    using Cfg = UmmaCfg<CG, ATOMS, RELAY>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms (same offset in both CTAs of a pair)
@@ -256,23 +278,33 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 0) {
         // ================================================================= TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            int64_t fills = 0;                 // stages filled so far (the first ring pass needs no release)
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 int64_t m0, n0; int I, J, half;
                 unit_coords(u, m0, n0, I, J, half);
                 const int64_t b_row = n0 + (CG == 2 ? int64_t(cta_rank) * 128 : 0);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
+                    if constexpr (CG == 2 && RELAY) {
+                        // the MMA thread released this stage on the leader only: pass it on
+                        if (leader && fills >= kStages) mbar_arrive_cluster(empty_bar(stage), 1);
+                    }
                     if constexpr (CG == 2) {
                         if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
                         else mbar_arrive_cluster(full_bar(stage), 0);
                     } else {
                         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     }
-                    tma_load_2d<CG>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), int(m0));
-                    tma_load_2d<CG>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), int(b_row));
+#pragma unroll
+                    for (int at = 0; at < ATOMS; ++at) {
+                        const int k0 = int((kb * ATOMS + at) * kBlockK);       // beyond K: zero-filled by TMA
+                        tma_load_2d<CG>(smem_a(stage) + at * Cfg::kAAtom, &map_a, full_bar(stage), k0, int(m0));
+                        tma_load_2d<CG>(smem_b(stage) + at * Cfg::kBAtom, &map_b, full_bar(stage), k0, int(b_row));
+                    }
+                    ++fills;
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -280,7 +312,9 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // ================================================================= MMA issuer (leader CTA)
-        if (leader && lane == 0) {
+        if (leader) {
+            // the whole warp walks the pipeline (warp-uniform control flow keeps descriptors in
+            // uniform registers); one elected lane issues the tensor-core instructions
             constexpr uint32_t idesc = make_i8_idesc(CG == 2 ? 256 : 128, kAccCols);
             int stage = 0;
             uint32_t phase = 0;
@@ -294,14 +328,21 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
-                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_i8<CG>(d_tmem, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
-                                    idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit<CG>(empty_bar(stage));
-                    if (kb == p.k_blocks - 1) umma_commit<CG>(tfull_bar(acc));
+                        for (int at = 0; at < ATOMS; ++at) {
+                            const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + at * Cfg::kAAtom);
+                            const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage) + at * Cfg::kBAtom);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                                umma_i8<CG>(d_tmem, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
+                                            idesc, (kb > 0 || at > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if constexpr (CG == 2 && RELAY) umma_commit_leader(empty_bar(stage));
+                        else umma_commit<CG>(empty_bar(stage));
+                        if (kb == p.k_blocks - 1) umma_commit<CG>(tfull_bar(acc));
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -326,7 +367,14 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int c0 = 0; c0 < kAccCols; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols + c0), v);
-                if (p.dense) {
+                if (p.dense == 3) {
+                    const int32_t cr = row < p.n ? p.rowsum[row] : 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t cj = n0 + c0 + j;
+                        v[j] = uint32_t(cr + (cj < p.n ? p.rowsum[cj] : 0) - int32_t(v[j]));
+                    }
+                } else if (p.dense) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
                 }
@@ -421,12 +469,13 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 0;
+int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
-template <int CG, typename OutT>
+template <int CG, typename OutT, int ATOMS = 1, bool RELAY = false>
 static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
-    using Cfg = UmmaCfg<CG>;
-    auto kernel = dist_umma_kernel<CG, OutT>;
+    using Cfg = UmmaCfg<CG, ATOMS, RELAY>;
+    auto kernel = dist_umma_kernel<CG, OutT, ATOMS, RELAY>;
     BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     int dev = 0, sms = 0;
     BTB_CUDA(cudaGetDevice(&dev));
@@ -506,7 +555,9 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     BTB_TRY(make_operand_map(&mb, B, n, kb, cg == 2 ? 128 : 256));
     UmmaParams p;
     p.n = n;
-    p.k_blocks = kb / kBlockK;
+    const int variant = cg == 2 ? g_umma_cg2_variant : 0;      // bit 0: 2 atoms per stage, bit 1: relay
+    const int atoms = (variant & 1) ? 2 : 1;
+    p.k_blocks = (kb / kBlockK + atoms - 1) / atoms;
     p.tile_lo = tile_lo;
     p.units = cg == 2 ? tiles : tiles * 2;
     p.out = d_out;
@@ -514,10 +565,18 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.out_mode = out_mode;
     p.mirror = mirror;
     p.dbg = nullptr;
-    p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex ? 2 : 1) : 0;
+    p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
-    if (cg == 2)
-        return out_elem_bytes == 2 ? launch_umma<2, uint16_t>(ma, mb, p, stream) : launch_umma<2, uint32_t>(ma, mb, p, stream);
+    p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+    if (cg == 2 && out_elem_bytes == 2) {
+        switch (variant & 3) {
+            case 1: return launch_umma<2, uint16_t, 2, false>(ma, mb, p, stream);
+            case 2: return launch_umma<2, uint16_t, 1, true>(ma, mb, p, stream);
+            case 3: return launch_umma<2, uint16_t, 2, true>(ma, mb, p, stream);
+            default: return launch_umma<2, uint16_t>(ma, mb, p, stream);
+        }
+    }
+    if (cg == 2) return launch_umma<2, uint32_t>(ma, mb, p, stream);
     return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);
 }
 

@@ -72,6 +72,33 @@ def test_dense_alignments_use_compact_encodings(capi, oracle, name, engine, cg, 
     assert (got == oracle.snp_dists_rows(seqs, threads=8)).all()
 
 
+def test_kernel_variants_agree(capi, oracle):
+    """Every tuning variant of the tensor-core engine gives the same integers: dense codes
+    (one-hot / +-1 simplex / 0-1 tetrahedron with row sums), CTA-pair stage shapes and release paths."""
+    lib = capi.lib()
+    dense = synth.snp_alignment(700, 3001, seed=12)
+    general = synth.snp_alignment(700, 3001, seed=13, heavy_n=0.1)
+    want_d = oracle.snp_dists_rows(dense, threads=8)
+    want_g = oracle.snp_dists_rows(general, threads=8)
+    try:
+        for code in (0, 1, 2):
+            capi.check(lib.btb_set_option(b"umma_dense_simplex", code))
+            for cg in (1, 2):
+                plan, got = gpu_matrix(capi, dense, 1, cg)
+                assert plan.sigma == capi.SIGMA_DENSE4 and (got == want_d).all(), (code, cg)
+        capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
+        for variant in (0, 1, 2, 3):
+            capi.check(lib.btb_set_option(b"umma_cg2_variant", variant))
+            _, got = gpu_matrix(capi, general, 1, 2)
+            assert (got == want_g).all(), variant
+            _, got = gpu_matrix(capi, dense, 1, 2)
+            assert (got == want_d).all(), variant
+    finally:
+        capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
+        capi.check(lib.btb_set_option(b"umma_cg2_variant", 0))
+        capi.check(lib.btb_set_option(b"umma_cta_group", 1))
+
+
 def test_golden_c1_matrix(capi, oracle):
     from tests.conftest import golden
     lines = golden("c1_snps.fas").split(b"\n")
