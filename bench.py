@@ -307,7 +307,7 @@ def gpu_arm(args):
         "metric": "pairwise SNP distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int8 -> int32 (exact)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 kind::i8, cta_group::%d" % _query(lib, b"umma_cta_group"),
+        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 kind::i8, cta_group::%d" % _query(lib, b"umma_cta_group"), "options": os.environ.get("BTB_OPTIONS", ""),
                    "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "sharding": "contiguous upper-triangle tile ranges, no collective",
                    "l2_policy": "operands (12 GB one-hot) and output (5 GB) exceed the 126 MB L2; no flush needed",
                    "timed_region": "operand encode + distance GEMM per step, CUDA events on the launching stream"},

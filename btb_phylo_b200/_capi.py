@@ -73,6 +73,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        # BTB_OPTIONS="umma_lockstep=0,umma_dense_simplex=2": tuning knobs of btb_set_option
+        for item in filter(None, os.environ.get("BTB_OPTIONS", "").split(",")):
+            key, _, val = item.partition("=")
+            if L.btb_set_option(key.strip().encode(), int(val)) != OK:
+                raise ValueError("BTB_OPTIONS: unknown option %r" % key)
     return _lib
 
 

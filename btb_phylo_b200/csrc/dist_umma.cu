@@ -194,6 +194,7 @@ struct UmmaParams {
     int dense;            // 0: out = acc; 1: out = bias - acc (one-hot matches); 2: out = (bias - acc) >> 2 (simplex)
     int32_t bias;         // len or 3 * len
     const int32_t *rowsum; // dense == 3: c_i, out = c_row + c_col - acc
+    unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
@@ -286,6 +287,24 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 int64_t m0, n0; int I, J, half;
                 unit_coords(u, m0, n0, I, J, half);
                 const int64_t b_row = n0 + (CG == 2 ? int64_t(cta_rank) * 128 : 0);
+                if (p.lockstep && u != worker) {
+                    // Re-align the producers of all CTAs at every unit boundary: CTAs that stream the
+                    // same operand panels then sit at the same K offset, so a panel block is fetched
+                    // from HBM once and hit in L2 by everyone else (needs all CTAs co-resident:
+                    // cooperative launch).  round r expects every worker that has a unit in round r.
+                    const int64_t round = (u - worker) / n_workers;
+                    const int64_t total_workers = CG == 2 ? n_workers * 2 : n_workers;
+                    const int64_t full_rounds = p.units / n_workers;          // rounds in which every worker has a unit
+                    const int64_t last_count = p.units - full_rounds * n_workers;
+                    const int64_t per_cta = CG == 2 ? 2 : 1;
+                    // arrivals expected by the time round `round` may start = arrivals of rounds 1..round
+                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * total_workers;
+                    if (round > full_rounds - 1) target += last_count * per_cta;
+                    (void)total_workers;
+                    __threadfence();
+                    atomicAdd(p.lockstep, 1u);
+                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+                }
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if constexpr (CG == 2 && RELAY) {
@@ -469,6 +488,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 0;
+int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
@@ -494,6 +514,18 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     UmmaParams q = p;
+    static unsigned int *d_lock[16] = {nullptr};
+    cudaLaunchAttribute attrs2[2];
+    if (g_umma_lockstep && p.units > ctas / (CG == 2 ? 2 : 1) && dev < 16) {
+        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
+        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
+        q.lockstep = d_lock[dev];
+        attrs2[0] = attr[0];
+        attrs2[1].id = cudaLaunchAttributeCooperative;
+        attrs2[1].val.cooperative = 1;
+        cfg.attrs = attrs2;
+        cfg.numAttrs = 2;
+    }
     unsigned long long *d_dbg = nullptr;
     const bool debug = getenv("BTB_UMMA_DEBUG") != nullptr;
     if (debug) {
@@ -565,6 +597,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.out_mode = out_mode;
     p.mirror = mirror;
     p.dbg = nullptr;
+    p.lockstep = nullptr;
     p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
