@@ -278,10 +278,16 @@ def gpu_arm(args):
         int8_lib = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
     except Exception:
         pass
+    dense_code = _query(lib, b"umma_dense_simplex")
+    planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
     roofline = {"bound": "tensor", "kernel": "dist_umma_kernel (tcgen05.mma kind::i8)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
+                "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-byte-per-site "
+                        "tetrahedron code, so the tensor pipe executes 3/4 of that: achieved_executed is the hardware rate",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(n, L, world),
                 "peak_source": peak_src, "ops": "int8 multiply-add = 2 ops; 2*sigma*L*N(N-1)/2 with sigma=4 (padding, diagonal tiles = overhead)",
                 "kernel_ms": kernel_ms, "peak_nominal_int8_dense": 4500.0, "frac_of_nominal": achieved / 4500.0,
+                "frac_of_nominal_executed": achieved * planes_executed / 4.0 / 4500.0,
                 "cublas_int8_8192_measured": int8_lib}
 
     # ---- CPU baseline on this box's host cores (bounded sample), also the parity spot-check -----
@@ -317,6 +323,19 @@ def gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _ncu_traffic(n, L, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one dist_umma_kernel launch, from the committed
+    `ncu --set full` capture of this very command (profiles/umma_traffic.json); None if the capture
+    was taken on another configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "umma_traffic.json")))
+        if t.get("n") == n and t.get("L") == L and t.get("n_gpus") == world:
+            return t["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 def _query(lib, key):

@@ -110,6 +110,7 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_max_active_clusters_cg2")) { BTB_TRY(umma_max_active_clusters(2, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_max_active_clusters_cg1")) { BTB_TRY(umma_max_active_clusters(1, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
+    if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
 }
 

@@ -487,7 +487,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
     return BTB_OK;
 }
 
-int g_umma_dense_simplex = 0;
+int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
 int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option

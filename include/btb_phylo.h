@@ -47,9 +47,9 @@ extern "C" {
 
 /* `sigma` (number of symbol planes) takes this value when the alignment is "dense": at most four
  * distinct symbols and no byte that is ignored anywhere (always true for what snp-sites -c writes).
- * The engines then use their compact encodings: UMMA a single one-hot operand (d = len - matches;
- * optionally a 3-byte +-1 simplex code, d = (3 len - dot) / 4), POPC two code planes without a
- * validity plane. */
+ * The engines then use their compact encodings: UMMA a single 3-byte-per-site operand whose
+ * symbols are the 0/1 vertices of a regular tetrahedron (d = c_i + c_j - dot), POPC two code planes
+ * without a validity plane. */
 #define BTB_SIGMA_DENSE4 (-4)
 
 /* side length of one scheduler tile of the distance matrix (rows == columns) */
@@ -59,7 +59,10 @@ int         btb_last_error(char *buf, size_t cap);       /* copies the message, 
 const char *btb_version(void);
 int         btb_device_count(int *count);                 /* number of usable sm_100 devices */
 /* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (single CTA 128x256 UMMA | CTA pair 256x256);
- * "umma_dense_simplex" = 0 | 1 (dense alignments: one-hot single operand | 3-byte +-1 simplex code) */
+ * "umma_dense_simplex" = 0 | 1 | 2 (dense alignments: one-hot | 3-byte +-1 simplex | 3-byte 0/1 tetrahedron, default 2);
+ * "umma_lockstep" = 0 | 1 (grid-wide re-alignment of the TMA producers at tile boundaries);
+ * "umma_cg2_variant" = 0..3 (CTA-pair kernel: bit 0 two K atoms per stage, bit 1 relayed stage release).
+ * The environment variable BTB_OPTIONS="key=value,..." sets them for the Python binding. */
 int         btb_set_option(const char *key, int value);
 /* introspection: "umma_cta_group", "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
 int         btb_query(const char *key, int64_t *value);
