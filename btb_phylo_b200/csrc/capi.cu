@@ -34,6 +34,7 @@ int distance_tiles_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, v
 extern int g_umma_cta_group;
 extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
+extern int g_umma_tile_mode;
 int umma_max_active_clusters(int cg, int *out);
 
 int require_device(int device) {
@@ -98,6 +99,7 @@ extern "C" int btb_device_count(int *count) {
 
 extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
+    if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_cg2_variant")) { g_umma_cg2_variant = value & 3; return BTB_OK; }
     if (key && !strcmp(key, "umma_dense_simplex")) { g_umma_dense_simplex = value < 0 || value > 2 ? 0 : value; return BTB_OK; }
@@ -111,6 +113,7 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_max_active_clusters_cg1")) { BTB_TRY(umma_max_active_clusters(1, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
     if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
+    if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
 }
 

@@ -198,6 +198,64 @@ struct UmmaParams {
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
+// Epilogue of one 128-row x 256-column accumulator buffer: this thread owns matrix row `row`
+// (TMEM lane of `taddr`), reads 32 columns at a time and writes the tile (16-byte stores), its
+// mirror (lane-coalesced 2/4-byte stores) or the tile-packed slot.
+template <typename OutT>
+__device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t taddr, int64_t row, int64_t n0,
+                                                  int row_in_tile, int64_t tile_slot, bool do_mirror) {
+    OutT *out = static_cast<OutT *>(p.out);
+#pragma unroll 1
+    for (int c0 = 0; c0 < kAccCols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + uint32_t(c0), v);
+        if (p.dense == 3) {
+            const int32_t cr = row < p.n ? p.rowsum[row] : 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int64_t cj = n0 + c0 + j;
+                v[j] = uint32_t(cr + (cj < p.n ? p.rowsum[cj] : 0) - int32_t(v[j]));
+            }
+        } else if (p.dense) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
+        }
+        const int64_t col = n0 + c0;
+        if (p.out_mode == 1) {
+            OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
+                        (int64_t)row_in_tile * BTB_TILE + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j] = (row < p.n && col + j < p.n) ? OutT(v[j]) : OutT(0);
+        } else {
+            if (row < p.n) {
+                OutT *dst = out + row * p.ld + col;
+                if (col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    // interior: 32 consecutive outputs of this row as 16-byte stores
+                    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                    if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
+                                               v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col + j < p.n) dst[j] = OutT(v[j]);
+                }
+            }
+            if (do_mirror && row < p.n) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+            }
+        }
+    }
+}
+
 // ATOMS = 128-byte K atoms per pipeline stage (one tcgen05.commit per stage: more atoms = fewer
 // commits); RELAY (CG = 2 only) = the leader's producer forwards the stage release to the peer
 // CTA with a remote mbarrier arrive instead of a multicast commit from the MMA thread.
@@ -370,7 +428,6 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp >= 4) {
         // ================================================================= epilogue
         const int quarter = warp & 3;                       // TMEM lanes 32*quarter .. +31
-        OutT *out = static_cast<OutT *>(p.out);
         int64_t it = 0;
         for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
             const int acc = int(it & 1);
@@ -382,55 +439,8 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int64_t row = m0 + quarter * 32 + lane;
             const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
             const int64_t tile_slot = CG == 2 ? u : u / 2;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kAccCols; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols + c0), v);
-                if (p.dense == 3) {
-                    const int32_t cr = row < p.n ? p.rowsum[row] : 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int64_t cj = n0 + c0 + j;
-                        v[j] = uint32_t(cr + (cj < p.n ? p.rowsum[cj] : 0) - int32_t(v[j]));
-                    }
-                } else if (p.dense) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
-                }
-                const int64_t col = n0 + c0;
-                if (p.out_mode == 1) {
-                    OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
-                                (int64_t)(half * 128 + quarter * 32 + lane) * BTB_TILE + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = (row < p.n && col + j < p.n) ? OutT(v[j]) : OutT(0);
-                } else {
-                    if (row < p.n) {
-                        OutT *dst = out + row * p.ld + col;
-                        if (col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                            // interior: 32 consecutive outputs of this row as 16-byte stores
-                            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-                            if constexpr (sizeof(OutT) == 2) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
-                                                       v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col + j < p.n) dst[j] = OutT(v[j]);
-                        }
-                    }
-                    if (do_mirror && row < p.n) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
-                    }
-                }
-            }
+            drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols), row, n0,
+                                    half * 128 + quarter * 32 + lane, tile_slot, do_mirror);
             // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
             tc_fence_before();
             __syncwarp();
@@ -451,6 +461,152 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         p.dbg[blockIdx.x * 4 + 1] = t;
         p.dbg[blockIdx.x * 4 + 3] = (unsigned long long)((p.units - worker + n_workers - 1) / n_workers);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full-tile variant: one CTA computes a whole 256 x 256 tile as two 128-row UMMA halves that share
+// every staged B block.  Per 128 K-bytes the CTA pulls 64 KB from L2 for 1024 tensor cycles
+// (64 B/clk instead of 96 B/clk for the half-tile kernel), so the same 192 KB of shared memory
+// covers 3072 instead of 2048 cycles of L2 latency.  The two TMEM buffers are the two halves of
+// the current tile; each has its own full/empty barrier, so the epilogue of half h of tile t
+// overlaps the K loop of tile t+1 as soon as that half is drained.
+struct TileCfg {
+    static constexpr int kABytes = 256 * kBlockK;                     // 32 KB: both halves of the row panel
+    static constexpr int kBBytes = 256 * kBlockK;                     // 32 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = 3;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const UmmaParams p) {
+    using Cfg = TileCfg;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int h) { return bar_base + 8u * (2 * kStages + h); };
+    auto tempty_bar = [&](int h) { return bar_base + 8u * (2 * kStages + 2 + h); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t worker = blockIdx.x, n_workers = gridDim.x;
+    const int64_t T = tiles_per_dim(p.n);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers) {
+                int I, J;
+                tile_coords(T, p.tile_lo + u, I, J);
+                const int m0 = I * BTB_TILE, n0 = J * BTB_TILE;
+                if (p.lockstep && u != worker) {
+                    // see dist_umma_kernel: all producers start a round of tiles together (L2 reuse)
+                    const int64_t round = (u - worker) / n_workers;
+                    const int64_t full_rounds = p.units / n_workers;
+                    const int64_t last_count = p.units - full_rounds * n_workers;
+                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
+                    if (round > full_rounds - 1) target += last_count;
+                    __threadfence();
+                    atomicAdd(p.lockstep, 1u);
+                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+                }
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), m0);
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc = make_i8_idesc(128, kAccCols);
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const uint32_t drained = (uint32_t(it) & 1u) ^ 1u;       // parity of the previous tile's drain
+            for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                if (kb == 0) mbar_wait(tempty_bar(0), drained);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_i8<1>(tmem_base, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4), idesc,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                __syncwarp();
+                if (kb == 0) { mbar_wait(tempty_bar(1), drained); tc_fence_after(); }
+                if (elect_one()) {
+                    // second half: rows 128..255 of the staged A block (16 KB further), accumulator columns 256..511
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + 128 * kBlockK);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_i8<1>(tmem_base + kAccCols, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
+                                   idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit<1>(empty_bar(stage));
+                    if (kb == p.k_blocks - 1) { umma_commit<1>(tfull_bar(0)); umma_commit<1>(tfull_bar(1)); }
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================= epilogue
+        const int quarter = warp & 3;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            int I, J;
+            tile_coords(T, p.tile_lo + u, I, J);
+            const int64_t n0 = int64_t(J) * BTB_TILE;
+            const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(tfull_bar(h), uint32_t(it) & 1u);
+                tc_fence_after();
+                const int row_in_tile = h * 128 + quarter * 32 + lane;
+                drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h * kAccCols),
+                                        int64_t(I) * BTB_TILE + row_in_tile, n0, row_in_tile, u, do_mirror);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(tempty_bar(h));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -488,6 +644,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
+int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
 int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
@@ -549,6 +706,36 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     return BTB_OK;
 }
 
+template <typename OutT>
+static int launch_umma_tile(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
+    auto kernel = dist_umma_tile_kernel<OutT>;
+    BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::kSmemBytes));
+    int dev = 0, sms = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t ctas = std::min<int64_t>(sms, p.units);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(unsigned(ctas));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = TileCfg::kSmemBytes;
+    cfg.stream = stream;
+    cfg.numAttrs = 0;
+    UmmaParams q = p;
+    static unsigned int *d_lock[16] = {nullptr};
+    if (g_umma_lockstep && p.units > ctas && dev < 16) {
+        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
+        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
+        q.lockstep = d_lock[dev];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, q));
+    return BTB_OK;
+}
+
 // how many CTA pairs of the CG = 2 kernel the device can keep resident at once
 int umma_max_active_clusters(int cg, int *out) {
     cudaLaunchConfig_t cfg = {};
@@ -583,6 +770,18 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
+    if (cg == 1 && g_umma_tile_mode == 1) {
+        BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+        BTB_TRY(make_operand_map(&mb, B, n, kb, 256));
+        UmmaParams p;
+        p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles;
+        p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
+        p.dbg = nullptr; p.lockstep = nullptr;
+        p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
+        p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
+        p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+        return out_elem_bytes == 2 ? launch_umma_tile<uint16_t>(ma, mb, p, stream) : launch_umma_tile<uint32_t>(ma, mb, p, stream);
+    }
     BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
     BTB_TRY(make_operand_map(&mb, B, n, kb, cg == 2 ? 128 : 256));
     UmmaParams p;
