@@ -770,7 +770,11 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
-    if (cg == 1 && g_umma_tile_mode == 1) {
+    int sms_now = 148, dev_now = 0;
+    if (cudaGetDevice(&dev_now) == cudaSuccess) cudaDeviceGetAttribute(&sms_now, cudaDevAttrMultiProcessorCount, dev_now);
+    // full tiles only pay off once every SM gets at least two of them; small problems keep the
+    // half-tile units (twice the parallelism)
+    if (cg == 1 && g_umma_tile_mode == 1 && tiles >= 2 * int64_t(sms_now)) {
         BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
         BTB_TRY(make_operand_map(&mb, B, n, kb, 256));
         UmmaParams p;

@@ -5,7 +5,8 @@
 // two distinct bases occur; kept columns are emitted upper-cased in genome order.
 //
 //   k1 pack_planes   : FASTA text -> 3 bit-planes per sample (code bit 0, code bit 1, validity),
-//                      32 columns per word.  code = (byte >> 1) & 3  (A=0 C=1 T=2 G=3).
+//                      32 columns per word (bit order: see plane_bit).  code = (byte >> 1) & 3
+//                      (A=0 C=1 T=2 G=3).  4 bytes are classified at a time with SWAR logic.
 //                      3 bits per base instead of 8 is what lets 50,000 x 4.35 Mb stay in 180 GB.
 //   k2 column_mask   : OR/AND reduction over samples -> seenA, seenC, seenG, seenT, anyInvalid.
 //   k3 select/compact: keep-mask, popc + shuffle-scan stream compaction of the kept column
@@ -37,6 +38,32 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
 }
 
 // ------------------------------------------------------------------------------------------ k1
+// Bit order inside a plane word: column c = 32 w + cl sits at bit 8 (cl & 3) + (cl >> 2), i.e.
+// byte j of the word holds the columns 4 g + j, bit g.  That is the order in which a 4-byte SWAR
+// classification produces its flags (one flag per byte lane), so k1 needs no bit transposition;
+// k2 is bit-parallel and order-agnostic, k3 undoes the permutation once on the G-bit keep mask.
+__host__ __device__ inline int plane_bit(int cl) { return 8 * (cl & 3) + (cl >> 2); }
+
+// SWAR classification of 4 text bytes.  Flags come out at bit 0 of every byte lane:
+//   valid <=> byte is one of ACGTacgt   (exact; checked exhaustively in tests/test_capi_host.py)
+//   code  = (byte >> 1) & 3             (A 0, C 1, T 2, G 3)
+// hi3 collects bit5|bit6|bit7 of every byte at bit 5: a byte < 0x20 (control character, e.g. a
+// stray CR/LF inside a line) clears it.
+struct Class4 { uint32_t v, b0, b1, hi3; };
+__device__ __forceinline__ Class4 classify4(uint32_t w) {
+    const uint32_t x1 = w >> 1, x2 = w >> 2, x3 = w >> 3, x4 = w >> 4, x6 = w >> 6, x7 = w >> 7;
+    const uint32_t t1 = w & (x1 | ~x2);
+    const uint32_t t2 = x2 & ~x1 & ~w;
+    const uint32_t f = (~x4 & t1) | (x4 & t2);
+    const uint32_t g = ~x7 & x6 & ~x3;
+    Class4 c;
+    c.v = f & g & 0x01010101u;
+    c.b0 = c.v & x1;
+    c.b1 = c.v & x2;
+    c.hi3 = w | x1 | x2;
+    return c;
+}
+
 __global__ void __launch_bounds__(kPackThreads)
 pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const int64_t *__restrict__ rec_off,
                    const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t first,
@@ -61,50 +88,64 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     int64_t hi = rec + off(c1 - 1) + 1 + e;               // incl. the terminator after the last column
     if (hi > text_bytes) hi = text_bytes;
     const int64_t alo = lo & ~int64_t(15);
-    const int nchunk = int((hi - alo + 15) >> 4);
+    const int nchunk = int((hi - alo + 15) >> 4) + 1;      // +1: the funnel shift may touch one word beyond
     for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
-        uint4 v = make_uint4(0, 0, 0, 0);
+        uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
         if (alo + 16 * int64_t(j) < text_bytes) v = ld_nc_v4(text + alo + 16 * int64_t(j));
         uint32_t *d = reinterpret_cast<uint32_t *>(stage + skew(16u * j));
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
+    auto word_at = [&](uint32_t q) { return sw[q + (q >> 3)]; };            // q = unskewed word index
     const int64_t c = c0 + 32 * int64_t(threadIdx.x);
-    uint32_t b0 = 0, b1 = 0, bv = 0;
+    uint32_t fv = 0, f0 = 0, f1 = 0, nonctl = 0x20202020u;
     bool irregular = false;
     if (c < c1) {
         const int64_t line = W ? c / W : 0;
-        int64_t pos = W ? c - line * W : 0;
-        uint32_t o = uint32_t(rec + c + line * e - alo);
-        const int kmax = c1 - c < 32 ? int(c1 - c) : 32;
-#pragma unroll 4
-        for (int k = 0; k < kmax; ++k) {
-            const uint32_t b = stage[skew(o)];
-            const uint32_t u = b & 0xDFu;
-            const uint32_t code = (b >> 1) & 3u;
-            const uint32_t expect = (0x47544341u >> (8 * code)) & 0xFFu;      // A C T G
-            const uint32_t valid = u == expect;
-            irregular |= (b == '\n') | (b == '\r');
-            bv |= valid << k;
-            b0 |= (valid & code) << k;
-            b1 |= (valid & (code >> 1)) << k;
-            ++o;
-            if (W && ++pos == W) {
-                if (c + k + 1 < G) {                      // a terminator must follow every full line
-                    if (e == 1) irregular |= stage[skew(o)] != '\n';
-                    else irregular |= (stage[skew(o)] != '\r') | (stage[skew(o + 1)] != '\n');
-                }
-                o += uint32_t(e);
-                pos = 0;
+        int64_t pos = W ? c - line * W : 0;                // column inside the current line
+        uint32_t o = uint32_t(rec + c + line * e - alo);   // byte offset inside the staged span
+        const int ncols = c1 - c < 32 ? int(c1 - c) : 32;
+        auto end_of_line = [&](int64_t next_col) {         // a terminator must follow every full line
+            if (next_col < G) {
+                if (e == 1) irregular |= stage[skew(o)] != '\n';
+                else irregular |= (stage[skew(o)] != '\r') | (stage[skew(o + 1)] != '\n');
             }
+            o += uint32_t(e);
+            pos = 0;
+        };
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int have = ncols - 4 * g;                // columns left for this group
+            if (have <= 0) break;
+            uint32_t w;
+            if (have >= 4 && (W == 0 || pos + 4 <= W)) {   // 4 bases on one line: one funnel shift
+                const uint32_t q = o >> 2, sh = (o & 3u) * 8u;
+                w = __funnelshift_r(word_at(q), word_at(q + 1), sh);
+                o += 4;
+                pos += 4;
+                if (W && pos == W) end_of_line(c + 4 * g + 4);
+            } else {                                        // the group straddles a line end or the row end
+                w = 0x20202020u;                            // blank = not a base, not a control byte
+                for (int j = 0; j < 4 && j < have; ++j) {
+                    w = (w & ~(0xFFu << (8 * j))) | (uint32_t(stage[skew(o)]) << (8 * j));
+                    ++o;
+                    if (W && ++pos == W) end_of_line(c + 4 * g + j + 1);
+                }
+            }
+            const Class4 k = classify4(w);
+            fv |= k.v << g;
+            f0 |= k.b0 << g;
+            f1 |= k.b1 << g;
+            nonctl &= k.hi3;
         }
     }
     if (wbase + threadIdx.x < words) {
-        p0[threadIdx.x] = b0;
-        p1[threadIdx.x] = b1;
-        pv[threadIdx.x] = bv;
+        p0[threadIdx.x] = f0;
+        p1[threadIdx.x] = f1;
+        pv[threadIdx.x] = fv;
     }
-    if (irregular) atomicOr(&flags[i], 1);
+    if (irregular || (nonctl & 0x20202020u) != 0x20202020u) atomicOr(&flags[i], 1);
 }
 
 // ------------------------------------------------------------------------------------------ k2
@@ -153,10 +194,13 @@ __device__ __forceinline__ uint32_t keep_word(const uint32_t *state, int64_t wor
     const uint32_t a = state[w], c = state[words + w], g = state[2 * words + w], t = state[3 * words + w];
     const uint32_t inv = state[4 * words + w];
     uint32_t two = (a & c) | (a & g) | (a & t) | (c & g) | (c & t) | (g & t);
-    uint32_t k = two & ~inv;
+    const uint32_t k = two & ~inv;                        // plane bit order
+    uint32_t kc = 0;                                      // column order: bit cl = column 32 w + cl
+#pragma unroll
+    for (int cl = 0; cl < 32; ++cl) kc |= ((k >> plane_bit(cl)) & 1u) << cl;
     const int64_t base = w * 32;
-    if (base + 32 > G) k &= base >= G ? 0u : (0xFFFFFFFFu >> (32 - int(G - base)));
-    return k;
+    if (base + 32 > G) kc &= base >= G ? 0u : (0xFFFFFFFFu >> (32 - int(G - base)));
+    return kc;
 }
 
 // pass 1: keep mask + per-block kept counts
@@ -250,7 +294,7 @@ compact_kernel(const uint32_t *__restrict__ planes, int64_t first, int64_t n_tot
     const uint32_t *P1 = planes + (1 * n_total + first + i) * words;
     for (int64_t l = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; l < L; l += int64_t(gridDim.x) * blockDim.x) {
         const uint32_t c = idx[l];
-        const uint32_t w = c >> 5, b = c & 31;
+        const uint32_t w = c >> 5, b = uint32_t(plane_bit(int(c & 31)));
         const uint32_t code = ((P0[w] >> b) & 1u) | (((P1[w] >> b) & 1u) << 1);
         out[i * ld + l] = uint8_t((0x47544341u >> (8 * code)) & 0xFFu);
     }

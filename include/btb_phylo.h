@@ -124,7 +124,8 @@ int64_t btb_plane_words(int64_t G);
  * 16-byte boundary).  Sample i's bases start at d_text + rec_off[i]; its lines are line_w[i] bases
  * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 8).  Writes three
  * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
- * sample i at d_planes + ((p * n_total + first + i) * words).  d_flags[i] is OR-ed with 1 when a
+ * sample i at d_planes + ((p * n_total + first + i) * words); column c = 32 w + cl is bit
+ * 8 (cl & 3) + (cl >> 2) of word w (the order a 4-byte SWAR classification produces).  d_flags[i] is OR-ed with 1 when a
  * line terminator is not where the layout says (the caller then re-stages that record unwrapped). */
 int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
                     const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
@@ -135,7 +136,7 @@ int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_
 int btb_column_mask(const uint32_t *d_planes, int64_t n, int64_t n_total, int64_t G,
                     uint32_t *d_colstate, int accumulate, void *stream);
 
-/* k3a: column state -> keep bitmask (G bits) + ascending kept-column indices; *d_count gets L.
+/* k3a: column state -> keep bitmask (G bits, plain order: bit c & 31 of word c >> 5) + ascending kept-column indices; *d_count gets L.
  * d_idx must hold G entries (worst case).  pure_mode as in btb_snp_sites. */
 int btb_select_columns(const uint32_t *d_colstate, int64_t G, int pure_mode,
                        uint32_t *d_keep, uint32_t *d_idx, uint32_t *d_count, void *stream);

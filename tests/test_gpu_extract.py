@@ -73,7 +73,8 @@ def test_level3_pack_wrapped_text(capi, oracle):
     f = flags.cpu().numpy()
     assert f[7] == 1 and (np.delete(f, 7) == 0).all()
     pl = planes.cpu().numpy().view(np.uint32).reshape(3, n, words)
-    bits = lambda w: ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).reshape(-1)[:G]
+    order = np.array([8 * (cl & 3) + (cl >> 2) for cl in range(32)], dtype=np.uint32)     # plane bit of column cl
+    bits = lambda w: ((w[:, None] >> order[None, :]) & 1).reshape(-1)[:G]
     for i in range(n):
         if i == 7:
             continue
