@@ -21,9 +21,10 @@
 namespace btb {
 
 constexpr int kPackThreads = 256;
-constexpr int kPackCols = kPackThreads * 32;             // columns per CTA
-constexpr int kPackStageBytes = 12 * 1024;               // staged text (incl. line terminators)
-constexpr int kMinLineW = 8;                             // shorter lines go through the host walk
+constexpr int kPackWordsPerThread = 4;                   // 128 columns = one 16-byte store per plane
+constexpr int kPackCols = kPackThreads * 32 * kPackWordsPerThread;   // 32,768 columns per CTA
+constexpr int kMinLineW = 16;                            // shorter lines go through the host walk
+constexpr int kPackStageBytes = kPackCols + kPackCols / kMinLineW * 2 + 64;   // staged text incl. terminators
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 
@@ -72,20 +73,27 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     __shared__ __align__(16) uint8_t stage[kPackStageBytes + kPackStageBytes / 8 + 64];
     const int64_t i = blockIdx.y;
     const int64_t c0 = int64_t(blockIdx.x) * kPackCols;
-    const int64_t c1 = min(G, c0 + kPackCols);
-    const int64_t W = line_w[i], e = eol_len[i], rec = rec_off[i];
-    const int64_t wbase = c0 >> 5;
+    const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+    const int64_t rec = rec_off[i];
+    const int64_t wbase = (c0 >> 5) + kPackWordsPerThread * threadIdx.x;     // first plane word of this thread
     uint32_t *p0 = planes + (0 * n_total + first + i) * words + wbase;
     uint32_t *p1 = planes + (1 * n_total + first + i) * words + wbase;
     uint32_t *pv = planes + (2 * n_total + first + i) * words + wbase;
+    const bool owns = wbase < words;                      // words is a multiple of 4: all four or none
     if (c0 >= G || (W && W < kMinLineW)) {                // padding words / layout the host must re-stage
-        if (wbase + threadIdx.x < words) p0[threadIdx.x] = p1[threadIdx.x] = pv[threadIdx.x] = 0;
+        if (owns) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(p0) = z; *reinterpret_cast<uint4 *>(p1) = z; *reinterpret_cast<uint4 *>(pv) = z;
+        }
         if (c0 < G && threadIdx.x == 0) atomicOr(&flags[i], 1);
         return;
     }
-    auto off = [&](int64_t c) { return W ? c + (c / W) * e : c; };
-    const int64_t lo = rec + off(c0);
-    int64_t hi = rec + off(c1 - 1) + 1 + e;               // incl. the terminator after the last column
+    // genome lengths fit 32 bits (the tools use int): 32-bit divisions only
+    const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);
+    const uint32_t ce = G32 - cb < uint32_t(kPackCols) ? G32 : cb + uint32_t(kPackCols);      // end of this CTA's columns
+    auto off = [&](uint32_t c) -> int64_t { return W ? int64_t(c) + int64_t(c / W) * e : int64_t(c); };
+    const int64_t lo = rec + off(cb);
+    int64_t hi = rec + off(ce - 1) + 1 + e;               // incl. the terminator after the last column
     if (hi > text_bytes) hi = text_bytes;
     const int64_t alo = lo & ~int64_t(15);
     const int nchunk = int((hi - alo + 15) >> 4) + 1;      // +1: the funnel shift may touch one word beyond
@@ -98,52 +106,74 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     __syncthreads();
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
     auto word_at = [&](uint32_t q) { return sw[q + (q >> 3)]; };            // q = unskewed word index
-    const int64_t c = c0 + 32 * int64_t(threadIdx.x);
-    uint32_t fv = 0, f0 = 0, f1 = 0, nonctl = 0x20202020u;
+    const uint32_t c = cb + 32u * kPackWordsPerThread * threadIdx.x;
+    uint32_t out_v[kPackWordsPerThread], out_0[kPackWordsPerThread], out_1[kPackWordsPerThread];
+    uint32_t nonctl = 0x20202020u;
     bool irregular = false;
-    if (c < c1) {
-        const int64_t line = W ? c / W : 0;
-        int64_t pos = W ? c - line * W : 0;                // column inside the current line
-        uint32_t o = uint32_t(rec + c + line * e - alo);   // byte offset inside the staged span
-        const int ncols = c1 - c < 32 ? int(c1 - c) : 32;
-        auto end_of_line = [&](int64_t next_col) {         // a terminator must follow every full line
-            if (next_col < G) {
-                if (e == 1) irregular |= stage[skew(o)] != '\n';
-                else irregular |= (stage[skew(o)] != '\r') | (stage[skew(o + 1)] != '\n');
-            }
-            o += uint32_t(e);
-            pos = 0;
-        };
+    const uint32_t line = (W && c < ce) ? c / W : 0u;
+    uint32_t pos = W ? c - line * W : 0u;                  // column inside the current line
+    uint32_t o = uint32_t(rec + int64_t(c) + int64_t(line) * e - alo);      // byte offset inside the staged span
+    auto end_of_line = [&](uint32_t next_col) {            // a terminator must follow every full line
+        if (next_col < G32) {
+            if (e == 1) irregular |= stage[skew(o)] != '\n';
+            else irregular |= (stage[skew(o)] != '\r') | (stage[skew(o + 1)] != '\n');
+        }
+        o += e;
+        pos = 0;
+    };
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int have = ncols - 4 * g;                // columns left for this group
-            if (have <= 0) break;
-            uint32_t w;
-            if (have >= 4 && (W == 0 || pos + 4 <= W)) {   // 4 bases on one line: one funnel shift
+    for (int wi = 0; wi < kPackWordsPerThread; ++wi) {
+        uint32_t fv = 0, f0 = 0, f1 = 0;
+        const uint32_t cw = c + 32u * wi;
+        if (cw < ce) {
+            const int ncols = ce - cw < 32u ? int(ce - cw) : 32;
+            if (ncols == 32 && (W == 0 || pos + 32 <= W)) {
+                // the whole word lies on one line: 8 funnel shifts, no bookkeeping
                 const uint32_t q = o >> 2, sh = (o & 3u) * 8u;
-                w = __funnelshift_r(word_at(q), word_at(q + 1), sh);
-                o += 4;
-                pos += 4;
-                if (W && pos == W) end_of_line(c + 4 * g + 4);
-            } else {                                        // the group straddles a line end or the row end
-                w = 0x20202020u;                            // blank = not a base, not a control byte
-                for (int j = 0; j < 4 && j < have; ++j) {
-                    w = (w & ~(0xFFu << (8 * j))) | (uint32_t(stage[skew(o)]) << (8 * j));
-                    ++o;
-                    if (W && ++pos == W) end_of_line(c + 4 * g + j + 1);
+                uint32_t prev = word_at(q);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint32_t next = word_at(q + g + 1);
+                    const Class4 k = classify4(__funnelshift_r(prev, next, sh));
+                    prev = next;
+                    fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
+                    nonctl &= k.hi3;
+                }
+                o += 32;
+                pos += 32;
+                if (W && pos == W) end_of_line(cw + 32);
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < 8; ++g) {
+                    const int have = ncols - 4 * g;        // columns left for this group
+                    if (have <= 0) break;
+                    uint32_t w;
+                    if (have >= 4 && (W == 0 || pos + 4 <= W)) {   // 4 bases on one line: one funnel shift
+                        const uint32_t q = o >> 2, sh = (o & 3u) * 8u;
+                        w = __funnelshift_r(word_at(q), word_at(q + 1), sh);
+                        o += 4;
+                        pos += 4;
+                        if (W && pos == W) end_of_line(cw + 4 * g + 4);
+                    } else {                                // the group straddles a line end or the row end
+                        w = 0x20202020u;                    // blank = not a base, not a control byte
+                        for (int j = 0; j < 4 && j < have; ++j) {
+                            w = (w & ~(0xFFu << (8 * j))) | (uint32_t(stage[skew(o)]) << (8 * j));
+                            ++o;
+                            if (W && ++pos == W) end_of_line(cw + 4 * g + j + 1);
+                        }
+                    }
+                    const Class4 k = classify4(w);
+                    fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
+                    nonctl &= k.hi3;
                 }
             }
-            const Class4 k = classify4(w);
-            fv |= k.v << g;
-            f0 |= k.b0 << g;
-            f1 |= k.b1 << g;
-            nonctl &= k.hi3;
         }
+        out_v[wi] = fv; out_0[wi] = f0; out_1[wi] = f1;
     }
-    if (wbase + threadIdx.x < words) {
-        p0[threadIdx.x] = f0;
-        p1[threadIdx.x] = f1;
-        pv[threadIdx.x] = fv;
+    if (owns) {
+        *reinterpret_cast<uint4 *>(p0) = make_uint4(out_0[0], out_0[1], out_0[2], out_0[3]);
+        *reinterpret_cast<uint4 *>(p1) = make_uint4(out_1[0], out_1[1], out_1[2], out_1[3]);
+        *reinterpret_cast<uint4 *>(pv) = make_uint4(out_v[0], out_v[1], out_v[2], out_v[3]);
     }
     if (irregular || (nonctl & 0x20202020u) != 0x20202020u) atomicOr(&flags[i], 1);
 }
