@@ -35,6 +35,7 @@ extern int g_umma_cta_group;
 extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
 extern int g_umma_tile_mode;
+extern int g_pack_wpt;
 int umma_max_active_clusters(int cg, int *out);
 
 int require_device(int device) {
@@ -99,6 +100,7 @@ extern "C" int btb_device_count(int *count) {
 
 extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
+    if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_cg2_variant")) { g_umma_cg2_variant = value & 3; return BTB_OK; }

@@ -21,10 +21,12 @@
 namespace btb {
 
 constexpr int kPackThreads = 256;
-constexpr int kPackWordsPerThread = 4;                   // 128 columns = one 16-byte store per plane
-constexpr int kPackCols = kPackThreads * 32 * kPackWordsPerThread;   // 32,768 columns per CTA
 constexpr int kMinLineW = 16;                            // shorter lines go through the host walk
-constexpr int kPackStageBytes = kPackCols + kPackCols / kMinLineW * 2 + 64;   // staged text incl. terminators
+template <int WPT> struct PackCfg {                      // WPT = plane words (32 columns each) per thread
+    static constexpr int kCols = kPackThreads * 32 * WPT;                     // columns per CTA
+    static constexpr int kStageBytes = kCols + kCols / kMinLineW * 2 + 64;    // staged text incl. terminators
+};
+int g_pack_wpt = 1;
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 
@@ -65,11 +67,14 @@ __device__ __forceinline__ Class4 classify4(uint32_t w) {
     return c;
 }
 
+template <int kPackWordsPerThread>
 __global__ void __launch_bounds__(kPackThreads)
 pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const int64_t *__restrict__ rec_off,
                    const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t first,
                    int64_t n_total, int64_t G, int64_t words, uint32_t *__restrict__ planes,
                    int32_t *__restrict__ flags) {
+    constexpr int kPackCols = PackCfg<kPackWordsPerThread>::kCols;
+    constexpr int kPackStageBytes = PackCfg<kPackWordsPerThread>::kStageBytes;
     __shared__ __align__(16) uint8_t stage[kPackStageBytes + kPackStageBytes / 8 + 64];
     const int64_t i = blockIdx.y;
     const int64_t c0 = int64_t(blockIdx.x) * kPackCols;
@@ -79,11 +84,11 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     uint32_t *p0 = planes + (0 * n_total + first + i) * words + wbase;
     uint32_t *p1 = planes + (1 * n_total + first + i) * words + wbase;
     uint32_t *pv = planes + (2 * n_total + first + i) * words + wbase;
-    const bool owns = wbase < words;                      // words is a multiple of 4: all four or none
+    const bool owns = wbase < words;                      // words is a multiple of 4: all of this thread's words or none
     if (c0 >= G || (W && W < kMinLineW)) {                // padding words / layout the host must re-stage
         if (owns) {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4 *>(p0) = z; *reinterpret_cast<uint4 *>(p1) = z; *reinterpret_cast<uint4 *>(pv) = z;
+#pragma unroll
+            for (int k = 0; k < kPackWordsPerThread; ++k) p0[k] = p1[k] = pv[k] = 0;
         }
         if (c0 < G && threadIdx.x == 0) atomicOr(&flags[i], 1);
         return;
@@ -171,9 +176,14 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         out_v[wi] = fv; out_0[wi] = f0; out_1[wi] = f1;
     }
     if (owns) {
-        *reinterpret_cast<uint4 *>(p0) = make_uint4(out_0[0], out_0[1], out_0[2], out_0[3]);
-        *reinterpret_cast<uint4 *>(p1) = make_uint4(out_1[0], out_1[1], out_1[2], out_1[3]);
-        *reinterpret_cast<uint4 *>(pv) = make_uint4(out_v[0], out_v[1], out_v[2], out_v[3]);
+        if constexpr (kPackWordsPerThread == 4) {
+            *reinterpret_cast<uint4 *>(p0) = make_uint4(out_0[0], out_0[1], out_0[2], out_0[3]);
+            *reinterpret_cast<uint4 *>(p1) = make_uint4(out_1[0], out_1[1], out_1[2], out_1[3]);
+            *reinterpret_cast<uint4 *>(pv) = make_uint4(out_v[0], out_v[1], out_v[2], out_v[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPackWordsPerThread; ++k) { p0[k] = out_0[k]; p1[k] = out_1[k]; pv[k] = out_v[k]; }
+        }
     }
     if (irregular || (nonctl & 0x20202020u) != 0x20202020u) atomicOr(&flags[i], 1);
 }
@@ -343,13 +353,18 @@ extern "C" int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const 
     if (!d_text || !d_rec_off || !d_line_w || !d_eol || !d_planes || !d_flags || n_chunk <= 0 || G <= 0)
         return fail(BTB_EINVAL, "btb_pack_planes: bad argument");
     const int64_t words = plane_words(G);
-    const int64_t gx = (words * 32 + kPackCols - 1) / kPackCols;
+    const int wpt = g_pack_wpt == 4 ? 4 : 1;
+    const int64_t cols = wpt == 4 ? PackCfg<4>::kCols : PackCfg<1>::kCols;
+    const int64_t gx = (words * 32 + cols - 1) / cols;
     for (int64_t y0 = 0; y0 < n_chunk; y0 += 65535) {
         const int64_t ny = std::min<int64_t>(65535, n_chunk - y0);
         dim3 grid((unsigned)gx, (unsigned)ny);
-        pack_planes_kernel<<<grid, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            d_text, text_bytes, d_rec_off + y0, d_line_w + y0, d_eol + y0, first + y0, n_total, G, words, d_planes,
-            d_flags + y0);
+        if (wpt == 4)
+            pack_planes_kernel<4><<<grid, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                d_text, text_bytes, d_rec_off + y0, d_line_w + y0, d_eol + y0, first + y0, n_total, G, words, d_planes, d_flags + y0);
+        else
+            pack_planes_kernel<1><<<grid, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                d_text, text_bytes, d_rec_off + y0, d_line_w + y0, d_eol + y0, first + y0, n_total, G, words, d_planes, d_flags + y0);
     }
     BTB_CUDA(cudaGetLastError());
     return BTB_OK;
