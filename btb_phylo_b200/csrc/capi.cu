@@ -388,12 +388,77 @@ extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, 
     return BTB_OK;
 }
 
+namespace {
+
+// Multi-GPU distance stage: operands replicated, bands of block rows dealt
+// to the devices in snake order (band sizes shrink with the row index), every device copies the
+// matrix rows it completed plus the mirrored column strip into the host matrix H.  No collective:
+// one host thread per device.  H is n x ld elements, pinned.
+int multi_gpu_matrix(const DenseFasta &df, int n_dev, int allchars, int keepcase, int engine, int eb, int64_t ld,
+                     char *H) {
+    const int64_t n = df.n, len = df.len, T = tiles_per_dim(n);
+    std::vector<std::vector<int64_t>> bands(static_cast<size_t>(n_dev));
+    int64_t k = 0;
+    for (int64_t r0 = 0; r0 < T; r0 += kBand, ++k) {
+        const int64_t lap = k / n_dev, pos = k % n_dev;
+        bands[size_t((lap & 1) ? n_dev - 1 - pos : pos)].push_back(r0);
+    }
+    std::vector<int> rcs(static_cast<size_t>(n_dev), BTB_OK);
+    std::vector<std::string> errs(static_cast<size_t>(n_dev));
+    auto worker = [&](int dev) {
+        auto body = [&]() -> int {
+            BTB_TRY(require_device(dev));
+            cudaStream_t st;
+            BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
+            auto done = [&](int rc) { cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out); cudaStreamDestroy(st); return rc; };
+            if (cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)) != cudaSuccess) return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
+            if (cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st) != cudaSuccess) return done(fail(BTB_ECUDA, "H2D failed"));
+            uint8_t table[256];
+            int sigma = 4;
+            int rc = btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st);
+            if (rc) return done(rc);
+            if (cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)) != cudaSuccess) return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
+            const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
+            if (cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))) != cudaSuccess)
+                return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
+            rc = btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st);
+            if (rc) return done(rc);
+            for (int64_t r0 : bands[size_t(dev)]) {
+                const int64_t w = std::min<int64_t>(kBand, T - r0), first = band_first_tile(T, r0);
+                rc = btb_distance_tiles(eng, d_ops, n, len, sigma, first, first + band_tiles(T, r0, w), d_out, eb, ld, 0, 1, st);
+                if (rc) return done(rc);
+                const int64_t row0 = r0 * BTB_TILE, row1 = std::min<int64_t>(n, (r0 + w) * BTB_TILE);
+                // rows of the band from its first column to the end ...
+                if (cudaMemcpy2DAsync(H + size_t(row0 * ld + row0) * eb, size_t(ld) * eb, d_out + size_t(row0 * ld + row0) * eb,
+                                      size_t(ld) * eb, size_t(n - row0) * eb, size_t(row1 - row0), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                    return done(fail(BTB_ECUDA, "D2H failed"));
+                // ... and the mirrored strip below it
+                if (row1 < n && cudaMemcpy2DAsync(H + size_t(row1 * ld + row0) * eb, size_t(ld) * eb, d_out + size_t(row1 * ld + row0) * eb,
+                                                  size_t(ld) * eb, size_t(row1 - row0) * eb, size_t(n - row1), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                    return done(fail(BTB_ECUDA, "D2H failed"));
+            }
+            if (cudaStreamSynchronize(st) != cudaSuccess) return done(fail(BTB_ECUDA, "device %d: kernel or copy failed: %s", dev, cudaGetErrorString(cudaGetLastError())));
+            return done(BTB_OK);
+        };
+        rcs[size_t(dev)] = body();
+        if (rcs[size_t(dev)]) errs[size_t(dev)] = last_error();
+    };
+    std::vector<std::thread> pool;
+    for (int d = 0; d < n_dev; ++d) pool.emplace_back(worker, d);
+    for (auto &t : pool) t.join();
+    for (int d = 0; d < n_dev; ++d)
+        if (rcs[size_t(d)]) return fail(rcs[size_t(d)], "%s", errs[size_t(d)].c_str());
+    return BTB_OK;
+}
+
+}  // namespace
+
 extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
                              char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
                              int64_t *n_samples, int64_t *seq_len) {
     if (!in_fasta || !out_path) return fail(BTB_EINVAL, "btb_snp_dists: NULL path");
     const int threads = std::max(1, host_threads);
-    (void)n_gpus;   // one device per call for now; multi-rank drivers use btb_dist_matrix_host / level 3
     if (!quiet) {
         fprintf(stderr, "This is snp-dists 0.8.2\n");
         fprintf(stderr, "Will use %d threads.\n", threads);
@@ -414,6 +479,7 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     BTB_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
     uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
     char *h_stage[2] = {nullptr, nullptr};
+    char *h_full = nullptr;            // multi-GPU: the devices fill this pinned matrix, then it is formatted
     FILE *fo = nullptr;
     const bool to_stdout = !strcmp(out_path, "-") || !strcmp(out_path, "/dev/stdout");
     std::string tmp_path = to_stdout ? std::string("/dev/stdout") : std::string(out_path) + ".tmp";
@@ -421,6 +487,7 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
         if (h_stage[0]) cudaFreeHost(h_stage[0]);
         if (h_stage[1]) cudaFreeHost(h_stage[1]);
+        if (h_full) cudaFreeHost(h_full);
         cudaStreamDestroy(st); cudaStreamDestroy(st2);
         if (fo) { fclose(fo); if (!to_stdout) remove(tmp_path.c_str()); }
     };
@@ -434,10 +501,19 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         }                                                                                                 \
     } while (0)
 #define L1_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
-    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)));
-    L1_CUDA(cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st));
+    int usable = 0;
+    btb_device_count(&usable);
+    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(std::min(n_gpus, usable), tiles_per_dim(n) / kBand)));
+    if (n_dev > 1) {
+        L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_full), size_t(n * ld * eb)));
+        rc = multi_gpu_matrix(df, n_dev, allchars, keepcase, engine, eb, ld, h_full);
+        if (rc != BTB_OK) { cleanup(); return rc; }
+    }
     uint8_t table[256];
     int sigma = 4;
+    if (n_dev == 1) {
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)));
+    L1_CUDA(cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st));
     L1_TRY(btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st));
     L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)));
     const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
@@ -445,6 +521,7 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     L1_TRY(btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st));
     L1_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, 0, tile_count(n), d_out, eb, ld, 0, 1, st));
     L1_CUDA(cudaStreamSynchronize(st));
+    }
 
     // ---- serialise: D2H row blocks (double-buffered) -> threads format -> ordered writes
     fo = fopen(tmp_path.c_str(), "wb");
@@ -469,6 +546,7 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     L1_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     auto issue = [&](int64_t b) -> cudaError_t {
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
+        if (h_full) return cudaEventRecord(ev[b & 1], st2);      // rows are already on the host
         cudaError_t e = cudaMemcpyAsync(h_stage[b & 1], d_out + size_t(r0 * ld * eb), size_t((r1 - r0) * ld * eb),
                                         cudaMemcpyDeviceToHost, st2);
         if (e != cudaSuccess) return e;
@@ -482,14 +560,16 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
         if (!molten) {
             size_t w = 0;
-            L1_TRY(btb_format_csv_rows(h_stage[b & 1], eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads,
+            const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
+            L1_TRY(btb_format_csv_rows(src_rows, eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads,
                                        text.data(), text.size(), &w));
             if (fwrite(text.data(), 1, w, fo) != w) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
         } else {
             for (int64_t r = r0; r < r1; ++r)
                 for (int64_t i = 0; i < n; ++i) {
-                    const uint32_t v = eb == 2 ? reinterpret_cast<const uint16_t *>(h_stage[b & 1])[(r - r0) * ld + i]
-                                               : reinterpret_cast<const uint32_t *>(h_stage[b & 1])[(r - r0) * ld + i];
+                    const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
+                    const uint32_t v = eb == 2 ? reinterpret_cast<const uint16_t *>(src_rows)[(r - r0) * ld + i]
+                                               : reinterpret_cast<const uint32_t *>(src_rows)[(r - r0) * ld + i];
                     fprintf(fo, "%s%c%s%c%u\n", df.names[size_t(r)].c_str(), sep, df.names[size_t(i)].c_str(), sep, v);
                 }
         }

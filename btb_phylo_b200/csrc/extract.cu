@@ -21,7 +21,7 @@
 namespace btb {
 
 constexpr int kPackThreads = 256;
-constexpr int kMinLineW = 16;                            // shorter lines go through the host walk
+constexpr int kMinLineW = 32;                            // shorter lines go through the host walk (<= 1 line end per 32 columns)
 template <int WPT> struct PackCfg {                      // WPT = plane words (32 columns each) per thread
     static constexpr int kCols = kPackThreads * 32 * WPT;                     // columns per CTA
     static constexpr int kStageBytes = kCols + kCols / kMinLineW * 2 + 64;    // staged text incl. terminators
@@ -118,59 +118,47 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     const uint32_t line = (W && c < ce) ? c / W : 0u;
     uint32_t pos = W ? c - line * W : 0u;                  // column inside the current line
     uint32_t o = uint32_t(rec + int64_t(c) + int64_t(line) * e - alo);      // byte offset inside the staged span
-    auto end_of_line = [&](uint32_t next_col) {            // a terminator must follow every full line
-        if (next_col < G32) {
-            if (e == 1) irregular |= stage[skew(o)] != '\n';
-            else irregular |= (stage[skew(o)] != '\r') | (stage[skew(o + 1)] != '\n');
-        }
-        o += e;
-        pos = 0;
-    };
 #pragma unroll
     for (int wi = 0; wi < kPackWordsPerThread; ++wi) {
         uint32_t fv = 0, f0 = 0, f1 = 0;
         const uint32_t cw = c + 32u * wi;
         if (cw < ce) {
-            const int ncols = ce - cw < 32u ? int(ce - cw) : 32;
-            if (ncols == 32 && (W == 0 || pos + 32 <= W)) {
-                // the whole word lies on one line: 8 funnel shifts, no bookkeeping
-                const uint32_t q = o >> 2, sh = (o & 3u) * 8u;
-                uint32_t prev = word_at(q);
+            const uint32_t ncols = ce - cw < 32u ? ce - cw : 32u;
+            // Branch-free for every lane: the 32 columns are the bytes o .. o+31, except that after the
+            // `rem` bases left on the current line the text skips e terminator bytes (at most one line
+            // end per word since W >= 32).  A[g] reads group g before the line end, B[g] after it.
+            const uint32_t rem = W ? W - pos : 0xFFFFu;
+            const uint32_t qa = o >> 2, sa = (o & 3u) * 8u, ob = o + e, qb = ob >> 2, sb = (ob & 3u) * 8u;
+            uint32_t pa = word_at(qa), pb = word_at(qb);
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint32_t next = word_at(q + g + 1);
-                    const Class4 k = classify4(__funnelshift_r(prev, next, sh));
-                    prev = next;
-                    fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
-                    nonctl &= k.hi3;
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t na = word_at(qa + g + 1), nb = word_at(qb + g + 1);
+                const uint32_t A = __funnelshift_r(pa, na, sa), B = __funnelshift_r(pb, nb, sb);
+                pa = na; pb = nb;
+                // bytes of this group that still belong to the current line: rem - 4g clamped to 0..4
+                const int keep = int(rem) - 4 * g;
+                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : (keep <= 0 ? 0u : (1u << (8 * keep)) - 1u);
+                uint32_t w = (A & m) | (B & ~m);
+                if (ncols < 32u) {                          // last word of the row: blank out columns >= G
+                    const int have = int(ncols) - 4 * g;
+                    const uint32_t hm = have >= 4 ? 0xFFFFFFFFu : (have <= 0 ? 0u : (1u << (8 * have)) - 1u);
+                    w = (w & hm) | (0x20202020u & ~hm);
                 }
-                o += 32;
-                pos += 32;
-                if (W && pos == W) end_of_line(cw + 32);
+                const Class4 k = classify4(w);
+                fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
+                nonctl &= k.hi3;
+            }
+            if (rem <= ncols) {                             // a line ends inside (or exactly at the end of) this word
+                if (cw + rem < G32) {                       // ... and more bases follow: the terminator must be there
+                    const uint32_t t = o + rem;
+                    if (e == 1) irregular |= stage[skew(t)] != '\n';
+                    else irregular |= (stage[skew(t)] != '\r') | (stage[skew(t + 1)] != '\n');
+                }
+                o += 32u + e;
+                pos = 32u - rem;
             } else {
-#pragma unroll 1
-                for (int g = 0; g < 8; ++g) {
-                    const int have = ncols - 4 * g;        // columns left for this group
-                    if (have <= 0) break;
-                    uint32_t w;
-                    if (have >= 4 && (W == 0 || pos + 4 <= W)) {   // 4 bases on one line: one funnel shift
-                        const uint32_t q = o >> 2, sh = (o & 3u) * 8u;
-                        w = __funnelshift_r(word_at(q), word_at(q + 1), sh);
-                        o += 4;
-                        pos += 4;
-                        if (W && pos == W) end_of_line(cw + 4 * g + 4);
-                    } else {                                // the group straddles a line end or the row end
-                        w = 0x20202020u;                    // blank = not a base, not a control byte
-                        for (int j = 0; j < 4 && j < have; ++j) {
-                            w = (w & ~(0xFFu << (8 * j))) | (uint32_t(stage[skew(o)]) << (8 * j));
-                            ++o;
-                            if (W && ++pos == W) end_of_line(cw + 4 * g + j + 1);
-                        }
-                    }
-                    const Class4 k = classify4(w);
-                    fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
-                    nonctl &= k.hi3;
-                }
+                o += 32u;
+                pos += 32u;
             }
         }
         out_v[wi] = fv; out_0[wi] = f0; out_1[wi] = f1;

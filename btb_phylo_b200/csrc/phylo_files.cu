@@ -146,7 +146,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
         return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
     }
     // Records the GPU cannot address with (line width, terminator length) go through the exact walk.
-    auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 16); };
+    auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 32); };
     for (auto &r : recs)
         if (needs_walk(r)) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
     const int64_t G = recs[0].seq_len;

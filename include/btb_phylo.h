@@ -122,7 +122,7 @@ int64_t btb_plane_words(int64_t G);
 
 /* k1: text -> bit-planes.  d_text holds text_bytes bytes of FASTA text (allocation padded to a
  * 16-byte boundary).  Sample i's bases start at d_text + rec_off[i]; its lines are line_w[i] bases
- * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 16).  Writes three
+ * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 32).  Writes three
  * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
  * sample i at d_planes + ((p * n_total + first + i) * words); column c = 32 w + cl is bit
  * 8 (cl & 3) + (cl >> 2) of word w (the order a 4-byte SWAR classification produces).  d_flags[i] is OR-ed with 1 when a

@@ -43,7 +43,7 @@ def test_level3_pack_wrapped_text(capi, oracle):
     n, G = 9, 12345
     aln = synth.genome_alignment(n, G, 500, seed=77, n_frac=0.03, lower=0.02)
     names = synth.sample_names(n)
-    wraps = [60, 70, 0, 61, 16, 60, 1000, 60, 8]            # 8 < 16: too short for the GPU layout -> flagged
+    wraps = [60, 70, 0, 61, 32, 60, 1000, 33, 8]            # 8 < 32: too short for the GPU layout -> flagged
     eols = [b"\n", b"\r\n", b"\n", b"\n", b"\n", b"\r\n", b"\n", b"\n", b"\n"]
     text = bytearray()
     offs, lws, els = [], [], []
@@ -55,7 +55,7 @@ def test_level3_pack_wrapped_text(capi, oracle):
         els.append(len(eols[i]) if lws[-1] else 0)
         text += rec
     # damage record 7: swap a base and its line terminator
-    p = offs[7] + 60
+    p = offs[7] + 33
     text[p - 1], text[p] = text[p], text[p - 1]
     text += b"\0" * 64
     lib = capi.lib()
