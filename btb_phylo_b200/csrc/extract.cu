@@ -26,7 +26,7 @@ template <int WPT> struct PackCfg {                      // WPT = plane words (3
     static constexpr int kCols = kPackThreads * 32 * WPT;                     // columns per CTA
     static constexpr int kStageBytes = kCols + kCols / kMinLineW * 2 + 64;    // staged text incl. terminators
 };
-int g_pack_wpt = 1;
+int g_pack_wpt = 4;                                     // plane words per thread: 4 (128 columns, 16-byte plane stores) or 1
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 

@@ -131,3 +131,22 @@ def test_full_genome_width_property(ph, oracle, tmp_path):
     ph.snp_sites(str(sf), str(mf), threads=8)
     assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
     assert sf.read_bytes() == o_sf.read_bytes()
+
+
+def test_multi_gpu_file_path_same_bytes(capi, oracle, tmp_path):
+    """n_gpus = 2 (bands of block rows dealt to the devices, host assembly) writes the same snps.csv
+    as one GPU and as the oracle.  Needs two visible devices (gpurun --gpus 2)."""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, L = 4500, 700
+    names = synth.sample_names(n)
+    seqs = synth.snp_alignment(n, L, seed=6, heavy_n=0.05)
+    sf = tmp_path / "snps.fas"
+    synth.write_fasta(str(sf), names, seqs, wrap=0)
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("snps_%d.csv" % gpus)
+        capi.check(capi.lib().btb_snp_dists(str(sf).encode(), str(out).encode(), 0, 0, 0, b",", 1, 1, gpus, 8, -1, None, None))
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1]
+    assert outs[0] == oracle.format_matrix(names, oracle.snp_dists_rows(seqs, threads=8))
