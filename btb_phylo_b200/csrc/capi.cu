@@ -1,5 +1,8 @@
 // C-ABI of libbtbphylo.so: error plumbing, distance stage (levels 1-3).  See include/btb_phylo.h.
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -337,27 +340,18 @@ int read_dense(const char *path, int threads, DenseFasta &df) {
 
 }  // namespace
 
-extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n, int64_t row0,
-                                   int64_t row1, const char *const *names, char sep, int host_threads,
-                                   char *buf, size_t cap, size_t *written) {
-    if (!mat || !buf || !names || row0 < 0 || row1 < row0 || (elem_bytes != 2 && elem_bytes != 4))
-        return fail(BTB_EINVAL, "btb_format_csv_rows: bad argument");
-    const int64_t rows = row1 - row0;
-    const size_t per_cell = elem_bytes == 2 ? 6 : 11;
-    std::vector<size_t> off(size_t(rows) + 1, 0);
-    for (int64_t r = 0; r < rows; ++r)
-        off[size_t(r) + 1] = off[size_t(r)] + strlen(names[row0 + r]) + size_t(n) * per_cell + 1 + 8;
-    std::vector<size_t> used(size_t(rows), 0);
-    // format into generously spaced slots, then compact
-    std::vector<char> tmp;
-    const bool direct = off[size_t(rows)] <= cap;
-    char *work = buf;
-    if (!direct) { tmp.resize(off[size_t(rows)]); work = tmp.data(); }
+namespace {
+// Formats `rows` matrix rows (name, then sep + decimal per cell, then \n) into generously spaced
+// slots of `work`: row r starts at off[r] and is used[r] bytes long.  host_threads workers.
+size_t csv_slot_bytes(const char *name, int64_t n, int elem_bytes) { return strlen(name) + size_t(n) * (elem_bytes == 2 ? 6 : 11) + 1 + 8; }
+
+void format_rows_spaced(const void *mat, int elem_bytes, int64_t ld, int64_t n, int64_t rows, const char *const *names,
+                        char sep, int host_threads, char *work, const std::vector<size_t> &off, std::vector<size_t> &used) {
     auto job = [&](int64_t lo, int64_t hi) {
         for (int64_t r = lo; r < hi; ++r) {
             char *p = work + off[size_t(r)];
-            const size_t nl = strlen(names[row0 + r]);
-            memcpy(p, names[row0 + r], nl);
+            const size_t nl = strlen(names[r]);
+            memcpy(p, names[r], nl);
             p += nl;
             p += format_row(static_cast<const char *>(mat) + size_t(r) * size_t(ld) * size_t(elem_bytes), elem_bytes, n, sep, p);
             *p++ = '\n';
@@ -365,17 +359,32 @@ extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, 
         }
     };
     const int threads = std::max(1, std::min<int>(host_threads, 64));
-    if (threads == 1 || rows < 2 * threads) {
-        job(0, rows);
-    } else {
-        std::vector<std::thread> pool;
-        const int64_t span = (rows + threads - 1) / threads;
-        for (int t = 0; t < threads; ++t) {
-            int64_t lo = t * span, hi = std::min(rows, lo + span);
-            if (lo < hi) pool.emplace_back(job, lo, hi);
-        }
-        for (auto &th : pool) th.join();
+    if (threads == 1 || rows < 2 * threads) { job(0, rows); return; }
+    std::vector<std::thread> pool;
+    const int64_t span = (rows + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        int64_t lo = t * span, hi = std::min(rows, lo + span);
+        if (lo < hi) pool.emplace_back(job, lo, hi);
     }
+    for (auto &th : pool) th.join();
+}
+}  // namespace
+
+extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n, int64_t row0,
+                                   int64_t row1, const char *const *names, char sep, int host_threads,
+                                   char *buf, size_t cap, size_t *written) {
+    if (!mat || !buf || !names || row0 < 0 || row1 < row0 || (elem_bytes != 2 && elem_bytes != 4))
+        return fail(BTB_EINVAL, "btb_format_csv_rows: bad argument");
+    const int64_t rows = row1 - row0;
+    std::vector<size_t> off(size_t(rows) + 1, 0);
+    for (int64_t r = 0; r < rows; ++r) off[size_t(r) + 1] = off[size_t(r)] + csv_slot_bytes(names[row0 + r], n, elem_bytes);
+    std::vector<size_t> used(size_t(rows), 0);
+    // format into generously spaced slots, then compact
+    std::vector<char> tmp;
+    const bool direct = off[size_t(rows)] <= cap;
+    char *work = buf;
+    if (!direct) { tmp.resize(off[size_t(rows)]); work = tmp.data(); }
+    format_rows_spaced(mat, elem_bytes, ld, n, rows, names + row0, sep, host_threads, work, off, used);
     size_t total = 0;
     for (int64_t r = 0; r < rows; ++r) total += used[size_t(r)];
     if (total > cap) return fail(BTB_EINVAL, "btb_format_csv_rows: buffer too small (%zu needed)", total);
@@ -529,12 +538,15 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     setvbuf(fo, nullptr, _IOFBF, 1 << 22);
     std::vector<const char *> name_ptr(static_cast<size_t>(n));
     for (int64_t i = 0; i < n; ++i) name_ptr[size_t(i)] = df.names[size_t(i)].c_str();
+    size_t file_pos = 0;
     if (!molten) {
         std::string head = corner ? "snp-dists 0.8.2" : "";
         for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
         head.push_back('\n');
         fwrite(head.data(), 1, head.size(), fo);
+        file_pos = head.size();
     }
+    fflush(fo);                                          // the matrix rows go through pwrite at absolute offsets
     const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / std::max<int64_t>(1, ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[0]), size_t(block_rows * ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[1]), size_t(block_rows * ld * eb)));
@@ -558,7 +570,41 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         L1_CUDA(cudaEventSynchronize(ev[b & 1]));
         if (b + 1 < blocks) L1_CUDA(issue(b + 1));
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
-        if (!molten) {
+        if (!molten && !to_stdout) {
+            // rows are formatted into spaced slots by `threads` workers; once the lengths are known every
+            // worker writes its rows at their final file offsets (pwrite: parallel copies into the page cache)
+            const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
+            const int64_t rows = r1 - r0;
+            std::vector<size_t> off(size_t(rows) + 1, 0), used(size_t(rows), 0), pos(size_t(rows) + 1, 0);
+            for (int64_t r = 0; r < rows; ++r) off[size_t(r) + 1] = off[size_t(r)] + csv_slot_bytes(name_ptr[size_t(r0 + r)], n, eb);
+            if (off[size_t(rows)] > text.size()) text.resize(off[size_t(rows)]);
+            format_rows_spaced(src_rows, eb, ld, n, rows, name_ptr.data() + r0, sep, threads, text.data(), off, used);
+            for (int64_t r = 0; r < rows; ++r) pos[size_t(r) + 1] = pos[size_t(r)] + used[size_t(r)];
+            std::atomic<bool> write_failed{false};
+            const int fd = fileno(fo);
+            auto wjob = [&](int64_t lo, int64_t hi) {
+                for (int64_t r = lo; r < hi; ++r) {
+                    const char *p = text.data() + off[size_t(r)];
+                    size_t left = used[size_t(r)];
+                    off_t at = off_t(file_pos + pos[size_t(r)]);
+                    while (left) {
+                        ssize_t w = pwrite(fd, p, left, at);
+                        if (w <= 0) { write_failed = true; return; }
+                        p += w; left -= size_t(w); at += w;
+                    }
+                }
+            };
+            const int wt = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), rows)));
+            if (wt == 1) wjob(0, rows);
+            else {
+                std::vector<std::thread> pool;
+                const int64_t span = (rows + wt - 1) / wt;
+                for (int t = 0; t < wt; ++t) { int64_t lo = t * span, hi = std::min(rows, lo + span); if (lo < hi) pool.emplace_back(wjob, lo, hi); }
+                for (auto &th : pool) th.join();
+            }
+            if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
+            file_pos += pos[size_t(rows)];
+        } else if (!molten) {
             size_t w = 0;
             const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
             L1_TRY(btb_format_csv_rows(src_rows, eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads,

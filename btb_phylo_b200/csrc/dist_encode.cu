@@ -181,48 +181,63 @@ encode_onehot_generic_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_
     }
 }
 
-// dense simplex operand: one thread per 4 sites -> 12 bytes
+// dense 3-byte-per-site operand (+-1 simplex or 0/1 tetrahedron): one thread per 16 sites -> one
+// 16-byte load, three 16-byte stores (48 operand bytes)
 __global__ void __launch_bounds__(256)
 encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
                       const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned,
                       int tetra01, int32_t *__restrict__ rowsum) {
-    __shared__ uint8_t table[256];
-    table[threadIdx.x] = table_g[threadIdx.x];
+    __shared__ uint32_t vertex[256];                        // symbol -> its 3 operand bytes (little endian)
+    {
+        const uint32_t code = table_g[threadIdx.x];
+        uint32_t t;
+        if (tetra01) t = code == 1 ? 0x000101u : code == 2 ? 0x010001u : code == 3 ? 0x010100u : 0u;
+        else t = code == 0 ? 0x010101u : code == 1 ? 0xFFFF01u : code == 2 ? 0xFF01FFu : code == 3 ? 0x01FFFFu : 0u;
+        vertex[threadIdx.x] = t;
+    }
     __syncthreads();
-    const int64_t groups = kbytes / 12 + (kbytes % 12 != 0);
+    const int64_t groups = (kbytes + 47) / 48;              // 16 sites = 48 operand bytes
+    const bool vec_in = aligned && (row_stride % 16 == 0) && (reinterpret_cast<uintptr_t>(seqs) % 16 == 0);
     for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
         const uint8_t *p = seqs + row * row_stride;
         uint32_t *dst = reinterpret_cast<uint32_t *>(A + row * kbytes);
+        const int64_t total = kbytes / 4;
         int nonzero = 0;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
              g += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t site = g * 4;
-            uint32_t raw = 0x2e2e2e2eu;
-            if (aligned && site + 3 < len) {
-                raw = *reinterpret_cast<const uint32_t *>(p + site);
+            const int64_t site = g * 16;
+            uint32_t raw[4] = {0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu};   // '.' = ignored
+            if (vec_in && site + 15 < len) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(p + site);
+                raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
             } else {
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (site + b < len) raw = (raw & ~(0xffu << (8 * b))) | (uint32_t(p[site + b]) << (8 * b));
+                for (int b = 0; b < 16; ++b)
+                    if (site + b < len) raw[b >> 2] = (raw[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (uint32_t(p[site + b]) << (8 * (b & 3)));
             }
-            uint32_t t[4];
+            uint32_t out[12];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t code = table[(raw >> (8 * b)) & 0xff];
-                // bytes (x, y, z) of the simplex vertex, little endian; sites beyond len -> 0
-                if (tetra01) {
-                    t[b] = code == 1 ? 0x000101u : code == 2 ? 0x010001u : code == 3 ? 0x010100u : 0u;
-                    nonzero += (code >= 1 && code <= 3);
-                } else {
-                    t[b] = code == 0 ? 0x010101u : code == 1 ? 0xFFFF01u : code == 2 ? 0xFF01FFu : code == 3 ? 0x01FFFFu : 0u;
+            for (int q = 0; q < 4; ++q) {
+                uint32_t t[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t byte = (raw[q] >> (8 * b)) & 0xff;
+                    t[b] = vertex[byte];
+                    if (tetra01) nonzero += t[b] != 0;
                 }
+                out[3 * q + 0] = t[0] | (t[1] << 24);
+                out[3 * q + 1] = (t[1] >> 8) | (t[2] << 16);
+                out[3 * q + 2] = (t[2] >> 16) | (t[3] << 8);
             }
-            const uint32_t w0 = t[0] | (t[1] << 24), w1 = (t[1] >> 8) | (t[2] << 16), w2 = (t[2] >> 16) | (t[3] << 8);
-            const int64_t wi = g * 3;
-            const int64_t total = kbytes / 4;
-            if (wi < total) dst[wi] = w0;
-            if (wi + 1 < total) dst[wi + 1] = w1;
-            if (wi + 2 < total) dst[wi + 2] = w2;
+            const int64_t wi = g * 12;
+            if (wi + 12 <= total) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst + wi);       // 48-byte groups: 16-byte aligned
+                d4[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                d4[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                d4[2] = make_uint4(out[8], out[9], out[10], out[11]);
+            } else {
+                for (int k = 0; k < 12; ++k)
+                    if (wi + k < total) dst[wi + k] = out[k];
+            }
         }
         if (tetra01) {
 #pragma unroll
@@ -321,7 +336,7 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
         if (sigma_dense(sigma) && g_umma_dense_simplex) {
-            dim3 grid((unsigned)std::min<int64_t>((kb / 12 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
             if (g_umma_dense_simplex == 2) BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));
             encode_simplex_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0,
