@@ -472,9 +472,12 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         fprintf(stderr, "This is snp-dists 0.8.2\n");
         fprintf(stderr, "Will use %d threads.\n", threads);
     }
+    StageTimer timer("btb_snp_dists");
     BTB_TRY(require_device(0));
+    timer.mark("device init");
     DenseFasta df;
     int rc = read_dense(in_fasta, threads, df);
+    timer.mark("read + parse snps.fas");
     if (rc != BTB_OK) { if (!quiet) fprintf(stderr, "%s\n", last_error().c_str()); return rc; }
     if (!quiet) fprintf(stderr, "Read %lld sequences of length %lld\n", (long long)df.n, (long long)df.len);
     if (n_samples) *n_samples = df.n;
@@ -492,7 +495,9 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     FILE *fo = nullptr;
     const bool to_stdout = !strcmp(out_path, "-") || !strcmp(out_path, "/dev/stdout");
     std::string tmp_path = to_stdout ? std::string("/dev/stdout") : std::string(out_path) + ".tmp";
+    std::thread *writer_ptr = nullptr;
     auto cleanup = [&]() {
+        if (writer_ptr && writer_ptr->joinable()) writer_ptr->join();
         cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
         if (h_stage[0]) cudaFreeHost(h_stage[0]);
         if (h_stage[1]) cudaFreeHost(h_stage[1]);
@@ -532,27 +537,32 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     L1_CUDA(cudaStreamSynchronize(st));
     }
 
+    timer.mark("H2D + encode + distance kernel");
     // ---- serialise: D2H row blocks (double-buffered) -> threads format -> ordered writes
     fo = fopen(tmp_path.c_str(), "wb");
     if (!fo) { rc = fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); cleanup(); return rc; }
     setvbuf(fo, nullptr, _IOFBF, 1 << 22);
     std::vector<const char *> name_ptr(static_cast<size_t>(n));
     for (int64_t i = 0; i < n; ++i) name_ptr[size_t(i)] = df.names[size_t(i)].c_str();
-    size_t file_pos = 0;
     if (!molten) {
         std::string head = corner ? "snp-dists 0.8.2" : "";
         for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
         head.push_back('\n');
         fwrite(head.data(), 1, head.size(), fo);
-        file_pos = head.size();
     }
-    fflush(fo);                                          // the matrix rows go through pwrite at absolute offsets
+    fflush(fo);                                          // the matrix rows go straight to the descriptor
     const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / std::max<int64_t>(1, ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[0]), size_t(block_rows * ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[1]), size_t(block_rows * ld * eb)));
     size_t max_name = 0;
     for (auto &s : df.names) max_name = std::max(max_name, s.size());
-    std::vector<char> text(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 16));
+    std::vector<char> text2[2];
+    text2[0].resize(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 16));
+    text2[1].resize(text2[0].size());
+    std::thread writer;
+    writer_ptr = &writer;
+    std::atomic<bool> write_failed{false};
+    const int fd = fileno(fo);
     cudaEvent_t ev[2];
     L1_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     L1_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
@@ -570,46 +580,26 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
         L1_CUDA(cudaEventSynchronize(ev[b & 1]));
         if (b + 1 < blocks) L1_CUDA(issue(b + 1));
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
-        if (!molten && !to_stdout) {
-            // rows are formatted into spaced slots by `threads` workers; once the lengths are known every
-            // worker writes its rows at their final file offsets (pwrite: parallel copies into the page cache)
-            const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
-            const int64_t rows = r1 - r0;
-            std::vector<size_t> off(size_t(rows) + 1, 0), used(size_t(rows), 0), pos(size_t(rows) + 1, 0);
-            for (int64_t r = 0; r < rows; ++r) off[size_t(r) + 1] = off[size_t(r)] + csv_slot_bytes(name_ptr[size_t(r0 + r)], n, eb);
-            if (off[size_t(rows)] > text.size()) text.resize(off[size_t(rows)]);
-            format_rows_spaced(src_rows, eb, ld, n, rows, name_ptr.data() + r0, sep, threads, text.data(), off, used);
-            for (int64_t r = 0; r < rows; ++r) pos[size_t(r) + 1] = pos[size_t(r)] + used[size_t(r)];
-            std::atomic<bool> write_failed{false};
-            const int fd = fileno(fo);
-            auto wjob = [&](int64_t lo, int64_t hi) {
-                for (int64_t r = lo; r < hi; ++r) {
-                    const char *p = text.data() + off[size_t(r)];
-                    size_t left = used[size_t(r)];
-                    off_t at = off_t(file_pos + pos[size_t(r)]);
-                    while (left) {
-                        ssize_t w = pwrite(fd, p, left, at);
-                        if (w <= 0) { write_failed = true; return; }
-                        p += w; left -= size_t(w); at += w;
-                    }
-                }
-            };
-            const int wt = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), rows)));
-            if (wt == 1) wjob(0, rows);
-            else {
-                std::vector<std::thread> pool;
-                const int64_t span = (rows + wt - 1) / wt;
-                for (int t = 0; t < wt; ++t) { int64_t lo = t * span, hi = std::min(rows, lo + span); if (lo < hi) pool.emplace_back(wjob, lo, hi); }
-                for (auto &th : pool) th.join();
-            }
-            if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
-            file_pos += pos[size_t(rows)];
-        } else if (!molten) {
+        if (!molten) {
+            // format block b with `threads` workers while the writer thread is still pushing block b-1
+            // into the file (one large sequential write per block: buffered writes to one inode
+            // serialise in the kernel, so parallel pwrite does not pay)
             size_t w = 0;
             const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
-            L1_TRY(btb_format_csv_rows(src_rows, eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads,
-                                       text.data(), text.size(), &w));
-            if (fwrite(text.data(), 1, w, fo) != w) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
+            std::vector<char> &tb = text2[b & 1];
+            L1_TRY(btb_format_csv_rows(src_rows, eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads, tb.data(), tb.size(), &w));
+            if (writer.joinable()) writer.join();
+            if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
+            const char *wp = tb.data();
+            writer = std::thread([&write_failed, fd, wp, w]() {
+                const char *p = wp;
+                size_t left = w;
+                while (left) {
+                    ssize_t k = write(fd, p, left);
+                    if (k <= 0) { write_failed = true; return; }
+                    p += k; left -= size_t(k);
+                }
+            });
         } else {
             for (int64_t r = r0; r < r1; ++r)
                 for (int64_t i = 0; i < n; ++i) {
@@ -620,8 +610,11 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
                 }
         }
     }
+    if (writer.joinable()) writer.join();
+    if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
+    timer.mark("D2H + format + write snps.csv");
     if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     fo = nullptr;
     if (!to_stdout && rename(tmp_path.c_str(), out_path) != 0) { rc = fail(BTB_EIO, "cannot rename to '%s'", out_path); cleanup(); return rc; }

@@ -7,13 +7,34 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <time.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
 #include "common.cuh"
 
 namespace btb {
+
+static double now_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec);
+}
+StageTimer::StageTimer(const char *w) : what(w), on(getenv("BTB_TIMING") != nullptr), t0(now_s()), last(t0) {}
+void StageTimer::mark(const char *stage) {
+    if (!on) return;
+    const double t = now_s();
+    marks.emplace_back(stage, t - last);
+    last = t;
+}
+StageTimer::~StageTimer() {
+    if (!on) return;
+    fprintf(stderr, "[btb timing] %s: total %.3f s\n", what, now_s() - t0);
+    for (auto &m : marks) fprintf(stderr, "[btb timing]   %-28s %8.3f s\n", m.first.c_str(), m.second);
+}
 
 FileBytes::~FileBytes() {
     if (map_base) munmap(map_base, map_size);

@@ -41,6 +41,17 @@ int index_fasta(const FileBytes &fb, std::vector<FastaRecord> &recs, int threads
 // (or only counts them when out == nullptr).  Returns the sequence length.
 int64_t walk_record(const FileBytes &fb, const FastaRecord &r, uint8_t *out);
 
+// Wall-clock stage report for the level-1 calls: BTB_TIMING=1 prints one line per stage on stderr.
+struct StageTimer {
+    const char *what;
+    bool on;
+    double t0, last;
+    std::vector<std::pair<std::string, double>> marks;
+    explicit StageTimer(const char *what);
+    void mark(const char *stage);
+    ~StageTimer();
+};
+
 // Fast decimal formatting of one matrix row segment; returns bytes written.
 size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst);
 

@@ -135,11 +135,14 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
     (void)n_gpus;
     const int threads = std::max(1, host_threads);
+    StageTimer timer("btb_snp_sites");
     BTB_TRY(require_device(0));
+    timer.mark("device init");
     FileBytes fb;
     BTB_TRY(load_file(in_fasta, fb));
     std::vector<FastaRecord> recs;
     BTB_TRY(index_fasta(fb, recs, threads));
+    timer.mark("map + index records");
     const int64_t n = int64_t(recs.size());
     if (n == 0) {
         fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
@@ -196,6 +199,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     BTB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
     BTB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     bool used[2] = {false, false};
+    timer.mark("allocate device + pinned");
 
     // stage records [i0, i1) into buffer b; `force_walk` re-stages with the exact walk (unwrapped)
     auto run_chunk = [&](int b, int64_t i0, int64_t i1, bool force_walk) -> int {
@@ -257,6 +261,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     std::vector<int32_t> h_flags(static_cast<size_t>(n));
     BTB_CUDA(cudaMemcpyAsync(h_flags.data(), flags.p, size_t(n * 4), cudaMemcpyDeviceToHost, st.s));
     BTB_CUDA(cudaStreamSynchronize(st.s));
+    timer.mark("stage + H2D + k1 pack");
     for (int64_t i = 0; i < n; ++i) {
         if (!h_flags[size_t(i)]) continue;
         FastaRecord &r = recs[size_t(i)];
@@ -273,6 +278,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     int64_t L = 0;
     BTB_TRY(reduce_and_select(planes.as<uint32_t>(), n, G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(),
                               idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
+    timer.mark("k2 mask + k3 select");
     if (n_snps) *n_snps = L;
     if (L == 0) {
         fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
@@ -311,6 +317,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
         if (fwrite(text.data(), 1, size_t(p - text.data()), fo) != size_t(p - text.data())) rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str());
     }
     if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
+    timer.mark("k3 compact + D2H + write snps.fas");
     if (rc == BTB_OK && rename(tmp_path.c_str(), out_fasta) != 0) rc = fail(BTB_EIO, "cannot rename to '%s'", out_fasta);
     if (rc != BTB_OK) remove(tmp_path.c_str());
     return rc;

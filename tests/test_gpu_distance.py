@@ -166,3 +166,20 @@ def test_properties_at_scale(capi, oracle):
     for r in (0, 1, 4097, 8191):
         assert (a[r] == oracle.snp_dists_rows(seqs, threads=8, row0=r, row1=r + 1)[0]).all()
     assert a.max() < L
+
+
+def test_allchars_heavy_gap_content_at_scale(capi, oracle):
+    """BASELINE config 5 shape cut to 6,000 rows: 60,000 sites, 25 % N / gap, IUPAC codes, a few
+    lower-case bases, snp-dists -a.  AUTO engine; sampled rows equal the oracle, engines agree."""
+    from btb_phylo_b200 import device
+    n, L = 6000, 60000
+    seqs = synth.snp_alignment(n, L, seed=5, heavy_n=0.25, iupac=0.001, lower=0.001)
+    plan, a = gpu_matrix(capi, seqs, 1, 1, allchars=True)
+    assert plan.sigma >= 6
+    _, b = gpu_matrix(capi, seqs, 0, 0, allchars=True)
+    assert (a == b).all() and (a == a.T).all() and (np.diag(a) == 0).all()
+    for r in (0, 2999, 5999):
+        assert (a[r] == oracle.snp_dists_rows(seqs, allchars=True, threads=8, row0=r, row1=r + 1)[0]).all()
+    # default mode on the same bytes (N and gaps ignored)
+    _, c = gpu_matrix(capi, seqs, 1, 1, allchars=False)
+    assert (c[17] == oracle.snp_dists_rows(seqs, threads=8, row0=17, row1=18)[0]).all()
