@@ -255,21 +255,37 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         int64_t lo, hi;
         tile_share(tile_count(n), rank, world, lo, hi);
         L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 0, 1, st));
-        // copy back the owned tiles and their mirrors, merging runs of tiles in one block column
-        int64_t t = lo;
-        while (t < hi) {
-            int I, J, I2, J2;
-            tile_coords(T, t, I, J);
-            int64_t e = t + 1;
-            while (e < hi) { tile_coords(T, e, I2, J2); if (J2 != J || I2 != I + int(e - t)) break; ++e; }
-            const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + (e - t) * BTB_TILE);
-            const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + BTB_TILE);
-            char *ho = static_cast<char *>(out);
-            L2_CUDA(cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
-                                      size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, st));
-            L2_CUDA(cudaMemcpy2DAsync(ho + (c0 * out_ld + r0) * eb, size_t(out_ld) * eb, d_out + (c0 * d_ld + r0) * eb,
-                                      size_t(d_ld) * eb, size_t(r1 - r0) * eb, size_t(c1 - c0), cudaMemcpyDeviceToHost, st));
-            t = e;
+        // copy back what this rank computed: whole bands as two wide 2-D copies (the band's rows from
+        // its first column on, and the mirrored strip below), partial bands run by run
+        char *ho = static_cast<char *>(out);
+        auto copy2d = [&](int64_t r0, int64_t r1, int64_t c0, int64_t c1) -> cudaError_t {
+            if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+            return cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
+                                     size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, st);
+        };
+        int64_t first = 0;
+        for (int64_t b0 = 0; b0 < T; b0 += kBand) {
+            const int64_t w = std::min<int64_t>(kBand, T - b0), cnt = band_tiles(T, b0, w), last = first + cnt;
+            if (first >= lo && last <= hi) {
+                const int64_t row0 = b0 * BTB_TILE, row1 = std::min<int64_t>(n, (b0 + w) * BTB_TILE);
+                L2_CUDA(copy2d(row0, row1, row0, n));
+                L2_CUDA(copy2d(row1, n, row0, row1));
+            } else {
+                int64_t t = std::max(first, lo);
+                const int64_t stop = std::min(last, hi);
+                while (t < stop) {
+                    int I, J, I2, J2;
+                    tile_coords(T, t, I, J);
+                    int64_t e = t + 1;
+                    while (e < stop) { tile_coords(T, e, I2, J2); if (J2 != J || I2 != I + int(e - t)) break; ++e; }
+                    const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + (e - t) * BTB_TILE);
+                    const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + BTB_TILE);
+                    L2_CUDA(copy2d(r0, r1, c0, c1));
+                    L2_CUDA(copy2d(c0, c1, r0, r1));
+                    t = e;
+                }
+            }
+            first = last;
         }
     }
     L2_CUDA(cudaStreamSynchronize(st));
@@ -618,7 +634,9 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     fo = nullptr;
     if (!to_stdout && rename(tmp_path.c_str(), out_path) != 0) { rc = fail(BTB_EIO, "cannot rename to '%s'", out_path); cleanup(); return rc; }
+    timer.mark("close + rename");
     cleanup();
+    timer.mark("free device + pinned buffers");
     return BTB_OK;
 #undef L1_CUDA
 #undef L1_TRY

@@ -187,7 +187,8 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     // ---- chunks of consecutive records, each staged as one byte range of the file ------------
     size_t max_rec = 0;
     for (auto &r : recs) max_rec = std::max(max_rec, r.raw_len + 64);
-    const size_t chunk_cap = std::max<size_t>(size_t(256) << 20, max_rec + (size_t(G) + 64));
+    // 64 MB chunks keep the H2D pipeline busy; larger pinned buffers only cost allocation time
+    const size_t chunk_cap = std::max<size_t>(size_t(64) << 20, max_rec + (size_t(G) + 64));
     PinnedBuf h_text[2];
     BTB_TRY(h_text[0].alloc(chunk_cap + 64));
     BTB_TRY(h_text[1].alloc(chunk_cap + 64));
