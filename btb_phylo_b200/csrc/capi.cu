@@ -633,6 +633,8 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     timer.mark("D2H + format + write snps.csv");
     if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     fo = nullptr;
+    // unlink first: replacing an existing file by rename makes ext4 flush the new file's data synchronously
+    if (!to_stdout) unlink(out_path);
     if (!to_stdout && rename(tmp_path.c_str(), out_path) != 0) { rc = fail(BTB_EIO, "cannot rename to '%s'", out_path); cleanup(); return rc; }
     timer.mark("close + rename");
     cleanup();

@@ -30,8 +30,11 @@ int g_pack_wpt = 4;                                     // plane words per threa
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 
-// smem skew: 4 bytes of padding per 32 so that threads 32..36 bytes apart hit distinct banks
-__device__ __forceinline__ uint32_t skew(uint32_t p) { return p + ((p >> 5) << 2); }
+// smem skew: 4 bytes of padding per 32 so that threads 32..36 bytes apart hit distinct banks.  Needed
+// when a thread owns 32 columns (neighbours 8.25 words apart); with 128 columns per thread the
+// neighbours are 33-34 words apart, which is conflict-free as it is.
+template <bool SKEW>
+__device__ __forceinline__ uint32_t skew(uint32_t p) { return SKEW ? p + ((p >> 5) << 2) : p; }
 
 __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     uint4 v;
@@ -53,17 +56,21 @@ __host__ __device__ inline int plane_bit(int cl) { return 8 * (cl & 3) + (cl >> 
 // hi3 collects bit5|bit6|bit7 of every byte at bit 5: a byte < 0x20 (control character, e.g. a
 // stray CR/LF inside a line) clears it.
 struct Class4 { uint32_t v, b0, b1, hi3; };
+// The bits of every byte lane are lined up at bit 7 with LEFT shifts (the compiler issues them as
+// IMAD.SHL on the FMA pipe, leaving the ALU pipe to the LOP3s); the three flags are then moved to
+// bit 0 of their lane.  hi3 keeps bit5|bit6|bit7 of every byte at bit 7.
 __device__ __forceinline__ Class4 classify4(uint32_t w) {
-    const uint32_t x1 = w >> 1, x2 = w >> 2, x3 = w >> 3, x4 = w >> 4, x6 = w >> 6, x7 = w >> 7;
-    const uint32_t t1 = w & (x1 | ~x2);
-    const uint32_t t2 = x2 & ~x1 & ~w;
-    const uint32_t f = (~x4 & t1) | (x4 & t2);
-    const uint32_t g = ~x7 & x6 & ~x3;
+    const uint32_t y0 = w << 7, y1 = w << 6, y2 = w << 5, y3 = w << 4, y4 = w << 3, y5 = w << 2, y6 = w << 1;
+    const uint32_t t1 = y0 & (y1 | ~y2);
+    const uint32_t t2 = y2 & ~y1 & ~y0;
+    const uint32_t f = (~y4 & t1) | (y4 & t2);
+    const uint32_t g = ~w & y6 & ~y3;
+    const uint32_t v7 = f & g & 0x80808080u;
     Class4 c;
-    c.v = f & g & 0x01010101u;
-    c.b0 = c.v & x1;
-    c.b1 = c.v & x2;
-    c.hi3 = w | x1 | x2;
+    c.v = v7 >> 7;
+    c.b0 = (v7 & y1) >> 7;
+    c.b1 = (v7 & y2) >> 7;
+    c.hi3 = w | y6 | y5;
     return c;
 }
 
@@ -73,6 +80,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
                    const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t first,
                    int64_t n_total, int64_t G, int64_t words, uint32_t *__restrict__ planes,
                    int32_t *__restrict__ flags) {
+    constexpr bool kSkew = kPackWordsPerThread == 1;
     constexpr int kPackCols = PackCfg<kPackWordsPerThread>::kCols;
     constexpr int kPackStageBytes = PackCfg<kPackWordsPerThread>::kStageBytes;
     __shared__ __align__(16) uint8_t stage[kPackStageBytes + kPackStageBytes / 8 + 64];
@@ -105,15 +113,15 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
         uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
         if (alo + 16 * int64_t(j) < text_bytes) v = ld_nc_v4(text + alo + 16 * int64_t(j));
-        uint32_t *d = reinterpret_cast<uint32_t *>(stage + skew(16u * j));
+        uint32_t *d = reinterpret_cast<uint32_t *>(stage + skew<kSkew>(16u * j));
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
-    auto word_at = [&](uint32_t q) { return sw[q + (q >> 3)]; };            // q = unskewed word index
+    auto word_at = [&](uint32_t q) { return sw[kSkew ? q + (q >> 3) : q]; };     // q = unskewed word index
     const uint32_t c = cb + 32u * kPackWordsPerThread * threadIdx.x;
     uint32_t out_v[kPackWordsPerThread], out_0[kPackWordsPerThread], out_1[kPackWordsPerThread];
-    uint32_t nonctl = 0x20202020u;
+    uint32_t nonctl = 0x80808080u;
     bool irregular = false;
     const uint32_t line = (W && c < ce) ? c / W : 0u;
     uint32_t pos = W ? c - line * W : 0u;                  // column inside the current line
@@ -129,30 +137,37 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             // end per word since W >= 32).  A[g] reads group g before the line end, B[g] after it.
             const uint32_t rem = W ? W - pos : 0xFFFFu;
             const uint32_t qa = o >> 2, sa = (o & 3u) * 8u, ob = o + e, qb = ob >> 2, sb = (ob & 3u) * 8u;
-            uint32_t pa = word_at(qa), pb = word_at(qb);
+            // groups are visited last to first so that the plane words build up as F = 2 F + flags
+            // (an IMAD on the FMA pipe): group g ends at bit g of its byte lane
+            const uint32_t bg = rem >> 2, bm = (1u << (8u * (rem & 3u))) - 1u;       // break group / its byte mask
+            const bool partial = ncols < 32u;              // only the last word of a row
+            uint32_t tail[8];
+            if (partial) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint32_t na = word_at(qa + g + 1), nb = word_at(qb + g + 1);
-                const uint32_t A = __funnelshift_r(pa, na, sa), B = __funnelshift_r(pb, nb, sb);
-                pa = na; pb = nb;
-                // bytes of this group that still belong to the current line: rem - 4g clamped to 0..4
-                const int keep = int(rem) - 4 * g;
-                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : (keep <= 0 ? 0u : (1u << (8 * keep)) - 1u);
-                uint32_t w = (A & m) | (B & ~m);
-                if (ncols < 32u) {                          // last word of the row: blank out columns >= G
+                for (int g = 0; g < 8; ++g) {
                     const int have = int(ncols) - 4 * g;
-                    const uint32_t hm = have >= 4 ? 0xFFFFFFFFu : (have <= 0 ? 0u : (1u << (8 * have)) - 1u);
-                    w = (w & hm) | (0x20202020u & ~hm);
+                    tail[g] = have >= 4 ? 0xFFFFFFFFu : (have <= 0 ? 0u : (1u << (8 * have)) - 1u);
                 }
+            }
+            uint32_t na = word_at(qa + 8), nb = word_at(qb + 8);
+#pragma unroll
+            for (int g = 7; g >= 0; --g) {
+                const uint32_t ca = word_at(qa + g), cbw = word_at(qb + g);
+                const uint32_t A = __funnelshift_r(ca, na, sa), B = __funnelshift_r(cbw, nb, sb);
+                na = ca; nb = cbw;
+                // bytes of this group that still belong to the current line come from A, the rest from B
+                const uint32_t m = uint32_t(g) < bg ? 0xFFFFFFFFu : (uint32_t(g) == bg ? bm : 0u);
+                uint32_t w = (A & m) | (B & ~m);
+                if (partial) w = (w & tail[g]) | (0x20202020u & ~tail[g]);     // last word of the row: blank columns >= G
                 const Class4 k = classify4(w);
-                fv |= k.v << g; f0 |= k.b0 << g; f1 |= k.b1 << g;
+                fv = fv * 2u + k.v; f0 = f0 * 2u + k.b0; f1 = f1 * 2u + k.b1;
                 nonctl &= k.hi3;
             }
             if (rem <= ncols) {                             // a line ends inside (or exactly at the end of) this word
                 if (cw + rem < G32) {                       // ... and more bases follow: the terminator must be there
                     const uint32_t t = o + rem;
-                    if (e == 1) irregular |= stage[skew(t)] != '\n';
-                    else irregular |= (stage[skew(t)] != '\r') | (stage[skew(t + 1)] != '\n');
+                    if (e == 1) irregular |= stage[skew<kSkew>(t)] != '\n';
+                    else irregular |= (stage[skew<kSkew>(t)] != '\r') | (stage[skew<kSkew>(t + 1)] != '\n');
                 }
                 o += 32u + e;
                 pos = 32u - rem;
@@ -173,7 +188,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             for (int k = 0; k < kPackWordsPerThread; ++k) { p0[k] = out_0[k]; p1[k] = out_1[k]; pv[k] = out_v[k]; }
         }
     }
-    if (irregular || (nonctl & 0x20202020u) != 0x20202020u) atomicOr(&flags[i], 1);
+    if (irregular || (nonctl & 0x80808080u) != 0x80808080u) atomicOr(&flags[i], 1);
 }
 
 // ------------------------------------------------------------------------------------------ k2

@@ -3,6 +3,8 @@
 // per-base decision is taken by the kernels in extract.cu.
 //
 // Reference call site: btbphylo/phylogeny.py:133  `snp-sites <multi_fasta> -c -o <snps.fas>`.
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstring>
 #include <functional>
@@ -319,6 +321,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     }
     if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
     timer.mark("k3 compact + D2H + write snps.fas");
+    if (rc == BTB_OK) unlink(out_fasta);                // see btb_snp_dists: avoid the replace-by-rename flush
     if (rc == BTB_OK && rename(tmp_path.c_str(), out_fasta) != 0) rc = fail(BTB_EIO, "cannot rename to '%s'", out_fasta);
     if (rc != BTB_OK) remove(tmp_path.c_str());
     return rc;
