@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -130,12 +131,135 @@ extern "C" int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64
     return BTB_OK;
 }
 
+namespace {
+
+// One device's share of the extraction stage: samples [s0, s1) of the file, their planes and the
+// staging pipeline (host threads copy record bytes into pinned chunks, H2D, k1).
+struct ExtractCtx {
+    int dev = 0, threads = 1, rc = BTB_OK;
+    std::string err;
+    int64_t s0 = 0, s1 = 0, nloc = 0, L = 0;
+    Stream st;
+    DeviceBuf planes, state, keepw, idx, count, flags, d_off, d_lw, d_el, d_text[2], snps;
+    PinnedBuf h_text[2];
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    size_t chunk_cap = 0;
+    std::vector<int64_t> h_off;
+    std::vector<int32_t> h_lw, h_el;
+
+    ~ExtractCtx() {
+        for (int k = 0; k < 2; ++k)
+            if (done[k]) cudaEventDestroy(done[k]);
+    }
+
+    int setup(const std::vector<FastaRecord> &recs, int64_t G, int64_t words) {
+        nloc = s1 - s0;
+        BTB_TRY(st.create());
+        BTB_TRY(planes.alloc(size_t(3 * nloc * words * 4)));
+        BTB_TRY(state.alloc(size_t(5 * words * 4)));
+        BTB_TRY(keepw.alloc(size_t(words * 4)));
+        BTB_TRY(idx.alloc(size_t(words * 32 * 4)));
+        BTB_TRY(count.alloc(16));
+        BTB_TRY(flags.alloc(size_t(nloc * 4)));
+        BTB_TRY(d_off.alloc(size_t(nloc * 8)));
+        BTB_TRY(d_lw.alloc(size_t(nloc * 4)));
+        BTB_TRY(d_el.alloc(size_t(nloc * 4)));
+        BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(nloc * 4), st.s));
+        size_t max_rec = 0;
+        for (int64_t i = s0; i < s1; ++i) max_rec = std::max(max_rec, recs[size_t(i)].raw_len + 64);
+        // 64 MB chunks keep the H2D pipeline busy; larger pinned buffers only cost allocation time
+        chunk_cap = std::max<size_t>(size_t(64) << 20, max_rec + (size_t(G) + 64));
+        for (int k = 0; k < 2; ++k) {
+            BTB_TRY(h_text[k].alloc(chunk_cap + 64));
+            BTB_TRY(d_text[k].alloc(chunk_cap + 64));
+            BTB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        }
+        h_off.assign(size_t(nloc), 0);
+        h_lw.assign(size_t(nloc), 0);
+        h_el.assign(size_t(nloc), 0);
+        return BTB_OK;
+    }
+
+    // stage records [i0, i1) (global indices) into buffer b; `force_walk` re-stages with the exact walk
+    int run_chunk(const FileBytes &fb, const std::vector<FastaRecord> &recs, int64_t G, int b, int64_t i0, int64_t i1, bool force_walk) {
+        if (used[b]) BTB_CUDA(cudaEventSynchronize(done[b]));
+        uint8_t *dst = h_text[b].as<uint8_t>();
+        size_t pos = 0;
+        std::vector<size_t> at(static_cast<size_t>(i1 - i0));
+        for (int64_t i = i0; i < i1; ++i) {
+            const FastaRecord &r = recs[size_t(i)];
+            const bool walk = force_walk || !r.regular;
+            at[size_t(i - i0)] = pos;
+            h_off[size_t(i - s0)] = int64_t(pos);
+            h_lw[size_t(i - s0)] = walk ? 0 : r.line_w;
+            h_el[size_t(i - s0)] = walk ? 0 : r.eol;
+            pos += walk ? size_t(G) : r.raw_len;
+            pos = (pos + 15) & ~size_t(15);
+        }
+        const size_t total = pos;
+        parallel_for(i1 - i0, threads, [&](int64_t lo, int64_t hi) {
+            for (int64_t k = lo; k < hi; ++k) {
+                const FastaRecord &r = recs[size_t(i0 + k)];
+                if (force_walk || !r.regular) walk_record(fb, r, dst + at[size_t(k)]);
+                else memcpy(dst + at[size_t(k)], fb.data + r.seq_off, r.raw_len);
+            }
+        });
+        const int64_t l0 = i0 - s0, cnt = i1 - i0;
+        BTB_CUDA(cudaMemcpyAsync(d_text[b].p, dst, total + 16, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + l0, h_off.data() + l0, size_t(cnt) * 8, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_lw.as<int32_t>() + l0, h_lw.data() + l0, size_t(cnt) * 4, cudaMemcpyHostToDevice, st.s));
+        BTB_CUDA(cudaMemcpyAsync(d_el.as<int32_t>() + l0, h_el.data() + l0, size_t(cnt) * 4, cudaMemcpyHostToDevice, st.s));
+        BTB_TRY(btb_pack_planes(d_text[b].as<uint8_t>(), int64_t(total), d_off.as<int64_t>() + l0, d_lw.as<int32_t>() + l0,
+                                d_el.as<int32_t>() + l0, cnt, l0, nloc, G, planes.as<uint32_t>(), flags.as<int32_t>() + l0, st.s));
+        BTB_CUDA(cudaEventRecord(done[b], st.s));
+        used[b] = true;
+        return BTB_OK;
+    }
+
+    // packs every sample of this device; *bad gets the global index of a record whose exact length
+    // turned out different from G (reported by the caller in file order)
+    int pack_all(const FileBytes &fb, std::vector<FastaRecord> &recs, int64_t G, int64_t *bad) {
+        int b = 0;
+        for (int64_t i0 = s0; i0 < s1;) {
+            size_t bytes = 0;
+            int64_t i1 = i0;
+            while (i1 < s1) {
+                const FastaRecord &r = recs[size_t(i1)];
+                const size_t need = (!r.regular ? size_t(G) : r.raw_len) + 16;
+                if (i1 > i0 && bytes + need > chunk_cap) break;
+                bytes += need;
+                ++i1;
+            }
+            BTB_TRY(run_chunk(fb, recs, G, b, i0, i1, false));
+            b ^= 1;
+            i0 = i1;
+        }
+        // records whose terminators were not where their first line promised: exact walk, pack again
+        std::vector<int32_t> h_flags(static_cast<size_t>(nloc));
+        BTB_CUDA(cudaMemcpyAsync(h_flags.data(), flags.p, size_t(nloc * 4), cudaMemcpyDeviceToHost, st.s));
+        BTB_CUDA(cudaStreamSynchronize(st.s));
+        for (int64_t i = s0; i < s1; ++i) {
+            if (!h_flags[size_t(i - s0)]) continue;
+            FastaRecord &r = recs[size_t(i)];
+            r.seq_len = walk_record(fb, r, nullptr);
+            r.regular = false;
+            if (r.seq_len != G) { *bad = i; return BTB_OK; }
+            BTB_TRY(run_chunk(fb, recs, G, b, i, i + 1, true));
+            b ^= 1;
+        }
+        BTB_CUDA(cudaStreamSynchronize(st.s));
+        return BTB_OK;
+    }
+};
+
+}  // namespace
+
 // =============================================================================== level 1
 extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode, int n_gpus,
                              int host_threads, int64_t *n_samples, int64_t *genome_len, int64_t *n_snps) {
     if (!in_fasta || !out_fasta) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
     if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
-    (void)n_gpus;
     const int threads = std::max(1, host_threads);
     StageTimer timer("btb_snp_sites");
     BTB_TRY(require_device(0));
@@ -170,157 +294,113 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
         return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
     }
 
-    Stream st, st2;
-    BTB_TRY(st.create());
-    BTB_TRY(st2.create());
+    // ---- devices: samples are dealt to the GPUs as contiguous record ranges of equal bytes ---------
+    int usable = 0;
+    btb_device_count(&usable);
+    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(std::min(n_gpus, usable), n)));
     const int64_t words = btb_plane_words(G);
-    DeviceBuf planes, state, keepw, idx, count, flags, d_off, d_lw, d_el, d_text[2], snps;
-    BTB_TRY(planes.alloc(size_t(3 * n * words * 4)));
-    BTB_TRY(state.alloc(size_t(5 * words * 4)));
-    BTB_TRY(keepw.alloc(size_t(words * 4)));
-    BTB_TRY(idx.alloc(size_t(words * 32 * 4)));
-    BTB_TRY(count.alloc(16));
-    BTB_TRY(flags.alloc(size_t(n * 4)));
-    BTB_TRY(d_off.alloc(size_t(n * 8)));
-    BTB_TRY(d_lw.alloc(size_t(n * 4)));
-    BTB_TRY(d_el.alloc(size_t(n * 4)));
-    BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(n * 4), st.s));
-
-    // ---- chunks of consecutive records, each staged as one byte range of the file ------------
-    size_t max_rec = 0;
-    for (auto &r : recs) max_rec = std::max(max_rec, r.raw_len + 64);
-    // 64 MB chunks keep the H2D pipeline busy; larger pinned buffers only cost allocation time
-    const size_t chunk_cap = std::max<size_t>(size_t(64) << 20, max_rec + (size_t(G) + 64));
-    PinnedBuf h_text[2];
-    BTB_TRY(h_text[0].alloc(chunk_cap + 64));
-    BTB_TRY(h_text[1].alloc(chunk_cap + 64));
-    BTB_TRY(d_text[0].alloc(chunk_cap + 64));
-    BTB_TRY(d_text[1].alloc(chunk_cap + 64));
-    std::vector<int64_t> h_off(static_cast<size_t>(n));
-    std::vector<int32_t> h_lw(static_cast<size_t>(n)), h_el(static_cast<size_t>(n));
-    cudaEvent_t done[2];
-    BTB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    BTB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    bool used[2] = {false, false};
-    timer.mark("allocate device + pinned");
-
-    // stage records [i0, i1) into buffer b; `force_walk` re-stages with the exact walk (unwrapped)
-    auto run_chunk = [&](int b, int64_t i0, int64_t i1, bool force_walk) -> int {
-        if (used[b]) BTB_CUDA(cudaEventSynchronize(done[b]));
-        uint8_t *dst = h_text[b].as<uint8_t>();
-        // layout pass (serial, cheap): where each record lands in the staging buffer
-        size_t pos = 0;
-        std::vector<size_t> at(static_cast<size_t>(i1 - i0));
-        for (int64_t i = i0; i < i1; ++i) {
-            const FastaRecord &r = recs[size_t(i)];
-            const bool walk = force_walk || !r.regular;
-            at[size_t(i - i0)] = pos;
-            h_off[size_t(i)] = int64_t(pos);
-            h_lw[size_t(i)] = walk ? 0 : r.line_w;
-            h_el[size_t(i)] = walk ? 0 : r.eol;
-            pos += walk ? size_t(G) : r.raw_len;
-            pos = (pos + 15) & ~size_t(15);
-        }
-        const size_t total = pos;
-        parallel_for(i1 - i0, threads, [&](int64_t lo, int64_t hi) {
-            for (int64_t k = lo; k < hi; ++k) {
-                const FastaRecord &r = recs[size_t(i0 + k)];
-                if (force_walk || !r.regular) walk_record(fb, r, dst + at[size_t(k)]);
-                else memcpy(dst + at[size_t(k)], fb.data + r.seq_off, r.raw_len);
+    std::vector<ExtractCtx> ctx(static_cast<size_t>(n_dev));
+    {
+        size_t total_bytes = 0;
+        for (auto &r : recs) total_bytes += r.raw_len;
+        size_t acc = 0;
+        int d = 0;
+        ctx[0].s0 = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            acc += recs[size_t(i)].raw_len;
+            while (d + 1 < n_dev && acc >= total_bytes * size_t(d + 1) / size_t(n_dev) && i + 1 < n && (n - i - 1) >= (n_dev - d - 1)) {
+                ctx[size_t(d)].s1 = i + 1;
+                ctx[size_t(++d)].s0 = i + 1;
             }
-        });
-        BTB_CUDA(cudaMemcpyAsync(d_text[b].p, dst, total + 16, cudaMemcpyHostToDevice, st.s));
-        BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + i0, h_off.data() + i0, size_t(i1 - i0) * 8, cudaMemcpyHostToDevice, st.s));
-        BTB_CUDA(cudaMemcpyAsync(d_lw.as<int32_t>() + i0, h_lw.data() + i0, size_t(i1 - i0) * 4, cudaMemcpyHostToDevice, st.s));
-        BTB_CUDA(cudaMemcpyAsync(d_el.as<int32_t>() + i0, h_el.data() + i0, size_t(i1 - i0) * 4, cudaMemcpyHostToDevice, st.s));
-        BTB_TRY(btb_pack_planes(d_text[b].as<uint8_t>(), int64_t(total), d_off.as<int64_t>() + i0, d_lw.as<int32_t>() + i0,
-                                d_el.as<int32_t>() + i0, i1 - i0, i0, n, G, planes.as<uint32_t>(),
-                                flags.as<int32_t>() + i0, st.s));
-        BTB_CUDA(cudaEventRecord(done[b], st.s));
-        used[b] = true;
+        }
+        ctx[size_t(d)].s1 = n;
+        for (int k = d + 1; k < n_dev; ++k) ctx[size_t(k)].s0 = ctx[size_t(k)].s1 = n;
+    }
+    for (int d = 0; d < n_dev; ++d) { ctx[size_t(d)].dev = d; ctx[size_t(d)].threads = std::max(1, threads / n_dev); }
+    auto for_each_device = [&](const std::function<int(ExtractCtx &)> &fn) -> int {
+        if (n_dev == 1) { int rc = fn(ctx[0]); return rc; }
+        std::vector<std::thread> pool;
+        for (int d = 0; d < n_dev; ++d)
+            pool.emplace_back([&, d] { ctx[size_t(d)].rc = fn(ctx[size_t(d)]); if (ctx[size_t(d)].rc) ctx[size_t(d)].err = last_error(); });
+        for (auto &t : pool) t.join();
+        for (int d = 0; d < n_dev; ++d)
+            if (ctx[size_t(d)].rc) return fail(ctx[size_t(d)].rc, "%s", ctx[size_t(d)].err.c_str());
         return BTB_OK;
     };
-    auto chunk_end = [&](int64_t i0, bool force_walk) {
-        size_t bytes = 0;
-        int64_t i = i0;
-        while (i < n) {
-            const FastaRecord &r = recs[size_t(i)];
-            const size_t need = ((force_walk || !r.regular) ? size_t(G) : r.raw_len) + 16;
-            if (i > i0 && bytes + need > chunk_cap) break;
-            bytes += need;
-            ++i;
-        }
-        return i;
-    };
-    int b = 0;
-    for (int64_t i0 = 0; i0 < n;) {
-        const int64_t i1 = chunk_end(i0, false);
-        int rc = run_chunk(b, i0, i1, false);
-        if (rc != BTB_OK) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return rc; }
-        b ^= 1;
-        i0 = i1;
-    }
-    // records whose terminators were not where their first line promised: exact walk, pack again
-    std::vector<int32_t> h_flags(static_cast<size_t>(n));
-    BTB_CUDA(cudaMemcpyAsync(h_flags.data(), flags.p, size_t(n * 4), cudaMemcpyDeviceToHost, st.s));
-    BTB_CUDA(cudaStreamSynchronize(st.s));
-    timer.mark("stage + H2D + k1 pack");
-    for (int64_t i = 0; i < n; ++i) {
-        if (!h_flags[size_t(i)]) continue;
-        FastaRecord &r = recs[size_t(i)];
-        r.seq_len = walk_record(fb, r, nullptr);
-        r.regular = false;
-        if (r.seq_len != G) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return unequal(r); }
-        int rc = run_chunk(b, i, i + 1, true);
-        if (rc != BTB_OK) { cudaEventDestroy(done[0]); cudaEventDestroy(done[1]); return rc; }
-        b ^= 1;
-    }
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
 
+    // phase 1: pack this device's samples, reduce them to a local column state, copy it to the host
+    std::vector<std::vector<uint32_t>> h_state(static_cast<size_t>(n_dev), std::vector<uint32_t>(size_t(5 * words), 0));
+    int bad_record = -1;
+    std::mutex bad_mutex;
+    BTB_TRY(for_each_device([&](ExtractCtx &c) -> int {
+        if (c.s1 <= c.s0) return BTB_OK;
+        BTB_TRY(require_device(c.dev));
+        BTB_TRY(c.setup(recs, G, words));
+        int64_t bad = -1;
+        BTB_TRY(c.pack_all(fb, recs, G, &bad));
+        if (bad >= 0) { std::lock_guard<std::mutex> lock(bad_mutex); if (bad_record < 0 || bad < bad_record) bad_record = int(bad); return BTB_OK; }
+        BTB_TRY(btb_column_mask(c.planes.as<uint32_t>(), c.nloc, c.nloc, G, c.state.as<uint32_t>(), 0, c.st.s));
+        BTB_CUDA(cudaMemcpyAsync(h_state[size_t(c.dev)].data(), c.state.p, size_t(5 * words * 4), cudaMemcpyDeviceToHost, c.st.s));
+        BTB_CUDA(cudaStreamSynchronize(c.st.s));
+        return BTB_OK;
+    }));
+    if (bad_record >= 0) return unequal(recs[size_t(bad_record)]);
+    timer.mark("stage + H2D + k1 pack + k2 mask");
+
+    // exchange: OR the per-device column states on the host (5 words per 32 columns, a few MB)
+    for (int d = 1; d < n_dev; ++d)
+        for (size_t k = 0; k < h_state[0].size(); ++k) h_state[0][k] |= h_state[size_t(d)][k];
+
+    // phase 2: every device selects the kept columns from the combined state
     int64_t L = 0;
-    BTB_TRY(reduce_and_select(planes.as<uint32_t>(), n, G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(),
-                              idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
-    timer.mark("k2 mask + k3 select");
+    BTB_TRY(for_each_device([&](ExtractCtx &c) -> int {
+        if (c.s1 <= c.s0) return BTB_OK;
+        BTB_TRY(require_device(c.dev));
+        if (n_dev > 1) BTB_CUDA(cudaMemcpyAsync(c.state.p, h_state[0].data(), size_t(5 * words * 4), cudaMemcpyHostToDevice, c.st.s));
+        BTB_TRY(btb_select_columns(c.state.as<uint32_t>(), G, pure_mode, c.keepw.as<uint32_t>(), c.idx.as<uint32_t>(), c.count.as<uint32_t>(), c.st.s));
+        uint32_t l = 0;
+        BTB_CUDA(cudaMemcpyAsync(&l, c.count.p, 4, cudaMemcpyDeviceToHost, c.st.s));
+        BTB_CUDA(cudaStreamSynchronize(c.st.s));
+        c.L = l;
+        return BTB_OK;
+    }));
+    L = ctx[0].L;
+    timer.mark("exchange + k3 select");
     if (n_snps) *n_snps = L;
     if (L == 0) {
         fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
         return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
     }
-    // ---- gather + write: >name\n + L bases + \n per sample, one line per sequence -------------
+
+    // phase 3: gather the kept columns of every sample into one pinned host matrix
     const int64_t ld = (L + 15) / 16 * 16;
-    const int64_t block = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(128) << 20) / ld));
-    BTB_TRY(snps.alloc(size_t(block * ld)));
-    PinnedBuf h_snps;
-    BTB_TRY(h_snps.alloc(size_t(block * ld)));
+    PinnedBuf h_rows;
+    BTB_TRY(h_rows.alloc(size_t(n * ld)));
+    BTB_TRY(for_each_device([&](ExtractCtx &c) -> int {
+        if (c.s1 <= c.s0) return BTB_OK;
+        BTB_TRY(require_device(c.dev));
+        BTB_TRY(c.snps.alloc(size_t(c.nloc * ld)));
+        BTB_TRY(btb_compact_columns(c.planes.as<uint32_t>(), 0, c.nloc, c.nloc, G, c.idx.as<uint32_t>(), L, c.snps.as<uint8_t>(), ld, c.st.s));
+        BTB_CUDA(cudaMemcpyAsync(h_rows.as<uint8_t>() + c.s0 * ld, c.snps.p, size_t(c.nloc * ld), cudaMemcpyDeviceToHost, c.st.s));
+        BTB_CUDA(cudaStreamSynchronize(c.st.s));
+        return BTB_OK;
+    }));
+    timer.mark("k3 compact + D2H");
+
+    // ---- write: >name\n + L bases + \n per sample, one line per sequence --------------------------
     std::string tmp_path = std::string(out_fasta) + ".tmp";
     FILE *fo = fopen(tmp_path.c_str(), "wb");
     if (!fo) return fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str());
     setvbuf(fo, nullptr, _IOFBF, 1 << 22);
-    std::vector<char> text;
     int rc = BTB_OK;
-    for (int64_t r0 = 0; r0 < n && rc == BTB_OK; r0 += block) {
-        const int64_t rows = std::min(block, n - r0);
-        rc = btb_compact_columns(planes.as<uint32_t>(), r0, rows, n, G, idx.as<uint32_t>(), L, snps.as<uint8_t>(), ld, st.s);
-        if (rc != BTB_OK) break;
-        if (cudaMemcpyAsync(h_snps.p, snps.p, size_t(rows * ld), cudaMemcpyDeviceToHost, st.s) != cudaSuccess ||
-            cudaStreamSynchronize(st.s) != cudaSuccess) { rc = fail(BTB_ECUDA, "copying SNP rows back failed"); break; }
-        size_t need = 0;
-        for (int64_t r = 0; r < rows; ++r) need += recs[size_t(r0 + r)].name.size() + size_t(L) + 3;
-        text.resize(need);
-        char *p = text.data();
-        for (int64_t r = 0; r < rows; ++r) {
-            const std::string &nm = recs[size_t(r0 + r)].name;
-            *p++ = '>';
-            memcpy(p, nm.data(), nm.size()); p += nm.size();
-            *p++ = '\n';
-            memcpy(p, h_snps.as<char>() + r * ld, size_t(L)); p += L;
-            *p++ = '\n';
-        }
-        if (fwrite(text.data(), 1, size_t(p - text.data()), fo) != size_t(p - text.data())) rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str());
+    for (int64_t r = 0; r < n && rc == BTB_OK; ++r) {
+        const std::string &nm = recs[size_t(r)].name;
+        if (fputc('>', fo) == EOF || fwrite(nm.data(), 1, nm.size(), fo) != nm.size() || fputc('\n', fo) == EOF ||
+            fwrite(h_rows.as<char>() + r * ld, 1, size_t(L), fo) != size_t(L) || fputc('\n', fo) == EOF)
+            rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str());
     }
     if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
-    timer.mark("k3 compact + D2H + write snps.fas");
+    timer.mark("write snps.fas");
     if (rc == BTB_OK) unlink(out_fasta);                // see btb_snp_dists: avoid the replace-by-rename flush
     if (rc == BTB_OK && rename(tmp_path.c_str(), out_fasta) != 0) rc = fail(BTB_EIO, "cannot rename to '%s'", out_fasta);
     if (rc != BTB_OK) remove(tmp_path.c_str());

@@ -150,3 +150,24 @@ def test_multi_gpu_file_path_same_bytes(capi, oracle, tmp_path):
         outs.append(out.read_bytes())
     assert outs[0] == outs[1]
     assert outs[0] == oracle.format_matrix(names, oracle.snp_dists_rows(seqs, threads=8))
+
+
+def test_multi_gpu_snp_sites_same_bytes(capi, oracle, tmp_path):
+    """n_gpus = 2: samples are dealt to the devices, the per-device column states are OR-ed on the
+    host, every device compacts its own samples.  Same snps.fas as one GPU and as the oracle."""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, G = 37, 250007
+    names = synth.sample_names(n)
+    aln = synth.genome_alignment(n, G, 3000, seed=41, n_frac=0.02, lower=0.01)
+    mf = tmp_path / "multi_fasta.fas"
+    mf.write_bytes(synth.fasta_bytes(names, aln, wrap=[60, 70, 0, 31], eol=b"\n"))
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / ("snps_%d.fas" % gpus)
+        L = ctypes.c_int64(0)
+        capi.check(capi.lib().btb_snp_sites(str(mf).encode(), str(out).encode(), 1, gpus, 8, None, None, ctypes.byref(L)))
+        outs.append(out.read_bytes())
+    o_sf = tmp_path / "o.fas"
+    assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
+    assert outs[0] == outs[1] == o_sf.read_bytes()
