@@ -104,6 +104,7 @@ extern "C" int btb_device_count(int *count) {
 extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
+    if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_cg2_variant")) { g_umma_cg2_variant = value & 3; return BTB_OK; }
@@ -119,6 +120,7 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
     if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
     if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
+    if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
 }
 

@@ -247,6 +247,62 @@ encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
     }
 }
 
+// dense tetrahedron code as packed e2m1 nibbles (1.0 = 0x2): one thread per 16 sites -> 48 nibbles = 24 bytes
+__global__ void __launch_bounds__(256)
+encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                  const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned,
+                  int32_t *__restrict__ rowsum) {
+    __shared__ uint32_t vertex[256];                        // symbol -> its 3 nibbles (x | y << 4 | z << 8)
+    {
+        const uint32_t code = table_g[threadIdx.x];
+        vertex[threadIdx.x] = code == 1 ? 0x022u : code == 2 ? 0x202u : code == 3 ? 0x220u : 0u;
+    }
+    __syncthreads();
+    const int64_t groups = (kbytes + 23) / 24;
+    const bool vec_in = aligned && (row_stride % 16 == 0) && (reinterpret_cast<uintptr_t>(seqs) % 16 == 0);
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+        const uint8_t *p = seqs + row * row_stride;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(A + row * kbytes);
+        const int64_t total = kbytes / 4;
+        int nonzero = 0;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t site = g * 16;
+            uint32_t raw[4] = {0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu};
+            if (vec_in && site + 15 < len) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(p + site);
+                raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+            } else {
+                for (int b = 0; b < 16; ++b)
+                    if (site + b < len) raw[b >> 2] = (raw[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (uint32_t(p[site + b]) << (8 * (b & 3)));
+            }
+            uint32_t out[6];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                   // 8 sites -> 96 bits
+                uint64_t lo = 0, hi = 0;                    // bits 0..63, 64..95
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t byte = (raw[2 * h + (b >> 2)] >> (8 * (b & 3))) & 0xff;
+                    const uint64_t t = vertex[byte];
+                    nonzero += t != 0;
+                    const int sh = 12 * b;
+                    if (sh < 64) lo |= t << sh;
+                    if (sh + 12 > 64) hi |= sh >= 64 ? t << (sh - 64) : t >> (64 - sh);
+                }
+                out[3 * h + 0] = uint32_t(lo);
+                out[3 * h + 1] = uint32_t(lo >> 32);
+                out[3 * h + 2] = uint32_t(hi);
+            }
+            const int64_t wi = g * 6;
+            for (int k = 0; k < 6; ++k)
+                if (wi + k < total) dst[wi + k] = out[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nonzero += __shfl_xor_sync(0xffffffffu, nonzero, o);
+        if ((threadIdx.x & 31) == 0 && nonzero) atomicAdd(&rowsum[row], nonzero);
+    }
+}
+
 }  // namespace btb
 
 using namespace btb;
@@ -335,7 +391,12 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         const int64_t kb = umma_k_bytes(len, sigma);
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
-        if (sigma_dense(sigma) && g_umma_dense_simplex) {
+        if (umma_use_fp4(sigma)) {
+            dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
+            BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));
+            encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0, rowsum);
+        } else if (sigma_dense(sigma) && g_umma_dense_simplex) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
             if (g_umma_dense_simplex == 2) BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));

@@ -193,6 +193,7 @@ struct UmmaParams {
     int mirror;
     int dense;            // 0: out = acc; 1: out = bias - acc (one-hot matches); 2: out = (bias - acc) >> 2 (simplex)
     int32_t bias;         // len or 3 * len
+    int fp32acc;          // accumulators are fp32 (kind::mxf4): convert to integers first
     const int32_t *rowsum; // dense == 3: c_i, out = c_row + c_col - acc
     unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
@@ -209,6 +210,10 @@ __device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t 
     for (int c0 = 0; c0 < kAccCols; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c0), v);
+        if (p.fp32acc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = uint32_t(__float2int_rn(__uint_as_float(v[j])));
+        }
         if (p.dense == 3) {
             const int32_t cr = row < p.n ? p.rowsum[row] : 0;
 #pragma unroll
@@ -609,6 +614,146 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP4 variant (experimental, dense alignments only): the 0/1 tetrahedron code stored as packed
+// e2m1 nibbles and multiplied with tcgen05.mma kind::mxf4.block_scale (K = 64 per instruction,
+// twice the int8 rate).  All block scale factors are 1.0 (UE8M0 0x7F): a 16-column TMEM region is
+// filled with 0x7F7F7F7F once, so its layout does not matter.  fp32 accumulators hold exact
+// integers (sums of 0/1 products < 2^24).  Unit of work = one 128-row half tile (UMMA 128x256x64),
+// one accumulator buffer (columns 0..255) + the scale-factor columns: the epilogue of a unit is not
+// overlapped with the next unit's K loop.
+__device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(v) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// block-scaled instruction descriptor, kind::mxf4: A/B = E2M1 (1 at [7,10) / [10,13)), K-major,
+// N>>3 at [17,23), scale format UE8M0 (1 at bit 23), M>>4 at [24,29), scale-factor ids 0, K64 dense
+__host__ __device__ constexpr uint32_t make_mxf4_idesc(int M, int N) {
+    return (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (1u << 23) | (uint32_t(M >> 4) << 24);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const UmmaParams p) {
+    using Cfg = UmmaCfg<1>;                                  // A 128 rows + B 256 rows per 128-byte K atom, 4 stages
+    constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t kSfCol = 256;                         // scale factors: TMEM columns 256..271
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * kStages);
+    const uint32_t tempty_bar = bar_base + 8u * (2 * kStages + 1);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t worker = blockIdx.x, n_workers = gridDim.x;
+    const int64_t T = tiles_per_dim(p.n);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp >= 4) tmem_st_32x32_x16(tmem_base + (uint32_t((warp & 3) * 32) << 16) + kSfCol, 0x7F7F7F7Fu);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    auto unit_coords = [&](int64_t u, int64_t &m0, int64_t &n0, int &I, int &J, int &half) {
+        half = int(u & 1);
+        tile_coords(T, p.tile_lo + u / 2, I, J);
+        m0 = int64_t(I) * BTB_TILE + half * 128;
+        n0 = int64_t(J) * BTB_TILE;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers) {
+                int64_t m0, n0; int I, J, half;
+                unit_coords(u, m0, n0, I, J, half);
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), int(m0));
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), int(n0));
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_mxf4_idesc(128, kAccCols);
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            mbar_wait(tempty_bar, (uint32_t(it) & 1u) ^ 1u);
+            tc_fence_after();
+            for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)               // 4 x 64 nibbles = 128 bytes
+                        umma_mxf4(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
+                                  tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit<1>(empty_bar(stage));
+                    if (kb == p.k_blocks - 1) umma_commit<1>(tfull_bar);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            int64_t m0, n0; int I, J, half;
+            unit_coords(u, m0, n0, I, J, half);
+            mbar_wait(tfull_bar, uint32_t(it) & 1u);
+            tc_fence_after();
+            const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
+            drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16), m0 + quarter * 32 + lane, n0,
+                                    half * 128 + quarter * 32 + lane, u / 2, do_mirror);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(tempty_bar);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -644,6 +789,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
+int g_umma_fp4 = 0;            // experimental kind::mxf4 path for dense alignments (see common.cuh)
 int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
 int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
@@ -770,6 +916,29 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
+    if (umma_use_fp4(sigma)) {
+        BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
+        BTB_TRY(make_operand_map(&mb, A, n, kb, 256));
+        UmmaParams p;
+        p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles * 2;
+        p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1;
+        p.dense = 3; p.bias = 0;
+        p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+        int dev = 0, sms = 0;
+        BTB_CUDA(cudaGetDevice(&dev));
+        BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+        if (out_elem_bytes == 2) {
+            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
+            dist_umma_fp4_kernel<uint16_t><<<ctas, kThreads, UmmaCfg<1>::kSmemBytes, stream>>>(ma, mb, p);
+        } else {
+            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
+            dist_umma_fp4_kernel<uint32_t><<<ctas, kThreads, UmmaCfg<1>::kSmemBytes, stream>>>(ma, mb, p);
+        }
+        BTB_CUDA(cudaGetLastError());
+        return BTB_OK;
+    }
     int sms_now = 148, dev_now = 0;
     if (cudaGetDevice(&dev_now) == cudaSuccess) cudaDeviceGetAttribute(&sms_now, cudaDevAttrMultiProcessorCount, dev_now);
     // full tiles only pay off once every SM gets at least two of them; small problems keep the
@@ -780,7 +949,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         UmmaParams p;
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0;
         p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
         p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
@@ -801,6 +970,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.mirror = mirror;
     p.dbg = nullptr;
     p.lockstep = nullptr;
+    p.fp32acc = 0;
     p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
