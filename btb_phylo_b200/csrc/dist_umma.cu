@@ -698,6 +698,16 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 int64_t m0, n0; int I, J, half;
                 unit_coords(u, m0, n0, I, J, half);
+                if (p.lockstep && u != worker) {                 // see dist_umma_kernel
+                    const int64_t round = (u - worker) / n_workers;
+                    const int64_t full_rounds = p.units / n_workers;
+                    const int64_t last_count = p.units - full_rounds * n_workers;
+                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
+                    if (round > full_rounds - 1) target += last_count;
+                    __threadfence();
+                    atomicAdd(p.lockstep, 1u);
+                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+                }
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -929,12 +939,29 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         BTB_CUDA(cudaGetDevice(&dev));
         BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = UmmaCfg<1>::kSmemBytes;
+        cfg.stream = stream;
+        cfg.numAttrs = 0;
+        static unsigned int *d_lock[16] = {nullptr};
+        if (g_umma_lockstep && p.units > ctas && dev < 16) {
+            if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
+            BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
+            p.lockstep = d_lock[dev];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
         if (out_elem_bytes == 2) {
             BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
-            dist_umma_fp4_kernel<uint16_t><<<ctas, kThreads, UmmaCfg<1>::kSmemBytes, stream>>>(ma, mb, p);
+            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_kernel<uint16_t>, ma, mb, p));
         } else {
             BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
-            dist_umma_fp4_kernel<uint32_t><<<ctas, kThreads, UmmaCfg<1>::kSmemBytes, stream>>>(ma, mb, p);
+            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_kernel<uint32_t>, ma, mb, p));
         }
         BTB_CUDA(cudaGetLastError());
         return BTB_OK;
