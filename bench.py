@@ -261,9 +261,13 @@ def gpu_arm(args):
     except (OSError, ValueError):
         pass
     bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-    peak = 2.0 * bf16 if bf16 else 2.0 * 1590.0
-    peak_src = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 = 2 x bf16 rate on sm_100; SURVEY.md 8d)" if bf16
-                else "2 x 1.59 PFLOP/s fallback of B200_PROFILING.md")
+    bf16_src = "bf16_tflops_sustained of MEASURED_PEAKS.json" if bf16 else "1.59 PFLOP/s fallback of B200_PROFILING.md"
+    bf16 = bf16 or 1590.0
+    fp4 = bool(_query(lib, b"umma_fp4")) and plan.sigma == _capi.SIGMA_DENSE4 and _query(lib, b"umma_dense_simplex") == 2
+    # the tensor pipe's rate for the operand type the kernel multiplies: int8 = 2 x bf16, e2m1 (kind::mxf4) = 4 x bf16
+    peak = (4.0 if fp4 else 2.0) * bf16
+    peak_src = "%d x %s (%s runs at %dx the bf16 rate on sm_100; SURVEY.md 8d uses the int8 figure = %.1f)" % (
+        4 if fp4 else 2, bf16_src, "kind::mxf4 e2m1" if fp4 else "kind::i8", 4 if fp4 else 2, 2.0 * bf16)
     ops_per_launch = 2.0 * SIGMA * L * unique_pairs(n) / world      # algorithmic ops of this rank's launch
     achieved = ops_per_launch / (kernel_ms * 1e-3) / 1e12
     int8_lib = None
@@ -280,14 +284,16 @@ def gpu_arm(args):
         pass
     dense_code = _query(lib, b"umma_dense_simplex")
     planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
-    roofline = {"bound": "tensor", "kernel": "dist_umma_kernel (tcgen05.mma kind::i8)", "achieved": achieved, "peak": peak,
+    nominal = 9000.0 if fp4 else 4500.0
+    roofline = {"bound": "tensor", "kernel": "dist_umma_fp4_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)" if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
+                "achieved": achieved, "peak": peak, "peak_int8_basis": 2.0 * bf16, "frac_int8_basis": achieved / (2.0 * bf16),
                 "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
-                "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-byte-per-site "
+                "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-element-per-site "
                         "tetrahedron code, so the tensor pipe executes 3/4 of that: achieved_executed is the hardware rate",
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(n, L, world),
                 "peak_source": peak_src, "ops": "int8 multiply-add = 2 ops; 2*sigma*L*N(N-1)/2 with sigma=4 (padding, diagonal tiles = overhead)",
-                "kernel_ms": kernel_ms, "peak_nominal_int8_dense": 4500.0, "frac_of_nominal": achieved / 4500.0,
-                "frac_of_nominal_executed": achieved * planes_executed / 4.0 / 4500.0,
+                "kernel_ms": kernel_ms, "peak_nominal_dense": nominal, "frac_of_nominal": achieved / nominal,
+                "frac_of_nominal_executed": achieved * planes_executed / 4.0 / nominal,
                 "cublas_int8_8192_measured": int8_lib}
 
     # ---- CPU baseline on this box's host cores (bounded sample), also the parity spot-check -----
@@ -312,8 +318,8 @@ def gpu_arm(args):
     line = {
         "metric": "pairwise SNP distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int8 -> int32 (exact)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 kind::i8, cta_group::%d" % _query(lib, b"umma_cta_group"), "options": os.environ.get("BTB_OPTIONS", ""),
+        "scaling": "strong", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> fp32 (0/1 operands, exact integers)" if _query(lib, b"umma_fp4") else "int8 x int8 -> int32 (exact)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", _query(lib, b"umma_cta_group")), "options": os.environ.get("BTB_OPTIONS", ""),
                    "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "sharding": "contiguous upper-triangle tile ranges, no collective",
                    "l2_policy": "operands (12 GB one-hot) and output (5 GB) exceed the 126 MB L2; no flush needed",
                    "timed_region": "operand encode + distance GEMM per step, CUDA events on the launching stream"},

@@ -98,14 +98,17 @@ __host__ __device__ inline int sigma4_of(int sigma) { return sigma <= 4 ? 4 : (s
 //       non-(0,0,0) sites of row i (int32 kept behind the operand rows).  Same 25 % saving, sparse
 //       0/1 data, no throttling (measured 571 W, 1965 MHz): the default.
 extern int g_umma_dense_simplex;
-// g_umma_fp4 (experimental, "umma_fp4"): dense alignments with the 0/1 tetrahedron code are stored
-// as packed 4-bit e2m1 values (0 -> 0x0, 1 -> 0x2) and multiplied with tcgen05.mma kind::mxf4
-// (unit block scales, fp32 accumulators: sums of 0/1 products < 2^24 are exact): 1.5 bytes per site.
+// g_umma_fp4 ("umma_fp4", default on): dense alignments with the 0/1 tetrahedron code are stored as
+// packed 4-bit e2m1 values (0 -> 0x0, 1.0 -> 0x2), 1.5 bytes per site, and multiplied with
+// tcgen05.mma kind::mxf4 (unit block scales) at twice the int8 rate.  The fp32 accumulators hold
+// exact integers as long as a row's dot product stays below 2^24, i.e. 3 len < 2^24.
 extern int g_umma_fp4;
-inline bool umma_use_fp4(int sigma) { return sigma_dense(sigma) && g_umma_fp4 && g_umma_dense_simplex == 2; }
+inline bool umma_use_fp4(int sigma, int64_t len) {
+    return sigma_dense(sigma) && g_umma_fp4 && g_umma_dense_simplex == 2 && 3 * len < (int64_t(1) << 24);
+}
 inline int umma_bytes_per_site(int sigma) { return sigma_dense(sigma) ? (g_umma_dense_simplex ? 3 : 4) : sigma4_of(sigma); }
 inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple of 128
-    int64_t k = umma_use_fp4(sigma) ? (len * 3 + 1) / 2 : len * umma_bytes_per_site(sigma);
+    int64_t k = umma_use_fp4(sigma, len) ? (len * 3 + 1) / 2 : len * umma_bytes_per_site(sigma);
     return (k + 127) / 128 * 128;
 }
 

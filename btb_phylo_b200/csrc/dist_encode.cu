@@ -391,7 +391,7 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         const int64_t kb = umma_k_bytes(len, sigma);
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
-        if (umma_use_fp4(sigma)) {
+        if (umma_use_fp4(sigma, len)) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
             BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));

@@ -799,7 +799,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
-int g_umma_fp4 = 0;            // experimental kind::mxf4 path for dense alignments (see common.cuh)
+int g_umma_fp4 = 1;            // kind::mxf4 path for dense alignments (see common.cuh); 0 = int8 only
 int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
 int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
@@ -926,7 +926,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
-    if (umma_use_fp4(sigma)) {
+    if (umma_use_fp4(sigma, len)) {
         BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
         BTB_TRY(make_operand_map(&mb, A, n, kb, 256));
         UmmaParams p;

@@ -81,11 +81,18 @@ def test_kernel_variants_agree(capi, oracle):
     want_d = oracle.snp_dists_rows(dense, threads=8)
     want_g = oracle.snp_dists_rows(general, threads=8)
     try:
-        for code in (0, 1, 2):
-            capi.check(lib.btb_set_option(b"umma_dense_simplex", code))
-            for cg in (1, 2):
-                plan, got = gpu_matrix(capi, dense, 1, cg)
-                assert plan.sigma == capi.SIGMA_DENSE4 and (got == want_d).all(), (code, cg)
+        for fp4 in (1, 0):                                   # kind::mxf4 on packed nibbles / kind::i8
+            capi.check(lib.btb_set_option(b"umma_fp4", fp4))
+            for code in (0, 1, 2):
+                capi.check(lib.btb_set_option(b"umma_dense_simplex", code))
+                for cg in (1, 2):
+                    plan, got = gpu_matrix(capi, dense, 1, cg)
+                    assert plan.sigma == capi.SIGMA_DENSE4 and (got == want_d).all(), (fp4, code, cg)
+        for tile_mode in (0, 1):                             # half-tile units / one CTA per full tile (int8)
+            capi.check(lib.btb_set_option(b"umma_tile_mode", tile_mode))
+            big = synth.snp_alignment(6400, 777, seed=14)    # 325 tiles >= 2 per SM: the full-tile kernel engages
+            _, got = gpu_matrix(capi, big, 1, 1)
+            assert (got == oracle.snp_dists_rows(big, threads=8)).all(), tile_mode
         capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
         for variant in (0, 1, 2, 3):
             capi.check(lib.btb_set_option(b"umma_cg2_variant", variant))
@@ -94,7 +101,9 @@ def test_kernel_variants_agree(capi, oracle):
             _, got = gpu_matrix(capi, dense, 1, 2)
             assert (got == want_d).all(), variant
     finally:
-        capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
+        capi.check(lib.btb_set_option(b"umma_dense_simplex", 2))
+        capi.check(lib.btb_set_option(b"umma_fp4", 1))
+        capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
         capi.check(lib.btb_set_option(b"umma_cg2_variant", 0))
         capi.check(lib.btb_set_option(b"umma_cta_group", 1))
 
