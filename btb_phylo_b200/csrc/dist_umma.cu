@@ -195,6 +195,7 @@ struct UmmaParams {
     int32_t bias;         // len or 3 * len
     int fp32acc;          // accumulators are fp32 (kind::mxf4): convert to integers first
     const int32_t *rowsum; // dense == 3: c_i, out = c_row + c_col - acc
+    const int2 *worklist;      // FP4 full-tile kernel: (block row I, 240-column block j) per unit
     unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
@@ -202,12 +203,15 @@ struct UmmaParams {
 // Epilogue of one 128-row x 256-column accumulator buffer: this thread owns matrix row `row`
 // (TMEM lane of `taddr`), reads 32 columns at a time and writes the tile (16-byte stores), its
 // mirror (lane-coalesced 2/4-byte stores) or the tile-packed slot.
+// `valid_cols` < 256 and `tri` = true serve the rectangular 256 x 240 tiles of the FP4 full-tile
+// kernel: a cell is written where column >= row (mirrored where column > row), whatever tile it is in.
 template <typename OutT>
 __device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t taddr, int64_t row, int64_t n0,
-                                                  int row_in_tile, int64_t tile_slot, bool do_mirror) {
+                                                  int row_in_tile, int64_t tile_slot, bool do_mirror,
+                                                  int valid_cols = kAccCols, bool tri = false) {
     OutT *out = static_cast<OutT *>(p.out);
 #pragma unroll 1
-    for (int c0 = 0; c0 < kAccCols; c0 += 32) {
+    for (int c0 = 0; c0 < valid_cols; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + uint32_t(c0), v);
         if (p.fp32acc) {
@@ -226,6 +230,35 @@ __device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t 
             for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
         }
         const int64_t col = n0 + c0;
+        if (tri) {
+            // rectangular tiles straddle the diagonal anywhere: per-cell rule
+            const int lim = valid_cols - c0 < 32 ? valid_cols - c0 : 32;
+            if (row < p.n) {
+                OutT *dst = out + row * p.ld + col;
+                if (lim == 32 && col >= row && col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                    if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
+                                               v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < lim && col + j >= row && col + j < p.n) dst[j] = OutT(v[j]);
+                }
+                if (do_mirror) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < lim && col + j > row && col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+                }
+            }
+            continue;
+        }
         if (p.out_mode == 1) {
             OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
                         (int64_t)row_in_tile * BTB_TILE + c0;
@@ -764,6 +797,150 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP4 full-tile variant: one CTA computes 256 rows x 240 columns as two 128-row halves that share
+// every staged B block (64 instead of 96 B/clk of L2 traffic per SM, as in dist_umma_tile_kernel).
+// The tiles are rectangular because two 256-column fp32 accumulators would fill all 512 TMEM
+// columns and leave no room for the (unit) block scale factors: 2 x 240 + 16 columns fit.  Units
+// come from a host-built work list in row-band order; cells are written where column >= row and
+// mirrored where column > row, so any set of whole block rows covers exactly the same cells as the
+// square-tile enumeration.
+struct Fp4TileCfg {
+    static constexpr int kBN = 240;
+    static constexpr int kABytes = 256 * kBlockK;                     // 32 KB
+    static constexpr int kBBytes = kBN * kBlockK;                     // 30 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB (multiple of 1024)
+    static constexpr int kStages = 3;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const UmmaParams p) {
+    using Cfg = Fp4TileCfg;
+    constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t kHalf1Col = 256, kSfCol = 496;         // accumulators at 0..239 and 256..495, scale factors 496..511
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int h) { return bar_base + 8u * (2 * kStages + h); };
+    auto tempty_bar = [&](int h) { return bar_base + 8u * (2 * kStages + 2 + h); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t worker = blockIdx.x, n_workers = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp >= 4) tmem_st_32x32_x16(tmem_base + (uint32_t((warp & 3) * 32) << 16) + kSfCol, 0x7F7F7F7Fu);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers) {
+                const int2 w = p.worklist[u];
+                const int m0 = w.x * BTB_TILE, n0 = w.y * Cfg::kBN;
+                if (p.lockstep && u != worker) {                 // see dist_umma_kernel
+                    const int64_t round = (u - worker) / n_workers;
+                    const int64_t full_rounds = p.units / n_workers;
+                    const int64_t last_count = p.units - full_rounds * n_workers;
+                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
+                    if (round > full_rounds - 1) target += last_count;
+                    __threadfence();
+                    atomicAdd(p.lockstep, 1u);
+                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+                }
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), m0);
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_mxf4_idesc(128, Cfg::kBN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const uint32_t drained = (uint32_t(it) & 1u) ^ 1u;
+            for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                if (kb == 0) mbar_wait(tempty_bar(0), drained);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_mxf4(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
+                                  tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                __syncwarp();
+                if (kb == 0) { mbar_wait(tempty_bar(1), drained); tc_fence_after(); }
+                if (elect_one()) {
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + 128 * kBlockK);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_mxf4(tmem_base + kHalf1Col, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
+                                  tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit<1>(empty_bar(stage));
+                    if (kb == p.k_blocks - 1) { umma_commit<1>(tfull_bar(0)); umma_commit<1>(tfull_bar(1)); }
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const int2 w = p.worklist[u];
+            const int64_t n0 = int64_t(w.y) * Cfg::kBN;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(tfull_bar(h), uint32_t(it) & 1u);
+                tc_fence_after();
+                const int row_in_tile = h * 128 + quarter * 32 + lane;
+                drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h) * kHalf1Col,
+                                        int64_t(w.x) * BTB_TILE + row_in_tile, n0, row_in_tile, 0, p.mirror != 0, Cfg::kBN, true);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(tempty_bar(h));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -926,13 +1103,95 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
+    if (umma_use_fp4(sigma, len) && g_umma_tile_mode == 1 && out_mode == 0) {
+        // whole bands of block rows (the full matrix, the level-1/2 band launches): rectangular full tiles
+        const int64_t Tt = tiles_per_dim(n);
+        int64_t first = 0, rb0 = -1, rb1 = -1;
+        for (int64_t r0 = 0; r0 <= Tt; r0 += kBand) {
+            if (first == tile_lo) rb0 = r0;
+            if (first == tile_hi) rb1 = std::min(r0, Tt);
+            if (r0 < Tt) first += band_tiles(Tt, r0, std::min<int64_t>(kBand, Tt - r0));
+        }
+        if (rb0 >= 0 && rb1 > rb0) {
+            // The work list of the whole problem is built once per (device, n) and kept on the device;
+            // a launch uses the slice of the bands it covers.
+            struct ListCache { int64_t n = -1; int2 *d = nullptr; size_t cap = 0; std::vector<int64_t> band_off; };
+            static ListCache cache[16];
+            int dev = 0, sms = 0;
+            BTB_CUDA(cudaGetDevice(&dev));
+            BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            if (dev < 16) {
+                ListCache &lc = cache[dev];
+                if (lc.n != n) {
+                    std::vector<int2> h_list;
+                    lc.band_off.clear();
+                    const int64_t NJ = (n + Fp4TileCfg::kBN - 1) / Fp4TileCfg::kBN;
+                    for (int64_t r0 = 0; r0 < Tt; r0 += kBand) {
+                        lc.band_off.push_back(int64_t(h_list.size()));
+                        const int64_t r1 = std::min(Tt, r0 + kBand);
+                        for (int64_t j = (r0 * BTB_TILE) / Fp4TileCfg::kBN; j < NJ; ++j)
+                            for (int64_t I = r0; I < r1; ++I)
+                                if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h_list.push_back(make_int2(int(I), int(j)));
+                    }
+                    lc.band_off.push_back(int64_t(h_list.size()));
+                    if (lc.cap < h_list.size()) {
+                        if (lc.d) cudaFree(lc.d);
+                        lc.cap = h_list.size() + 1024;
+                        BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&lc.d), lc.cap * sizeof(int2)));
+                    }
+                    BTB_CUDA(cudaMemcpy(lc.d, h_list.data(), h_list.size() * sizeof(int2), cudaMemcpyHostToDevice));
+                    lc.n = n;
+                }
+                const int64_t b0 = rb0 / kBand, b1 = (rb1 + kBand - 1) / kBand;
+                const int64_t list_lo = lc.band_off[size_t(b0)], list_hi = lc.band_off[size_t(b1)];
+              if (list_hi - list_lo >= 2 * int64_t(sms)) {
+                const int2 *d_units = lc.d + list_lo;
+                const int64_t n_units = list_hi - list_lo;
+                BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+                BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN));
+                UmmaParams p;
+                p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
+                p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
+                p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units;
+                p.dense = 3; p.bias = 0;
+                p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+                const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+                cudaLaunchConfig_t cfg = {};
+                cudaLaunchAttribute attr[1];
+                cfg.gridDim = dim3(ctas);
+                cfg.blockDim = dim3(kThreads);
+                cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
+                cfg.stream = stream;
+                cfg.numAttrs = 0;
+                static unsigned int *d_lock[16] = {nullptr};
+                if (g_umma_lockstep && p.units > ctas) {
+                    if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
+                    BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
+                    p.lockstep = d_lock[dev];
+                    attr[0].id = cudaLaunchAttributeCooperative;
+                    attr[0].val.cooperative = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                }
+                if (out_elem_bytes == 2) {
+                    BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
+                    BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t>, ma, mb, p));
+                } else {
+                    BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
+                    BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint32_t>, ma, mb, p));
+                }
+                return BTB_OK;
+              }
+            }
+        }
+    }
     if (umma_use_fp4(sigma, len)) {
         BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
         BTB_TRY(make_operand_map(&mb, A, n, kb, 256));
         UmmaParams p;
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles * 2;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr;
         p.dense = 3; p.bias = 0;
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
         int dev = 0, sms = 0;
@@ -976,7 +1235,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         UmmaParams p;
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0; p.worklist = nullptr;
         p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
         p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
@@ -998,6 +1257,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.dbg = nullptr;
     p.lockstep = nullptr;
     p.fp32acc = 0;
+    p.worklist = nullptr;
     p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
