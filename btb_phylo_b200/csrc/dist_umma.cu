@@ -1107,7 +1107,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         // whole bands of block rows (the full matrix, the level-1/2 band launches): rectangular full tiles
         const int64_t Tt = tiles_per_dim(n);
         int64_t first = 0, rb0 = -1, rb1 = -1;
-        for (int64_t r0 = 0; r0 <= Tt; r0 += kBand) {
+        for (int64_t r0 = 0; r0 < Tt + kBand; r0 += kBand) {       // band starts, plus one step past the end
             if (first == tile_lo) rb0 = r0;
             if (first == tile_hi) rb1 = std::min(r0, Tt);
             if (r0 < Tt) first += band_tiles(Tt, r0, std::min<int64_t>(kBand, Tt - r0));
