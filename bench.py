@@ -177,14 +177,16 @@ def gpu_arm(args):
 
     seqs = make_alignment_cuda(n, L, device)                      # identical on every rank (operands are replicated)
     plan = dev.DistancePlan(seqs, length=L, engine=_capi.ENGINE_UMMA)
-    lo, hi = multirank.tile_share(n, rank, world)
-    packed = world > 1
-    out = plan.alloc_tiles(lo, hi) if packed else plan.alloc_matrix()
-    my_pairs = unique_pairs(n) if world == 1 else None            # whole-job pairs are what `value` counts
+    # The path shards by block rows of the matrix: each rank owns a contiguous range of 256-row blocks
+    # holding (nearly) equal numbers of upper-triangle tiles; no data-path collective.
+    row_lo, row_hi = dev.row_share(n, rank, world)
+    T = dev.block_rows(n)
+    my_tiles = sum(T - i for i in range(row_lo, row_hi))
+    out = plan.alloc_matrix()
 
     def step():
         plan.encode()
-        plan.compute(out, lo, hi, packed=packed)
+        plan.compute_rows(out, row_lo, row_hi)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -203,7 +205,7 @@ def gpu_arm(args):
     for s in range(args.steps):
         plan.encode()
         ev[2 * s + 1].record()
-        plan.compute(out, lo, hi, packed=packed)
+        plan.compute_rows(out, row_lo, row_hi)
         ev[2 * s + 2].record()
     sync_all()
     clocks = sampler.stop()
@@ -242,8 +244,8 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
-    my_tiles = hi - lo
-    d2h = n * n * elem if world == 1 else 2 * my_tiles * 256 * 256 * elem
+    r0, r1 = min(n, row_lo * 256), min(n, row_hi * 256)
+    d2h = n * n * elem if world == 1 else ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * elem
     e2e = {"value": unique_pairs(n) / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(n * L),
            "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_s, "steps": e2e_steps,
            "call": "btb_dist_matrix_host (C-ABI level 2; per-rank bytes)"}
@@ -268,7 +270,7 @@ def gpu_arm(args):
     peak = (4.0 if fp4 else 2.0) * bf16
     peak_src = "%d x %s (%s runs at %dx the bf16 rate on sm_100; SURVEY.md 8d uses the int8 figure = %.1f)" % (
         4 if fp4 else 2, bf16_src, "kind::mxf4 e2m1" if fp4 else "kind::i8", 4 if fp4 else 2, 2.0 * bf16)
-    ops_per_launch = 2.0 * SIGMA * L * unique_pairs(n) / world      # algorithmic ops of this rank's launch
+    ops_per_launch = 2.0 * SIGMA * L * unique_pairs(n) * my_tiles / multirank.tile_count(n)   # this rank's launch
     achieved = ops_per_launch / (kernel_ms * 1e-3) / 1e12
     int8_lib = None
     try:                                                            # context only: cuBLAS int8 GEMM on this GPU
@@ -285,7 +287,7 @@ def gpu_arm(args):
     dense_code = _query(lib, b"umma_dense_simplex")
     planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
     nominal = 9000.0 if fp4 else 4500.0
-    roofline = {"bound": "tensor", "kernel": "dist_umma_fp4_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)" if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
+    roofline = {"bound": "tensor", "kernel": "dist_umma_fp4_tile_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)" if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
                 "achieved": achieved, "peak": peak, "peak_int8_basis": 2.0 * bf16, "frac_int8_basis": achieved / (2.0 * bf16),
                 "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
                 "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-element-per-site "
@@ -301,14 +303,8 @@ def gpu_arm(args):
     h_np = h_seqs.numpy()[:, :L]
     rows, dt, cpu_rows = cpu_rows_per_second(h_np, threads, 12.0)
     gpu_rows = h_out.numpy()[:rows, :n].astype(np.uint32)
-    owned = np.ones((rows, n), dtype=bool)
-    if world > 1:                                                    # rank 0 only holds its own tiles
-        owned[:] = False
-        for tix in range(lo, hi):
-            I, J = multirank.tile_coords(n, tix)
-            owned[I * 256:(I + 1) * 256, J * 256:(J + 1) * 256] = True
-            if J * 256 < rows:
-                owned[J * 256:(J + 1) * 256, I * 256:(I + 1) * 256] = True
+    owned = np.ones((rows, n), dtype=bool)                           # rank 0 owns block rows [0, row_hi): the
+    owned[r1:, r1:] = False                                          # first matrix rows are always among them
     match = bool((gpu_rows[owned] == cpu_rows[owned]).all())
     t_row = dt / rows
     cpu = {"value": unique_pairs(n) / (t_row * n), "unit": "pairs/s", "cores": threads, "kind": "port",
@@ -320,7 +316,7 @@ def gpu_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> fp32 (0/1 operands, exact integers)" if _query(lib, b"umma_fp4") else "int8 x int8 -> int32 (exact)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", _query(lib, b"umma_cta_group")), "options": os.environ.get("BTB_OPTIONS", ""),
-                   "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "sharding": "contiguous upper-triangle tile ranges, no collective",
+                   "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "block_rows_this_rank": [row_lo, row_hi], "sharding": "contiguous 256-row blocks with equal upper-triangle tile counts per rank, no collective",
                    "l2_policy": "operands (12 GB one-hot) and output (5 GB) exceed the 126 MB L2; no flush needed",
                    "timed_region": "operand encode + distance GEMM per step, CUDA events on the launching stream"},
         "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -42,6 +42,9 @@ SIGNATURES = {
     "btb_dist_tile_count": (c_i64, [c_i64]),
     "btb_dist_tile_coords": (c_int, [c_i64, c_i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "btb_distance_tiles": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
+    "btb_dist_block_rows": (c_i64, [c_i64]),
+    "btb_dist_row_share": (c_int, [c_i64, c_int, c_int, p_i64, p_i64]),
+    "btb_distance_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp]),
     "btb_format_csv_rows": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(ctypes.c_char_p),
                                     ctypes.c_char, c_int, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
 }

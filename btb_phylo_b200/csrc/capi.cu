@@ -31,9 +31,11 @@ int fail(int code, const char *fmt, ...) {
 }
 
 int distance_tiles_popc(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, int,
-                        cudaStream_t);
+                        cudaStream_t, const int2 *);
 int distance_tiles_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, int,
-                        cudaStream_t);
+                        cudaStream_t, const int2 *);
+int distance_rows_popc(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, cudaStream_t);
+int distance_rows_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, cudaStream_t);
 extern int g_umma_cta_group;
 extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
@@ -145,10 +147,45 @@ extern "C" int btb_distance_tiles(int engine, const void *d_operands, int64_t n,
     if (out_mode == 0 && out_ld < n) return fail(BTB_EINVAL, "out_ld < n");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (engine == BTB_ENGINE_POPC)
-        return distance_tiles_popc(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s);
+        return distance_tiles_popc(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s, nullptr);
     if (engine == BTB_ENGINE_UMMA)
-        return distance_tiles_umma(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s);
+        return distance_tiles_umma(d_operands, n, len, sigma, tile_lo, tile_hi, d_out, out_elem_bytes, out_ld, out_mode, mirror, s, nullptr);
     return fail(BTB_EINVAL, "btb_distance_tiles: engine must be POPC or UMMA");
+}
+
+extern "C" int64_t btb_dist_block_rows(int64_t n) { return n > 0 ? tiles_per_dim(n) : 0; }
+
+// block rows [lo, hi) of rank `rank`: contiguous, (nearly) equal numbers of upper-triangle tiles
+extern "C" int btb_dist_row_share(int64_t n, int rank, int world, int64_t *lo, int64_t *hi) {
+    if (n <= 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return fail(BTB_EINVAL, "btb_dist_row_share: bad argument");
+    const int64_t T = tiles_per_dim(n), total = tile_count(n);
+    auto boundary = [&](int r) -> int64_t {                 // first block row of rank r
+        if (r <= 0) return 0;
+        if (r >= world) return T;
+        const int64_t want = total * r / world;
+        int64_t acc = 0, I = 0;
+        while (I < T && acc + (T - I) <= want) { acc += T - I; ++I; }
+        return I;
+    };
+    *lo = boundary(rank);
+    *hi = boundary(rank + 1);
+    return BTB_OK;
+}
+
+extern "C" int btb_distance_rows(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
+                                 int64_t row_block_lo, int64_t row_block_hi, void *d_out, int out_elem_bytes,
+                                 int64_t out_ld, int mirror, void *stream) {
+    if (!d_operands || !d_out || n <= 0 || len < 0) return fail(BTB_EINVAL, "btb_distance_rows: bad argument");
+    if (out_elem_bytes != 2 && out_elem_bytes != 4) return fail(BTB_EINVAL, "out_elem_bytes must be 2 or 4");
+    if (out_elem_bytes == 2 && len > 65535) return fail(BTB_EINVAL, "uint16 output needs len < 65536");
+    if (row_block_lo < 0 || row_block_hi > tiles_per_dim(n) || row_block_lo > row_block_hi || out_ld < n)
+        return fail(BTB_EINVAL, "btb_distance_rows: block row range or out_ld out of bounds");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (engine == BTB_ENGINE_POPC)
+        return distance_rows_popc(d_operands, n, len, sigma, row_block_lo, row_block_hi, d_out, out_elem_bytes, out_ld, mirror, s);
+    if (engine == BTB_ENGINE_UMMA)
+        return distance_rows_umma(d_operands, n, len, sigma, row_block_lo, row_block_hi, d_out, out_elem_bytes, out_ld, mirror, s);
+    return fail(BTB_EINVAL, "btb_distance_rows: engine must be POPC or UMMA");
 }
 
 // =============================================================================== level 2
@@ -254,41 +291,20 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         }
         L2_CUDA(cudaStreamSynchronize(ws.st2));
     } else {
-        int64_t lo, hi;
-        tile_share(tile_count(n), rank, world, lo, hi);
-        L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 0, 1, st));
-        // copy back what this rank computed: whole bands as two wide 2-D copies (the band's rows from
-        // its first column on, and the mirrored strip below), partial bands run by run
+        // this rank's contiguous block rows: every cell (r, c >= r) of those rows plus the mirrors, copied
+        // back as two wide 2-D copies (the rows from their first column on, and the mirrored strip below)
+        int64_t lo = 0, hi = 0;
+        L2_TRY(btb_dist_row_share(n, rank, world, &lo, &hi));
+        L2_TRY(btb_distance_rows(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 1, st));
         char *ho = static_cast<char *>(out);
         auto copy2d = [&](int64_t r0, int64_t r1, int64_t c0, int64_t c1) -> cudaError_t {
             if (r1 <= r0 || c1 <= c0) return cudaSuccess;
             return cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
                                      size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, st);
         };
-        int64_t first = 0;
-        for (int64_t b0 = 0; b0 < T; b0 += kBand) {
-            const int64_t w = std::min<int64_t>(kBand, T - b0), cnt = band_tiles(T, b0, w), last = first + cnt;
-            if (first >= lo && last <= hi) {
-                const int64_t row0 = b0 * BTB_TILE, row1 = std::min<int64_t>(n, (b0 + w) * BTB_TILE);
-                L2_CUDA(copy2d(row0, row1, row0, n));
-                L2_CUDA(copy2d(row1, n, row0, row1));
-            } else {
-                int64_t t = std::max(first, lo);
-                const int64_t stop = std::min(last, hi);
-                while (t < stop) {
-                    int I, J, I2, J2;
-                    tile_coords(T, t, I, J);
-                    int64_t e = t + 1;
-                    while (e < stop) { tile_coords(T, e, I2, J2); if (J2 != J || I2 != I + int(e - t)) break; ++e; }
-                    const int64_t r0 = int64_t(I) * BTB_TILE, r1 = std::min<int64_t>(n, r0 + (e - t) * BTB_TILE);
-                    const int64_t c0 = int64_t(J) * BTB_TILE, c1 = std::min<int64_t>(n, c0 + BTB_TILE);
-                    L2_CUDA(copy2d(r0, r1, c0, c1));
-                    L2_CUDA(copy2d(c0, c1, r0, r1));
-                    t = e;
-                }
-            }
-            first = last;
-        }
+        const int64_t row0 = std::min<int64_t>(n, lo * BTB_TILE), row1 = std::min<int64_t>(n, hi * BTB_TILE);
+        L2_CUDA(copy2d(row0, row1, row0, n));
+        L2_CUDA(copy2d(row1, n, row0, row1));
     }
     L2_CUDA(cudaStreamSynchronize(st));
     cleanup();

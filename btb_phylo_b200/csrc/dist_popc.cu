@@ -44,7 +44,7 @@ __device__ __forceinline__ void store_tile_from_smem(const uint32_t *s_acc /*[12
 template <int Q, int kKC, bool HASV, typename OutT>
 __global__ void __launch_bounds__(256)
 dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, int64_t tile_lo,
-                 OutT *__restrict__ out, int64_t ld, int out_mode, int mirror) {
+                 OutT *__restrict__ out, int64_t ld, int out_mode, int mirror, const int2 *__restrict__ sq_list) {
     constexpr int P = Q + (HASV ? 1 : 0);                   // code planes (+ validity unless dense)
     constexpr int kStride = kKC + 1;                        // odd: conflict-free column-row reads
     extern __shared__ uint32_t smem[];
@@ -56,7 +56,8 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
     const int64_t tile = tile_lo + blockIdx.x / 4;
     const int quad = blockIdx.x & 3, qr = quad >> 1, qc = quad & 1;
     int I, J;
-    tile_coords(T, tile, I, J);
+    if (sq_list) { const int2 w = sq_list[tile]; I = w.x; J = w.y; }
+    else tile_coords(T, tile, I, J);
     const int64_t row0 = (int64_t)I * BTB_TILE + qr * kPT;
     const int64_t col0 = (int64_t)J * BTB_TILE + qc * kPT;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -138,7 +139,7 @@ dist_popc_kernel(const uint32_t *__restrict__ planes, int64_t n, int64_t words, 
 
 template <int Q, bool HASV, typename OutT>
 static int launch_popc(const uint32_t *planes, int64_t n, int64_t words, int64_t tile_lo, int64_t tiles,
-                       void *out, int64_t ld, int out_mode, int mirror, cudaStream_t stream) {
+                       void *out, int64_t ld, int out_mode, int mirror, cudaStream_t stream, const int2 *sq_list) {
     constexpr int P = Q + (HASV ? 1 : 0);
     constexpr int kKC = P <= 5 ? 16 : 8;                    // staged words per chunk: keep 4 buffers < 227 KB
     size_t smem = size_t(4) * P * kPT * (kKC + 1) * 4;
@@ -146,14 +147,14 @@ static int launch_popc(const uint32_t *planes, int64_t n, int64_t words, int64_t
     if (smem < epi) smem = epi;
     BTB_CUDA(cudaFuncSetAttribute(dist_popc_kernel<Q, kKC, HASV, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dist_popc_kernel<Q, kKC, HASV, OutT><<<unsigned(tiles * 4), 256, smem, stream>>>(
-        planes, n, words, tile_lo, static_cast<OutT *>(out), ld, out_mode, mirror);
+        planes, n, words, tile_lo, static_cast<OutT *>(out), ld, out_mode, mirror, sq_list);
     BTB_CUDA(cudaGetLastError());
     return BTB_OK;
 }
 
 int distance_tiles_popc(const void *d_operands, int64_t n, int64_t len, int sigma, int64_t tile_lo,
                         int64_t tile_hi, void *d_out, int out_elem_bytes, int64_t out_ld, int out_mode,
-                        int mirror, cudaStream_t stream) {
+                        int mirror, cudaStream_t stream, const int2 *sq_list) {
     const int q = popc_code_planes(sigma);
     const int64_t words = popc_words(len);
     const uint32_t *planes = static_cast<const uint32_t *>(d_operands);
@@ -162,12 +163,12 @@ int distance_tiles_popc(const void *d_operands, int64_t n, int64_t len, int sigm
 #define BTB_POPC_CASE(QQ)                                                                             \
     case QQ:                                                                                          \
         return out_elem_bytes == 2                                                                    \
-                   ? launch_popc<QQ, true, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream) \
-                   : launch_popc<QQ, true, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream);
+                   ? launch_popc<QQ, true, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream, sq_list) \
+                   : launch_popc<QQ, true, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream, sq_list);
     if (sigma_dense(sigma))
         return out_elem_bytes == 2
-                   ? launch_popc<2, false, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream)
-                   : launch_popc<2, false, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream);
+                   ? launch_popc<2, false, uint16_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream, sq_list)
+                   : launch_popc<2, false, uint32_t>(planes, n, words, tile_lo, tiles, d_out, out_ld, out_mode, mirror, stream, sq_list);
     switch (q) {
         BTB_POPC_CASE(1)
         BTB_POPC_CASE(2)
@@ -180,6 +181,17 @@ int distance_tiles_popc(const void *d_operands, int64_t n, int64_t len, int sigm
     }
 #undef BTB_POPC_CASE
     return fail(BTB_EINVAL, "POPC engine: unsupported plane count %d", q);
+}
+
+int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_out, int64_t *count);
+
+int distance_rows_popc(const void *d_operands, int64_t n, int64_t len, int sigma, int64_t row_lo, int64_t row_hi,
+                       void *d_out, int out_elem_bytes, int64_t out_ld, int mirror, cudaStream_t stream) {
+    if (row_hi <= row_lo) return BTB_OK;
+    const int2 *d_list = nullptr;
+    int64_t count = 0;
+    BTB_TRY(get_rows_list(n, row_lo, row_hi, 0, &d_list, &count));
+    return distance_tiles_popc(d_operands, n, len, sigma, 0, count, d_out, out_elem_bytes, out_ld, 0, mirror, stream, d_list);
 }
 
 }  // namespace btb

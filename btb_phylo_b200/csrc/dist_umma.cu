@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -151,6 +152,12 @@ __device__ __forceinline__ void umma_commit_leader(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+struct UmmaParams;
+__device__ __forceinline__ void tile_of(const int2 *sq_list, int64_t T, int64_t tile, int &I, int &J) {
+    if (sq_list) { const int2 w = sq_list[tile]; I = w.x; J = w.y; }
+    else tile_coords(T, tile, I, J);
+}
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -196,6 +203,7 @@ struct UmmaParams {
     int fp32acc;          // accumulators are fp32 (kind::mxf4): convert to integers first
     const int32_t *rowsum; // dense == 3: c_i, out = c_row + c_col - acc
     const int2 *worklist;      // FP4 full-tile kernel: (block row I, 240-column block j) per unit
+    const int2 *sq_list;       // optional explicit list of square tiles (I, J) replacing the band enumeration
     unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
@@ -368,7 +376,7 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto unit_coords = [&](int64_t u, int64_t &m0, int64_t &n0, int &I, int &J, int &half) {
         const int64_t tile = p.tile_lo + (CG == 2 ? u : u / 2);
         half = CG == 2 ? int(cta_rank) : int(u & 1);
-        tile_coords(T, tile, I, J);
+        tile_of(p.sq_list, T, tile, I, J);
         m0 = int64_t(I) * BTB_TILE + half * 128;
         n0 = int64_t(J) * BTB_TILE;
     };
@@ -560,7 +568,7 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 int I, J;
-                tile_coords(T, p.tile_lo + u, I, J);
+                tile_of(p.sq_list, T, p.tile_lo + u, I, J);
                 const int m0 = I * BTB_TILE, n0 = J * BTB_TILE;
                 if (p.lockstep && u != worker) {
                     // see dist_umma_kernel: all producers start a round of tiles together (L2 reuse)
@@ -626,7 +634,7 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         int64_t it = 0;
         for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
             int I, J;
-            tile_coords(T, p.tile_lo + u, I, J);
+            tile_of(p.sq_list, T, p.tile_lo + u, I, J);
             const int64_t n0 = int64_t(J) * BTB_TILE;
             const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
 #pragma unroll 1
@@ -719,7 +727,7 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     auto unit_coords = [&](int64_t u, int64_t &m0, int64_t &n0, int &I, int &J, int &half) {
         half = int(u & 1);
-        tile_coords(T, p.tile_lo + u / 2, I, J);
+        tile_of(p.sq_list, T, p.tile_lo + u / 2, I, J);
         m0 = int64_t(I) * BTB_TILE + half * 128;
         n0 = int64_t(J) * BTB_TILE;
     };
@@ -1092,9 +1100,104 @@ int umma_max_active_clusters(int cg, int *out) {
     return BTB_OK;
 }
 
+// ---- explicit work lists (device resident, cached per device) ----------------------------------
+// kind 0: square tiles (I, J >= I) of block rows [lo, hi); kind 1: rectangular 256 x 240 tiles (I, j).
+// Both in band order relative to `lo`: bands of kBand block rows, column-major inside a band.
+struct DevList { int64_t n, lo, hi; int kind; int2 *d; int64_t count; };
+static std::vector<DevList> g_lists[16];
+static std::mutex g_lists_mutex;
+
+int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_out, int64_t *count) {
+    int dev = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 16) return fail(BTB_EINVAL, "device ordinal too large");
+    std::lock_guard<std::mutex> lock(g_lists_mutex);
+    for (auto &e : g_lists[dev])
+        if (e.n == n && e.lo == lo && e.hi == hi && e.kind == kind) { *d_out = e.d; *count = e.count; return BTB_OK; }
+    if (g_lists[dev].size() > 96) {
+        BTB_CUDA(cudaDeviceSynchronize());
+        for (auto &e : g_lists[dev]) cudaFree(e.d);
+        g_lists[dev].clear();
+    }
+    const int64_t T = tiles_per_dim(n);
+    std::vector<int2> h;
+    if (kind == 0) {
+        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
+            const int64_t r1 = std::min(hi, r0 + kBand);
+            for (int64_t J = r0; J < T; ++J)
+                for (int64_t I = r0; I < r1 && I <= J; ++I) h.push_back(make_int2(int(I), int(J)));
+        }
+    } else {
+        const int64_t NJ = (n + Fp4TileCfg::kBN - 1) / Fp4TileCfg::kBN;
+        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
+            const int64_t r1 = std::min(hi, r0 + kBand);
+            for (int64_t j = (r0 * BTB_TILE) / Fp4TileCfg::kBN; j < NJ; ++j)
+                for (int64_t I = r0; I < r1; ++I)
+                    if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h.push_back(make_int2(int(I), int(j)));
+        }
+    }
+    DevList e{n, lo, hi, kind, nullptr, int64_t(h.size())};
+    BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&e.d), std::max<size_t>(h.size(), 1) * sizeof(int2)));
+    if (!h.empty()) BTB_CUDA(cudaMemcpy(e.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    g_lists[dev].push_back(e);
+    *d_out = e.d;
+    *count = e.count;
+    return BTB_OK;
+}
+
+// FP4 full-tile kernel over the block rows [row_lo, row_hi); *launched = 0 when the range is too
+// small to fill the GPU twice (the caller then uses the half-tile kernel)
+static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t row_lo, int64_t row_hi, void *d_out,
+                           int out_elem_bytes, int64_t out_ld, int mirror, cudaStream_t stream, int *launched) {
+    *launched = 0;
+    int dev = 0, sms = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int2 *d_units = nullptr;
+    int64_t n_units = 0;
+    BTB_TRY(get_rows_list(n, row_lo, row_hi, 1, &d_units, &n_units));
+    if (n_units < 2 * int64_t(sms) || dev >= 16) return BTB_OK;
+    CUtensorMap ma, mb;
+    BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+    BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN));
+    UmmaParams p;
+    p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
+    p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
+    p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
+    p.dense = 3; p.bias = 0;
+    p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+    const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
+    cfg.stream = stream;
+    cfg.numAttrs = 0;
+    static unsigned int *d_lock[16] = {nullptr};
+    if (g_umma_lockstep && p.units > ctas) {
+        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
+        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
+        p.lockstep = d_lock[dev];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    if (out_elem_bytes == 2) {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t>, ma, mb, p));
+    } else {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint32_t>, ma, mb, p));
+    }
+    *launched = 1;
+    return BTB_OK;
+}
+
 int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigma, int64_t tile_lo,
                         int64_t tile_hi, void *d_out, int out_elem_bytes, int64_t out_ld, int out_mode,
-                        int mirror, cudaStream_t stream) {
+                        int mirror, cudaStream_t stream, const int2 *sq_list) {
     const int64_t tiles = tile_hi - tile_lo;
     if (tiles <= 0) return BTB_OK;
     const int64_t kb = umma_k_bytes(len, sigma);
@@ -1103,7 +1206,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     CUtensorMap ma, mb;
-    if (umma_use_fp4(sigma, len) && g_umma_tile_mode == 1 && out_mode == 0) {
+    if (!sq_list && umma_use_fp4(sigma, len) && g_umma_tile_mode == 1 && out_mode == 0) {
         // whole bands of block rows (the full matrix, the level-1/2 band launches): rectangular full tiles
         const int64_t Tt = tiles_per_dim(n);
         int64_t first = 0, rb0 = -1, rb1 = -1;
@@ -1113,76 +1216,9 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
             if (r0 < Tt) first += band_tiles(Tt, r0, std::min<int64_t>(kBand, Tt - r0));
         }
         if (rb0 >= 0 && rb1 > rb0) {
-            // The work list of the whole problem is built once per (device, n) and kept on the device;
-            // a launch uses the slice of the bands it covers.
-            struct ListCache { int64_t n = -1; int2 *d = nullptr; size_t cap = 0; std::vector<int64_t> band_off; };
-            static ListCache cache[16];
-            int dev = 0, sms = 0;
-            BTB_CUDA(cudaGetDevice(&dev));
-            BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            if (dev < 16) {
-                ListCache &lc = cache[dev];
-                if (lc.n != n) {
-                    std::vector<int2> h_list;
-                    lc.band_off.clear();
-                    const int64_t NJ = (n + Fp4TileCfg::kBN - 1) / Fp4TileCfg::kBN;
-                    for (int64_t r0 = 0; r0 < Tt; r0 += kBand) {
-                        lc.band_off.push_back(int64_t(h_list.size()));
-                        const int64_t r1 = std::min(Tt, r0 + kBand);
-                        for (int64_t j = (r0 * BTB_TILE) / Fp4TileCfg::kBN; j < NJ; ++j)
-                            for (int64_t I = r0; I < r1; ++I)
-                                if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h_list.push_back(make_int2(int(I), int(j)));
-                    }
-                    lc.band_off.push_back(int64_t(h_list.size()));
-                    if (lc.cap < h_list.size()) {
-                        if (lc.d) cudaFree(lc.d);
-                        lc.cap = h_list.size() + 1024;
-                        BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&lc.d), lc.cap * sizeof(int2)));
-                    }
-                    BTB_CUDA(cudaMemcpy(lc.d, h_list.data(), h_list.size() * sizeof(int2), cudaMemcpyHostToDevice));
-                    lc.n = n;
-                }
-                const int64_t b0 = rb0 / kBand, b1 = (rb1 + kBand - 1) / kBand;
-                const int64_t list_lo = lc.band_off[size_t(b0)], list_hi = lc.band_off[size_t(b1)];
-              if (list_hi - list_lo >= 2 * int64_t(sms)) {
-                const int2 *d_units = lc.d + list_lo;
-                const int64_t n_units = list_hi - list_lo;
-                BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
-                BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN));
-                UmmaParams p;
-                p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
-                p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
-                p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units;
-                p.dense = 3; p.bias = 0;
-                p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-                const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
-                cudaLaunchConfig_t cfg = {};
-                cudaLaunchAttribute attr[1];
-                cfg.gridDim = dim3(ctas);
-                cfg.blockDim = dim3(kThreads);
-                cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
-                cfg.stream = stream;
-                cfg.numAttrs = 0;
-                static unsigned int *d_lock[16] = {nullptr};
-                if (g_umma_lockstep && p.units > ctas) {
-                    if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
-                    BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-                    p.lockstep = d_lock[dev];
-                    attr[0].id = cudaLaunchAttributeCooperative;
-                    attr[0].val.cooperative = 1;
-                    cfg.attrs = attr;
-                    cfg.numAttrs = 1;
-                }
-                if (out_elem_bytes == 2) {
-                    BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
-                    BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t>, ma, mb, p));
-                } else {
-                    BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
-                    BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint32_t>, ma, mb, p));
-                }
-                return BTB_OK;
-              }
-            }
+            int launched = 0;
+            BTB_TRY(launch_fp4_rows(A, n, kb, rb0, rb1, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
+            if (launched) return BTB_OK;
         }
     }
     if (umma_use_fp4(sigma, len)) {
@@ -1191,7 +1227,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         UmmaParams p;
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles * 2;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr; p.sq_list = sq_list;
         p.dense = 3; p.bias = 0;
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
         int dev = 0, sms = 0;
@@ -1235,7 +1271,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         UmmaParams p;
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0; p.worklist = nullptr;
+        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0; p.worklist = nullptr; p.sq_list = sq_list;
         p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
         p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
@@ -1257,7 +1293,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     p.dbg = nullptr;
     p.lockstep = nullptr;
     p.fp32acc = 0;
-    p.worklist = nullptr;
+    p.worklist = nullptr; p.sq_list = sq_list;
     p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
@@ -1271,6 +1307,24 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     }
     if (cg == 2) return launch_umma<2, uint32_t>(ma, mb, p, stream);
     return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);
+}
+
+
+// every cell (r, c >= r) with r in the block rows [row_lo, row_hi), mirrored when asked: n x n output
+int distance_rows_umma(const void *d_operands, int64_t n, int64_t len, int sigma, int64_t row_lo, int64_t row_hi,
+                       void *d_out, int out_elem_bytes, int64_t out_ld, int mirror, cudaStream_t stream) {
+    if (row_hi <= row_lo) return BTB_OK;
+    const int64_t kb = umma_k_bytes(len, sigma);
+    const uint8_t *A = static_cast<const uint8_t *>(d_operands);
+    if (umma_use_fp4(sigma, len) && g_umma_tile_mode == 1) {
+        int launched = 0;
+        BTB_TRY(launch_fp4_rows(A, n, kb, row_lo, row_hi, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
+        if (launched) return BTB_OK;
+    }
+    const int2 *d_list = nullptr;
+    int64_t count = 0;
+    BTB_TRY(get_rows_list(n, row_lo, row_hi, 0, &d_list, &count));
+    return distance_tiles_umma(d_operands, n, len, sigma, 0, count, d_out, out_elem_bytes, out_ld, 0, mirror, stream, d_list);
 }
 
 }  // namespace btb

@@ -34,6 +34,17 @@ def tile_share(n, rank, world):
     return t * rank // world, t * (rank + 1) // world
 
 
+def block_rows(n):
+    return int(_capi.lib().btb_dist_block_rows(n))
+
+
+def row_share(n, rank, world):
+    """Block rows [lo, hi) of `rank`: contiguous, (nearly) equal numbers of upper-triangle tiles."""
+    lo, hi = ctypes.c_int64(0), ctypes.c_int64(0)
+    _capi.check(_capi.lib().btb_dist_row_share(n, rank, world, ctypes.byref(lo), ctypes.byref(hi)), "btb_dist_row_share")
+    return lo.value, hi.value
+
+
 class DistancePlan:
     """Operands + output of the distance stage for one alignment resident in HBM.
 
@@ -82,6 +93,13 @@ class DistancePlan:
                                                 lo, hi, _ptr(out), self.elem, ld, 1 if packed else 0,
                                                 1 if mirror else 0, _stream()),
                     "btb_distance_tiles")
+
+    def compute_rows(self, out, row_lo, row_hi, mirror=True):
+        """Every cell (r, c >= r) of the block rows [row_lo, row_hi) (+ mirrors) into the n x n matrix `out`."""
+        _capi.check(self.lib.btb_distance_rows(self.engine, _ptr(self.operands), self.n, self.len, self.sigma,
+                                               row_lo, row_hi, _ptr(out), self.elem, out.stride(0),
+                                               1 if mirror else 0, _stream()),
+                    "btb_distance_rows")
 
 
 def distance_matrix_host(seqs, allchars=False, keepcase=False, engine=_capi.ENGINE_AUTO, device=0,

@@ -45,6 +45,38 @@ def tile_share(n, rank, world):
     return t * rank // world, t * (rank + 1) // world
 
 
+def row_share(n, rank, world):
+    """Block rows [lo, hi) of `rank` (same rule as btb_dist_row_share): contiguous ranges holding
+    (nearly) equal numbers of upper-triangle tiles -- the unit the multi-GPU paths shard by."""
+    T = tiles_per_dim(n)
+    total = tile_count(n)
+
+    def boundary(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return T
+        want = total * r // world
+        acc = i = 0
+        while i < T and acc + (T - i) <= want:
+            acc += T - i
+            i += 1
+        return i
+    return boundary(rank), boundary(rank + 1)
+
+
+def assemble_rows(n, shares, mats, out=None):
+    """shares: list of block-row ranges (lo, hi); mats: per-rank n x n matrices in which the rank has
+    written the cells (r, c >= r) of its rows and their mirrors.  Returns the merged matrix."""
+    if out is None:
+        out = np.zeros((n, n), dtype=mats[0].dtype)
+    for (lo, hi), m in zip(shares, mats):
+        r0, r1 = min(n, lo * TILE), min(n, hi * TILE)
+        out[r0:r1, r0:] = m[r0:r1, r0:n]
+        out[r1:, r0:r1] = m[r1:n, r0:r1]
+    return out
+
+
 def assemble(n, shares, packed, out=None):
     """shares: list of (lo, hi); packed: list of arrays [(hi-lo), TILE, TILE] in the same order.
     Returns the full symmetric n x n matrix (both triangles)."""

@@ -94,8 +94,9 @@ int btb_snp_dists(const char *in_fasta, const char *out_path,
 /* Full n x n distance matrix of n sequences of `len` bytes (row i at seqs + i*row_stride).
  * out is row-major with out_ld elements per row, out_elem_bytes = 2 (uint16, needs len < 65536)
  * or 4 (uint32).  seqs/out may be pageable or pinned host memory.  Ranks of a multi-process
- * job pass (rank, world) to compute only their share of upper-triangle tiles; cells of tiles
- * the rank does not own are left untouched.  (world = 1: the whole matrix, both triangles.) */
+ * job pass (rank, world) to compute only their share (btb_dist_row_share block rows: the cells
+ * (r, c >= r) of those rows and their mirrors); other cells are left untouched.
+ * (world = 1: the whole matrix, both triangles.) */
 int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
                          int allchars, int keepcase, int engine, int device,
                          int rank, int world,
@@ -179,6 +180,17 @@ int btb_distance_tiles(int engine, const void *d_operands, int64_t n, int64_t le
                        int64_t tile_lo, int64_t tile_hi,
                        void *d_out, int out_elem_bytes, int64_t out_ld, int out_mode, int mirror,
                        void *stream);
+
+/* Multi-GPU unit: block rows.  btb_dist_block_rows = number of BTB_TILE-row blocks; btb_dist_row_share
+ * gives rank `rank` of `world` a contiguous range of block rows holding (nearly) the same number of
+ * upper-triangle tiles; btb_distance_rows computes every cell (r, c >= r) whose row r lies in the block
+ * rows [row_block_lo, row_block_hi) into the n x n matrix d_out and, when mirror != 0, the transposed
+ * cells as well (so the rows are complete once every earlier block row has been computed too). */
+int64_t btb_dist_block_rows(int64_t n);
+int btb_dist_row_share(int64_t n, int rank, int world, int64_t *row_block_lo, int64_t *row_block_hi);
+int btb_distance_rows(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
+                      int64_t row_block_lo, int64_t row_block_hi,
+                      void *d_out, int out_elem_bytes, int64_t out_ld, int mirror, void *stream);
 
 /* ---- serialisation: k5 ---- */
 

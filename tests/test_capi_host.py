@@ -77,6 +77,25 @@ def test_tile_shares_partition(world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("n", [1, 256, 257, 5000, 50000])
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 300])
+def test_row_shares_partition_block_rows(capi, n, world):
+    from btb_phylo_b200 import device, multirank
+    T = device.block_rows(n)
+    assert T == (n + 255) // 256
+    total = multirank.tile_count(n)
+    prev, counts = 0, []
+    for r in range(world):
+        lo, hi = device.row_share(n, r, world)
+        assert (lo, hi) == multirank.row_share(n, r, world)
+        assert lo == prev and hi >= lo
+        counts.append(sum(T - i for i in range(lo, hi)))
+        prev = hi
+    assert prev == T and sum(counts) == total
+    if world <= 8 and T >= 16 * world:                               # balanced within one block row of tiles
+        assert max(counts) - min(counts) <= 2 * T
+
+
 @pytest.mark.parametrize("elem", [2, 4])
 def test_format_csv_rows_matches_snp_dists_layout(capi, oracle, elem):
     rng = np.random.default_rng(5)

@@ -141,6 +141,69 @@ def test_tile_packed_rank_shares_assemble(capi, oracle, name, engine, cg):
     assert (mat == oracle.snp_dists_rows(seqs, threads=8)).all()
 
 
+@pytest.mark.parametrize("name,engine,cg", ENGINES)
+@pytest.mark.parametrize("n,L,dense,world", [(1100, 700, False, 3), (2900, 1200, True, 2), (2900, 1200, True, 5), (300, 90, True, 4)])
+def test_block_row_shares_cover_the_matrix(capi, oracle, name, engine, cg, n, L, dense, world):
+    """btb_distance_rows: each rank writes the cells (r, c >= r) of its block rows plus their mirrors
+    into its own n x n matrix; merged by ownership they equal the oracle, and a rank never writes
+    outside what it owns (the rest of its matrix stays zero)."""
+    from btb_phylo_b200 import device
+    seqs = synth.snp_alignment(n, L, seed=21, heavy_n=0.0 if dense else 0.1, lower=0.0 if dense else 0.01)
+    if dense:
+        seqs = np.where(np.isin(seqs, list(b"ACGT")), seqs, ord("A")).astype(np.uint8)
+    if cg:
+        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+    plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
+    assert (plan.sigma == capi.SIGMA_DENSE4) == dense
+    plan.encode()
+    want = oracle.snp_dists_rows(seqs, threads=8)
+    shares, mats = [], []
+    for r in range(world):
+        lo, hi = device.row_share(n, r, world)
+        out = plan.alloc_matrix()
+        plan.compute_rows(out, lo, hi)
+        torch.cuda.synchronize()
+        m = out[:, :n].cpu().numpy().astype(np.uint32)
+        r0, r1 = min(n, lo * 256), min(n, hi * 256)
+        own = np.zeros((n, n), dtype=bool)
+        own[r0:r1, r0:] = True
+        own[r1:, r0:r1] = True
+        assert (m[own] == want[own]).all()
+        assert not m[~own].any()
+        shares.append((lo, hi))
+        mats.append(m)
+    assert (multirank.assemble_rows(n, shares, mats) == want).all()
+
+
+def test_block_rows_without_mirror_and_arbitrary_ranges(capi, oracle):
+    from btb_phylo_b200 import device
+    n, L = 1600, 500
+    seqs = synth.snp_alignment(n, L, seed=22, heavy_n=0.0)
+    seqs = np.where(np.isin(seqs, list(b"ACGT")), seqs, ord("C")).astype(np.uint8)
+    want = oracle.snp_dists_rows(seqs, threads=8)
+    for _, engine, cg in ENGINES:
+        if cg:
+            capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+        plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
+        plan.encode()
+        for lo, hi in [(0, 7), (2, 5), (6, 7), (3, 3)]:
+            out = plan.alloc_matrix()
+            plan.compute_rows(out, lo, hi, mirror=False)
+            torch.cuda.synchronize()
+            m = out[:, :n].cpu().numpy().astype(np.uint32)
+            r0, r1 = min(n, lo * 256), min(n, hi * 256)
+            upper = np.triu(np.ones((n, n), dtype=bool))
+            own = np.zeros((n, n), dtype=bool)
+            own[r0:r1, r0:] = True
+            lower = own & ~upper                                   # lower halves of diagonal tiles: engine's choice
+            own &= upper
+            assert (m[own] == want[own]).all()
+            assert ((m[lower] == want[lower]) | (m[lower] == 0)).all()
+            outside = np.ones((n, n), dtype=bool)
+            outside[r0:r1, r0:] = False
+            assert not m[outside].any()
+
+
 def test_uint32_output_and_long_rows(capi, oracle):
     seqs = synth.snp_alignment(300, 70001, seed=2, heavy_n=0.05)
     for _, engine, cg in ENGINES:

@@ -1,5 +1,6 @@
-"""CPU, world_size 2 over gloo: the N>1 path of the distance stage is tile sharding with no
-data-path collective -- each rank produces its tile-packed share, the host gathers.  Here the
+"""CPU, world_size 2 over gloo: the N>1 path of the distance stage is sharding (tile ranges, or
+block rows with equal tile counts) with no data-path collective -- each rank produces its share,
+the host gathers.  Here the
 per-rank tiles come from the oracle (no GPU in this container); the sharding, the gather and the
 max-over-ranks timing reduction that bench.py uses are the code under test."""
 import os
@@ -62,3 +63,35 @@ def test_two_rank_tile_sharding_assembles_full_matrix():
     mp.spawn(_worker, args=(world, _free_port(), n, L, ret), nprocs=world, join=True)
     from btb_phylo_b200 import multirank
     assert ret["equal"] and ret["max_ms"] == 11.0 and ret["tiles"] == multirank.tile_count(n)
+
+
+def _row_worker(rank, world, port, n, L, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from btb_phylo_b200 import device, multirank, synth
+    from oracle import oracle
+    seqs = synth.snp_alignment(n, L, seed=12, heavy_n=0.05)
+    lo, hi = device.row_share(n, rank, world)                        # C-ABI: btb_dist_row_share (host only)
+    assert (lo, hi) == multirank.row_share(n, rank, world)
+    full = oracle.snp_dists_rows(seqs, threads=2)
+    r0, r1 = min(n, lo * 256), min(n, hi * 256)
+    mine = np.zeros((n, n), dtype=np.uint32)                         # stands in for btb_distance_rows(mirror=1)
+    mine[r0:r1, r0:] = full[r0:r1, r0:]
+    mine[r1:, r0:r1] = full[r1:, r0:r1]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, mine))
+    if rank == 0:
+        mat = multirank.assemble_rows(n, [(g[0], g[1]) for g in gathered], [g[2] for g in gathered])
+        ret["equal"] = bool((mat == full).all())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_block_row_sharding_assembles_full_matrix():
+    n, L, world = 1100, 90, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_row_worker, args=(world, _free_port(), n, L, ret), nprocs=world, join=True)
+    assert ret["equal"]
