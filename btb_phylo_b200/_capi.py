@@ -47,6 +47,12 @@ SIGNATURES = {
     "btb_distance_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp]),
     "btb_format_csv_rows": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(ctypes.c_char_p),
                                     ctypes.c_char, c_int, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "btb_process_sample_name": (c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]),
+    "btb_fasta_names": (c_int, [ctypes.c_char_p, c_int, ctypes.c_char_p, ctypes.c_size_t, p_i64, ctypes.POINTER(ctypes.c_size_t)]),
+    "btb_csv_row_names": (c_int, [ctypes.c_char_p, ctypes.c_char, ctypes.c_char_p, ctypes.c_size_t, p_i64, ctypes.POINTER(ctypes.c_size_t)]),
+    "btb_snp_dists_labelled": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int, ctypes.c_char, c_int, c_int,
+                                       c_int, c_int, c_int, ctypes.c_char_p, c_i64, p_i64, p_i64]),
+    "btb_relabel_csv": (c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char, ctypes.c_char_p, c_i64]),
 }
 
 

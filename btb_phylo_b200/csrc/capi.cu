@@ -497,9 +497,112 @@ int multi_gpu_matrix(const DenseFasta &df, int n_dev, int allchars, int keepcase
 
 }  // namespace
 
+namespace {
+// '\n'-separated blob -> exactly `count` strings.
+int split_labels(const char *labels, int64_t count, std::vector<std::string> &out) {
+    out.clear();
+    if (count <= 0) return labels && *labels ? fail(BTB_EINVAL, "labels given for zero rows") : BTB_OK;
+    const char *p = labels;
+    for (;;) {
+        const char *nl = strchr(p, '\n');
+        out.emplace_back(p, nl ? size_t(nl - p) : strlen(p));
+        if (!nl) break;
+        p = nl + 1;
+    }
+    if (int64_t(out.size()) != count)
+        return fail(BTB_EINVAL, "%lld labels expected, %zu given", (long long)count, out.size());
+    return BTB_OK;
+}
+
+int join_names(const std::vector<std::string> &names, char *buf, size_t cap, int64_t *n, size_t *needed) {
+    size_t total = 1;
+    for (auto &s : names) total += s.size() + 1;
+    if (n) *n = int64_t(names.size());
+    if (needed) *needed = total;
+    if (!buf) return BTB_OK;
+    if (cap < total) return fail(BTB_EINVAL, "name buffer too small: %zu bytes needed", total);
+    char *p = buf;
+    for (size_t i = 0; i < names.size(); ++i) {
+        if (i) *p++ = '\n';
+        memcpy(p, names[i].data(), names[i].size());
+        p += names[i].size();
+    }
+    *p = 0;
+    return BTB_OK;
+}
+}  // namespace
+
+extern "C" int btb_process_sample_name(const char *name, char *out, size_t cap) {
+    if (!name || !out) return fail(BTB_EINVAL, "btb_process_sample_name: NULL argument");
+    const std::string l = process_sample_name(name);
+    if (l.size() + 1 > cap) return fail(BTB_EINVAL, "label buffer too small: %zu bytes needed", l.size() + 1);
+    memcpy(out, l.c_str(), l.size() + 1);
+    return BTB_OK;
+}
+
+extern "C" int btb_fasta_names(const char *in_fasta, int host_threads, char *buf, size_t cap, int64_t *n, size_t *needed) {
+    if (!in_fasta) return fail(BTB_EINVAL, "btb_fasta_names: NULL path");
+    FileBytes fb;
+    BTB_TRY(load_file(in_fasta, fb));
+    std::vector<FastaRecord> recs;
+    BTB_TRY(index_fasta(fb, recs, std::max(1, host_threads)));
+    std::vector<std::string> names(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i) names[i] = recs[i].name;
+    return join_names(names, buf, cap, n, needed);
+}
+
+extern "C" int btb_csv_row_names(const char *csv_path, char sep, char *buf, size_t cap, int64_t *n, size_t *needed) {
+    if (!csv_path) return fail(BTB_EINVAL, "btb_csv_row_names: NULL path");
+    FileBytes fb;
+    BTB_TRY(load_file(csv_path, fb));
+    std::vector<std::string> names;
+    BTB_TRY(csv_row_names(fb, sep, names));
+    return join_names(names, buf, cap, n, needed);
+}
+
+extern "C" int btb_relabel_csv(const char *in_csv, const char *out_csv, char sep, const char *labels, int64_t n_labels) {
+    if (!in_csv || !out_csv || !labels) return fail(BTB_EINVAL, "btb_relabel_csv: NULL argument");
+    std::vector<std::string> lab;
+    BTB_TRY(split_labels(labels, n_labels, lab));
+    const std::string tmp = std::string(out_csv) + ".tmp";
+    int rc;
+    {
+        FileBytes fb;                                    // unmapped before the rename below
+        BTB_TRY(load_file(in_csv, fb));
+        FILE *fo = fopen(tmp.c_str(), "wb");
+        if (!fo) return fail(BTB_EIO, "cannot open '%s' for writing", tmp.c_str());
+        setvbuf(fo, nullptr, _IOFBF, 1 << 22);
+        rc = relabel_csv(fb, sep, lab, fo);
+        if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp.c_str());
+    }
+    if (rc != BTB_OK) { remove(tmp.c_str()); return rc; }
+    unlink(out_csv);
+    if (rename(tmp.c_str(), out_csv) != 0) { remove(tmp.c_str()); return fail(BTB_EIO, "cannot rename to '%s'", out_csv); }
+    return BTB_OK;
+}
+
+static int snp_dists_impl(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
+                          char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
+                          const char *labels, int64_t n_labels, int64_t *n_samples, int64_t *seq_len);
+
 extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
                              char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
                              int64_t *n_samples, int64_t *seq_len) {
+    return snp_dists_impl(in_fasta, out_path, allchars, keepcase, molten, sep, corner, quiet, n_gpus, host_threads, engine,
+                          nullptr, 0, n_samples, seq_len);
+}
+
+extern "C" int btb_snp_dists_labelled(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
+                                      char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
+                                      const char *labels, int64_t n_labels, int64_t *n_samples, int64_t *seq_len) {
+    if (!labels) return fail(BTB_EINVAL, "btb_snp_dists_labelled: NULL labels");
+    return snp_dists_impl(in_fasta, out_path, allchars, keepcase, molten, sep, corner, quiet, n_gpus, host_threads, engine,
+                          labels, n_labels, n_samples, seq_len);
+}
+
+static int snp_dists_impl(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
+                          char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
+                          const char *labels, int64_t n_labels, int64_t *n_samples, int64_t *seq_len) {
     if (!in_fasta || !out_path) return fail(BTB_EINVAL, "btb_snp_dists: NULL path");
     const int threads = std::max(1, host_threads);
     if (!quiet) {
@@ -516,6 +619,11 @@ extern "C" int btb_snp_dists(const char *in_fasta, const char *out_path, int all
     if (!quiet) fprintf(stderr, "Read %lld sequences of length %lld\n", (long long)df.n, (long long)df.len);
     if (n_samples) *n_samples = df.n;
     if (seq_len) *seq_len = df.len;
+    if (labels) {                                        // printed instead of the record names
+        if (n_labels != df.n)
+            return fail(BTB_EINVAL, "%lld labels given for %lld sequences", (long long)n_labels, (long long)df.n);
+        BTB_TRY(split_labels(labels, n_labels, df.names));
+    }
     const int64_t n = df.n, len = df.len;
     const int eb = len < 65536 ? 2 : 4;
     const int64_t ld = (n + 7) / 8 * 8;

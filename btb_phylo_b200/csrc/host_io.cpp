@@ -292,4 +292,92 @@ size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *ds
     return size_t(p - dst);
 }
 
+// ---- ViewBovine labels (btbphylo/phylogeny.py:206-216 process_sample_name, btbphylo/utils.py:110-119
+// extract_submission_no).  ASCII rule: drop a trailing "_consensus"; the first substring of the
+// form DD-DDDD[D]-DD (D = decimal digit, leftmost match, five middle digits preferred over four)
+// becomes "AF-" + that substring, otherwise the name stays; the result is upper-cased.
+namespace {
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+
+// Length of the match starting at s[i], or 0.
+size_t submission_match(const std::string &s, size_t i) {
+    const size_t n = s.size();
+    if (i + 10 > n || !is_digit(s[i]) || !is_digit(s[i + 1]) || s[i + 2] != '-') return 0;
+    for (size_t mid = 5; mid >= 4; --mid) {
+        const size_t dash = i + 3 + mid;
+        if (dash + 3 > n) continue;
+        bool ok = true;
+        for (size_t k = i + 3; k < dash && ok; ++k) ok = is_digit(s[k]);
+        if (ok && s[dash] == '-' && is_digit(s[dash + 1]) && is_digit(s[dash + 2])) return dash + 3 - i;
+    }
+    return 0;
+}
+}  // namespace
+
+std::string process_sample_name(const std::string &name) {
+    static const char kSuffix[] = "_consensus";
+    const size_t sl = sizeof(kSuffix) - 1;
+    std::string s = name;
+    if (s.size() >= sl && s.compare(s.size() - sl, sl, kSuffix) == 0) s.resize(s.size() - sl);
+    for (size_t i = 0; i + 10 <= s.size(); ++i) {
+        const size_t m = submission_match(s, i);
+        if (m) { s = "AF-" + s.substr(i, m); break; }
+    }
+    for (char &c : s) if (c >= 'a' && c <= 'z') c = char(c - 'a' + 'A');
+    return s;
+}
+
+// First field of every line after the header line.
+int csv_row_names(const FileBytes &fb, char sep, std::vector<std::string> &names) {
+    names.clear();
+    const char *p = reinterpret_cast<const char *>(fb.data), *end = p + fb.size;
+    const char *nl = static_cast<const char *>(memchr(p, '\n', size_t(end - p)));
+    if (!nl) return BTB_OK;
+    p = nl + 1;
+    while (p < end) {
+        nl = static_cast<const char *>(memchr(p, '\n', size_t(end - p)));
+        const char *line_end = nl ? nl : end;
+        if (line_end > p) {
+            const char *f = static_cast<const char *>(memchr(p, sep, size_t(line_end - p)));
+            names.emplace_back(p, f ? f : line_end);
+        }
+        p = line_end + 1;
+    }
+    return BTB_OK;
+}
+
+int relabel_csv(const FileBytes &fb, char sep, const std::vector<std::string> &labels, FILE *fo) {
+    const char *p = reinterpret_cast<const char *>(fb.data), *end = p + fb.size;
+    const char *nl = static_cast<const char *>(memchr(p, '\n', size_t(end - p)));
+    const char *head_end = nl ? nl : end;
+    int64_t fields = 1;
+    for (const char *q = p; q < head_end; ++q) fields += *q == sep;
+    if (fields - 1 != int64_t(labels.size()))
+        return fail(BTB_EFORMAT, "Length mismatch: Expected axis has %lld elements, new values have %lld elements",
+                    (long long)(fields - 1), (long long)labels.size());
+    const char *corner_end = static_cast<const char *>(memchr(p, sep, size_t(head_end - p)));
+    std::string head(p, corner_end ? corner_end : head_end);
+    for (auto &l : labels) { head.push_back(sep); head += l; }
+    head.push_back('\n');
+    if (fwrite(head.data(), 1, head.size(), fo) != head.size()) return fail(BTB_EIO, "write failed");
+    p = head_end + 1;
+    size_t row = 0;
+    while (p < end) {
+        nl = static_cast<const char *>(memchr(p, '\n', size_t(end - p)));
+        const char *line_end = nl ? nl : end;
+        if (line_end > p) {
+            if (row >= labels.size()) return fail(BTB_EFORMAT, "csv has more rows than labels (%zu)", labels.size());
+            const char *f = static_cast<const char *>(memchr(p, sep, size_t(line_end - p)));
+            if (!f) f = line_end;
+            const std::string &l = labels[row++];
+            if (fwrite(l.data(), 1, l.size(), fo) != l.size() ||
+                fwrite(f, 1, size_t(line_end - f), fo) != size_t(line_end - f) || fputc('\n', fo) == EOF)
+                return fail(BTB_EIO, "write failed");
+        }
+        p = line_end + 1;
+    }
+    if (row != labels.size()) return fail(BTB_EFORMAT, "csv has %zu rows but %zu labels were given", row, labels.size());
+    return BTB_OK;
+}
+
 }  // namespace btb

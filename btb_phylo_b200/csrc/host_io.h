@@ -2,6 +2,7 @@
 // No sequence arithmetic happens here -- only parsing and printing (SURVEY.md App. A.1, A.3 output).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,12 @@ struct StageTimer {
     void mark(const char *stage);
     ~StageTimer();
 };
+
+// ViewBovine label of one sample name (ASCII restatement of btbphylo/phylogeny.py:206-216).
+std::string process_sample_name(const std::string &name);
+// snps.csv helpers behind btb_csv_row_names / btb_relabel_csv.
+int csv_row_names(const FileBytes &fb, char sep, std::vector<std::string> &names);
+int relabel_csv(const FileBytes &fb, char sep, const std::vector<std::string> &labels, FILE *fo);
 
 // Fast decimal formatting of one matrix row segment; returns bytes written.
 size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst);

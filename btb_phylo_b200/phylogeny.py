@@ -14,10 +14,12 @@ calls raise.
 """
 import ctypes
 import os
+import re
 
 from . import _capi
 
-__all__ = ["snp_sites", "build_snp_matrix", "PhylogenyError"]
+__all__ = ["snp_sites", "build_snp_matrix", "post_process_snps_csv", "post_process_snps_df",
+           "process_sample_name", "extract_submission_no", "PhylogenyError"]
 
 
 class PhylogenyError(Exception):
@@ -70,12 +72,93 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=1):
     return metadata
 
 
-def build_snp_matrix(snp_dists_outpath, snp_sites_outpath, threads=1):
+def build_snp_matrix(snp_dists_outpath, snp_sites_outpath, threads=1, post_process=False):
     """Run the snp-dists stage (reference: phylogeny.py:144-150).  `threads` may be int or str
-    (btb_phylo.py:683 passes the CLI string through)."""
+    (btb_phylo.py:683 passes the CLI string through).
+
+    post_process=True (not in the reference signature) makes the CSV writer print the ViewBovine
+    labels directly, i.e. the file is what build_snp_matrix() followed by post_process_snps_csv()
+    (phylogeny.py:172-187, called at btb_phylo.py:598) leaves behind -- without the pandas parse and
+    re-serialisation of the O(N^2) matrix."""
     t = max(1, int(threads))
-    rc = _capi.lib().btb_snp_dists(os.fsencode(snp_sites_outpath), os.fsencode(snp_dists_outpath),
-                                   0, 0, 0, b",", 1, 0, _gpus(), t, _engine(), None, None)
+    if post_process:
+        labels = _labels_for(_names_from(_capi.lib().btb_fasta_names, os.fsencode(snp_sites_outpath), t))
+        blob = "\n".join(labels).encode("utf-8")
+        rc = _capi.lib().btb_snp_dists_labelled(os.fsencode(snp_sites_outpath), os.fsencode(snp_dists_outpath),
+                                                0, 0, 0, b",", 1, 0, _gpus(), t, _engine(), blob, len(labels), None, None)
+    else:
+        rc = _capi.lib().btb_snp_dists(os.fsencode(snp_sites_outpath), os.fsencode(snp_dists_outpath),
+                                       0, 0, 0, b",", 1, 0, _gpus(), t, _engine(), None, None)
     if rc != _capi.OK:
         _raise_like_run("snp-dists -c -j %s %s > %s" % (threads, snp_sites_outpath, snp_dists_outpath),
                         _capi.last_error())
+
+
+# ---------------------------------------------------------------- labels for ViewBovine (SURVEY.md 8f-2)
+_SUBMISSION = re.compile(r"\d{2,2}-\d{4,5}-\d{2,2}")   # the pattern btbphylo/utils.py:116 searches for
+
+
+def extract_submission_no(sample_name):
+    """Submission number of a sample name (reference: btbphylo/utils.py:110-119): the first
+    NN-NNNN[N]-NN run prefixed with 'AF-', or the name itself; upper-cased."""
+    found = _SUBMISSION.search(sample_name)
+    return ("AF-" + found.group(0) if found else sample_name).upper()
+
+
+def process_sample_name(sample_name):
+    """Label used by the cattle / movement datasets (reference: phylogeny.py:206-216): the
+    '_consensus' suffix is dropped, then extract_submission_no() applies."""
+    if sample_name.endswith("_consensus"):
+        sample_name = sample_name[: -len("_consensus")]
+    return extract_submission_no(sample_name)
+
+
+def post_process_snps_df(snp_matrix):
+    """Reference: phylogeny.py:190-203 -- a copy of the dataframe whose index and columns are the
+    processed index labels."""
+    out = snp_matrix.copy(deep=True)
+    labels = snp_matrix.index.map(process_sample_name)
+    out.index = labels
+    out.columns = labels
+    return out
+
+
+# what pandas.read_csv turns into NaN by default; such a row name makes the reference fail
+_PANDAS_NA = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>",
+              "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null"}
+_NUMERIC = re.compile(r"[+-]?(\d+\.?\d*(e[+-]?\d+)?|\.\d+(e[+-]?\d+)?|inf|infinity)", re.IGNORECASE)
+_BOOLS = {"True", "TRUE", "true", "False", "FALSE", "false"}
+
+
+def _names_from(call, *args):
+    n, need = ctypes.c_int64(0), ctypes.c_size_t(0)
+    _capi.check(call(*args, None, 0, ctypes.byref(n), ctypes.byref(need)), "names")
+    buf = ctypes.create_string_buffer(max(1, need.value))
+    _capi.check(call(*args, buf, need.value, ctypes.byref(n), ctypes.byref(need)), "names")
+    return buf.value.decode("utf-8").split("\n") if n.value else []
+
+
+def _labels_for(names):
+    """process_sample_name over the row names, refusing the inputs on which the reference's pandas
+    round trip (read_csv(index_col=0) -> rename -> to_csv) does not give a plain relabelled file:
+    names pandas would read as missing values, an all-numeric / all-boolean index (not strings any
+    more: the reference dies in .endswith), and names that need CSV quoting."""
+    if any(x in _PANDAS_NA for x in names):
+        raise PhylogenyError("sample name read as a missing value by pandas: cannot be relabelled")
+    if names and (all(_NUMERIC.fullmatch(x) for x in names) or all(x in _BOOLS for x in names)):
+        raise PhylogenyError("sample names are all numeric / boolean: pandas would not keep them as strings")
+    if any(x.startswith('"') or "," in x or "\r" in x for x in names):
+        raise PhylogenyError("sample name needs CSV quoting: snps.csv would not parse")
+    # a quote inside a name survives read_csv as a literal and makes to_csv quote the field
+    return ['"%s"' % l.replace('"', '""') if '"' in l else l for l in map(process_sample_name, names)]
+
+
+def post_process_snps_csv(snp_dists_outpath):
+    """Reference: phylogeny.py:172-187 -- rewrites snps.csv in place with the row and column labels
+    processed.  The reference parses all N^2 numbers with pandas and prints them again; here one
+    streaming pass swaps the names and copies every distance byte through (btb_relabel_csv)."""
+    path = os.fsencode(snp_dists_outpath)
+    labels = _labels_for(_names_from(_capi.lib().btb_csv_row_names, path, b","))
+    rc = _capi.lib().btb_relabel_csv(path, path, b",", "\n".join(labels).encode("utf-8"), len(labels))
+    if rc != _capi.OK:
+        raise PhylogenyError("post_process_snps_csv(%s): %s" % (snp_dists_outpath, _capi.last_error()))

@@ -200,6 +200,32 @@ int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n,
                         int64_t row0, int64_t row1, const char *const *names, char sep,
                         int host_threads, char *buf, size_t cap, size_t *written);
 
+/* ---- sample labels: the step after snps.csv ----
+ * btbphylo/phylogeny.py:172-187 post_process_snps_csv parses the O(N^2) snps.csv with pandas only to
+ * rename its row and column labels (phylogeny.py:190-203) with process_sample_name
+ * (phylogeny.py:206-216 + btbphylo/utils.py:110-119) and writes it back.  Here the labels are
+ * printed by the CSV writer directly, or swapped in a finished file by a streaming pass that never
+ * parses a number; both produce the bytes pandas' to_csv would. */
+
+/* ASCII restatement of process_sample_name: strip "_consensus", "AF-" + first DD-DDDD[D]-DD match
+ * (else the name), upper-cased.  out receives a NUL-terminated string. */
+int btb_process_sample_name(const char *name, char *out, size_t cap);
+
+/* Record names of a FASTA file / first field of every data row of a snps.csv, joined by '\n' into
+ * buf (NUL-terminated).  With buf == NULL only *n and *needed (bytes incl. NUL) are set. */
+int btb_fasta_names(const char *in_fasta, int host_threads, char *buf, size_t cap, int64_t *n, size_t *needed);
+int btb_csv_row_names(const char *csv_path, char sep, char *buf, size_t cap, int64_t *n, size_t *needed);
+
+/* btb_snp_dists printing `labels` (n_labels strings joined by '\n', one per sequence, in file order)
+ * in the header row and as row names instead of the FASTA record names. */
+int btb_snp_dists_labelled(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
+                           char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
+                           const char *labels, int64_t n_labels, int64_t *n_samples, int64_t *seq_len);
+
+/* Rewrites in_csv to out_csv (may be the same path) with the header names and the row names
+ * replaced by `labels`; the corner cell and every distance byte are copied through. */
+int btb_relabel_csv(const char *in_csv, const char *out_csv, char sep, const char *labels, int64_t n_labels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,57 @@ def through_reference(ph, tmp, multi_fasta_bytes, tag, postprocess=True):
     return meta
 
 
+def label_fixtures(ph, tmp):
+    """Sample-label vectors.  Inputs: the literal lists the reference's own unit
+    tests hold (tests/phylogeny_test.py test_process_sample_name, tests/utils_test.py
+    test_extract_submission_no -- read from those files with `ast`, nothing is executed) plus a few
+    extra names; expected values: the reference test's own expectation AND what the unmodified
+    reference functions return here.  Then a snps.csv with those names through the unmodified
+    post_process_snps_csv (pandas read_csv -> rename -> to_csv)."""
+    import ast
+
+    def literal_lists(path, func):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name == func:
+                found = {}
+                for st in ast.walk(node):
+                    if isinstance(st, ast.Assign) and isinstance(st.targets[0], ast.Name) and isinstance(st.value, ast.List):
+                        found[st.targets[0].id] = ast.literal_eval(st.value)
+                return found
+        raise KeyError(func)
+
+    import btbphylo.utils as ref_utils
+    pt = literal_lists(os.path.join(REFERENCE, "tests", "phylogeny_test.py"), "test_process_sample_name")
+    ut = literal_lists(os.path.join(REFERENCE, "tests", "utils_test.py"), "test_extract_submission_no")
+    extra = ["af-12-3456-89_consensus", "x_consensus_consensus", "_consensus", "consensus", "123-45678-901",
+             "1-2345-67", "12-345-67", "12-345678-90", "99-1234-5612-34567-89", "AF-61-00123-19_consensus",
+             "s12-3456-78.trimmed", "12-3456-7", "a12-34567-89b", "Sample_12-1234-12_consensus"]
+    fixture = {
+        "process_sample_name": [{"in": i, "ref_test_expects": o, "ref_returns": ph.process_sample_name(i)}
+                                for i, o in zip(pt["test_input"], pt["test_output"])] +
+                               [{"in": i, "ref_test_expects": None, "ref_returns": ph.process_sample_name(i)} for i in extra],
+        "extract_submission_no": [{"in": i, "ref_test_expects": o, "ref_returns": ref_utils.extract_submission_no(i)}
+                                  for i, o in zip(ut["test_input"], ut["test_output"])],
+    }
+    for group in fixture.values():
+        for row in group:
+            assert row["ref_test_expects"] in (None, row["ref_returns"]), row
+    w("labels_expected.json", (json.dumps(fixture, indent=1, sort_keys=True) + "\n").encode())
+
+    # a matrix whose names exercise the relabel (duplicates after mapping included)
+    names = [n for n in dict.fromkeys(pt["test_input"] + extra) if n and not n.isdigit()]
+    seqs = synth.snp_alignment(len(names), 120, seed=31, heavy_n=0.1)
+    fas = os.path.join(tmp, "labels.fas")
+    csv = os.path.join(tmp, "labels.csv")
+    open(fas, "wb").write(synth.fasta_bytes(names, seqs, wrap=0))
+    ph.build_snp_matrix(csv, fas, threads=2)
+    w("labels_snps.fas", open(fas, "rb").read())
+    w("labels_snps.csv", open(csv, "rb").read())
+    ph.post_process_snps_csv(csv)
+    w("labels_snps_postprocessed.csv", open(csv, "rb").read())
+
+
 def main():
     oracle.build(force=True)
     tmp = tempfile.mkdtemp(prefix="golden_")
@@ -167,6 +218,7 @@ def main():
         names = synth.sample_names(4)
         meta = through_reference(ph, tmp, synth.fasta_bytes(names, seqs, wrap=60), "c1")
         assert meta == {"number_of_snps": 831}, meta
+        label_fixtures(ph, tmp)
         print("golden fixtures written to", HERE)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

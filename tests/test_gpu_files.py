@@ -35,6 +35,20 @@ def test_golden_pipeline(ph, tmp_path, tag):
     assert sc.read_bytes() == golden(tag + "_snps.csv")
 
 
+@pytest.mark.parametrize("tag", ["kat3", "c1", "labels"])
+def test_fused_labels_equal_reference_post_processing(ph, tmp_path, tag):
+    """build_snp_matrix(post_process=True) leaves the file that build_snp_matrix + the reference's
+    post_process_snps_csv (phylogeny.py:172-187; golden recorded through it) would."""
+    sf, sc = tmp_path / "snps.fas", tmp_path / "snps.csv"
+    sf.write_bytes(golden(tag + "_snps.fas"))
+    ph.build_snp_matrix(str(sc), str(sf), threads=2, post_process=True)
+    assert sc.read_bytes() == golden(tag + "_snps_postprocessed.csv")
+    ph.build_snp_matrix(str(sc), str(sf), threads=2)
+    assert sc.read_bytes() == golden(tag + "_snps.csv")
+    ph.post_process_snps_csv(str(sc))
+    assert sc.read_bytes() == golden(tag + "_snps_postprocessed.csv")
+
+
 def test_kat1_and_edge_modes_through_capi(capi, oracle, tmp_path):
     lib = capi.lib()
     src = tmp_path / "in.fa"
