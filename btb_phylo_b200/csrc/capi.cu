@@ -39,6 +39,8 @@ int distance_rows_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, vo
 extern int g_umma_cta_group;
 extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
+extern int g_umma_dbg_negate;
+extern int g_umma_prefetch;
 extern int g_umma_tile_mode;
 extern int g_pack_wpt;
 int umma_max_active_clusters(int cg, int *out);
@@ -107,8 +109,11 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
+    if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_dbg_negate")) { g_umma_dbg_negate = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
-    if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value < 0 ? 0 : value; return BTB_OK; }
     if (key && !strcmp(key, "umma_cg2_variant")) { g_umma_cg2_variant = value & 3; return BTB_OK; }
     if (key && !strcmp(key, "umma_dense_simplex")) { g_umma_dense_simplex = value < 0 || value > 2 ? 0 : value; return BTB_OK; }
     return fail(BTB_EINVAL, "unknown option");

@@ -103,12 +103,24 @@ extern int g_umma_dense_simplex;
 // tcgen05.mma kind::mxf4 (unit block scales) at twice the int8 rate.  The fp32 accumulators hold
 // exact integers as long as a row's dot product stays below 2^24, i.e. 3 len < 2^24.
 extern int g_umma_fp4;
-inline bool umma_use_fp4(int sigma, int64_t len) {
+inline bool umma_fp4_dense(int sigma, int64_t len) {
     return sigma_dense(sigma) && g_umma_fp4 && g_umma_dense_simplex == 2 && 3 * len < (int64_t(1) << 24);
 }
+// g_umma_fp4_general ("umma_fp4_general", default on): every other alphabet (ignored bytes present,
+// or -a with more than four symbols) as sigma + 1 nibble planes per row -- validity V, then the
+// one-hot planes X_s -- in ONE operand that serves both sides: d = V_i.V_j - sum_s X_s,i.X_s,j, the
+// X blocks multiplied with the descriptor's negate-A bit.  (sigma + 1) / 2 bytes per site instead of
+// 2 * sigma int8 bytes, and the mxf4 rate.
+extern int g_umma_fp4_general;
+inline bool umma_fp4_general(int sigma, int64_t len) {
+    return !sigma_dense(sigma) && sigma >= 1 && g_umma_fp4 && g_umma_fp4_general && len < (int64_t(1) << 24);
+}
+inline bool umma_use_fp4(int sigma, int64_t len) { return umma_fp4_dense(sigma, len) || umma_fp4_general(sigma, len); }
+inline int64_t umma_fp4_plane_bytes(int64_t len) { return (len + 255) / 256 * 128; }   // one nibble plane, whole K blocks
 inline int umma_bytes_per_site(int sigma) { return sigma_dense(sigma) ? (g_umma_dense_simplex ? 3 : 4) : sigma4_of(sigma); }
 inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple of 128
-    int64_t k = umma_use_fp4(sigma, len) ? (len * 3 + 1) / 2 : len * umma_bytes_per_site(sigma);
+    if (umma_fp4_general(sigma, len)) return (sigma + 1) * umma_fp4_plane_bytes(len);
+    int64_t k = umma_fp4_dense(sigma, len) ? (len * 3 + 1) / 2 : len * umma_bytes_per_site(sigma);
     return (k + 127) / 128 * 128;
 }
 

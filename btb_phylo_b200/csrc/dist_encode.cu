@@ -303,6 +303,57 @@ encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int6
     }
 }
 
+// general alphabets as packed e2m1 nibbles (1.0 = 0x2): plane 0 = validity (site not ignored), planes
+// 1..sigma = one-hot of the symbol code; every plane is `plane_bytes` long (len nibbles padded to a
+// whole 128-byte K block), planes follow each other along K.  d = dot(V_i, V_j) - sum_s dot(X_s,i, X_s,j):
+// the kernel multiplies the X blocks with the negate-A bit of the instruction descriptor.
+// One thread per 32 sites -> one 16-byte store per plane.
+__global__ void __launch_bounds__(256)
+encode_fp4_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                         const uint8_t *__restrict__ table_g, int sigma, int64_t plane_bytes, int64_t kbytes,
+                         uint8_t *__restrict__ A, int aligned) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int64_t groups = plane_bytes / 16;
+    const bool vec_in = aligned && (row_stride % 16 == 0) && (reinterpret_cast<uintptr_t>(seqs) % 16 == 0);
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+        const uint8_t *p = seqs + row * row_stride;
+        uint8_t *dst = A + row * kbytes;
+        for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
+             g += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t site = g * 32;
+            uint32_t raw[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) raw[q] = 0x2e2e2e2eu;                    // '.' = ignored
+            if (vec_in && site + 31 < len) {
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(p + site);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(p + site + 16);
+                raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w;
+                raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+            } else {
+                for (int b = 0; b < 32; ++b)
+                    if (site + b < len) raw[b >> 2] = (raw[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (uint32_t(p[site + b]) << (8 * (b & 3)));
+            }
+            uint32_t code[8];                               // 4 symbol codes per word
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                code[q] = uint32_t(table[raw[q] & 0xff]) | (uint32_t(table[(raw[q] >> 8) & 0xff]) << 8) |
+                          (uint32_t(table[(raw[q] >> 16) & 0xff]) << 16) | (uint32_t(table[raw[q] >> 24]) << 24);
+            for (int plane = 0; plane <= sigma; ++plane) {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    const uint32_t c = (code[b >> 2] >> (8 * (b & 3))) & 0xff;
+                    const bool hot = plane == 0 ? c != 0xff : c == uint32_t(plane - 1);
+                    w[b >> 3] |= (hot ? 2u : 0u) << (4 * (b & 7));
+                }
+                *reinterpret_cast<uint4 *>(dst + plane * plane_bytes + g * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+}
+
 }  // namespace btb
 
 using namespace btb;
@@ -361,7 +412,7 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
 
 extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma) {
     if (engine == BTB_ENGINE_POPC) return (popc_code_planes(sigma) + (sigma_dense(sigma) ? 0 : 1)) * n * popc_words(len) * 4;
-    if (engine == BTB_ENGINE_UMMA) return (sigma_dense(sigma) ? 1 : 2) * n * umma_k_bytes(len, sigma) + n * 4;
+    if (engine == BTB_ENGINE_UMMA) return (sigma_dense(sigma) || umma_use_fp4(sigma, len) ? 1 : 2) * n * umma_k_bytes(len, sigma) + n * 4;
     return -1;
 }
 
@@ -391,7 +442,11 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
         const int64_t kb = umma_k_bytes(len, sigma);
         uint8_t *A = static_cast<uint8_t *>(d_operands);
         uint8_t *B = A + n * kb;
-        if (umma_use_fp4(sigma, len)) {
+        if (umma_fp4_general(sigma, len)) {
+            const int64_t pb = umma_fp4_plane_bytes(len);
+            dim3 grid((unsigned)std::min<int64_t>((pb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            encode_fp4_planes_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, sigma, pb, kb, A, aligned ? 1 : 0);
+        } else if (umma_fp4_dense(sigma, len)) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
             BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));

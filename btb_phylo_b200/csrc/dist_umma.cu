@@ -205,6 +205,11 @@ struct UmmaParams {
     const int2 *worklist;      // FP4 full-tile kernel: (block row I, 240-column block j) per unit
     const int2 *sq_list;       // optional explicit list of square tiles (I, J) replacing the band enumeration
     unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
+    int lock_slack = 0;        // a producer may run this many rounds ahead of the slowest one (0 = strict)
+    int prefetch = 0;          // FP4 full-tile kernel: K blocks of L2 prefetch distance (0 = off)
+    int64_t neg_from = INT64_MAX;   // kind::mxf4: K blocks >= neg_from are subtracted (general alphabets: V blocks - X blocks)
+    int64_t b_shift = 0;       // 0: subtract with the instruction descriptor's negate-A bit; else B reads K block kb + b_shift
+                               //    (a sign-flipped copy of the X blocks)
     unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
 };
 
@@ -405,6 +410,7 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * total_workers;
                     if (round > full_rounds - 1) target += last_count * per_cta;
                     (void)total_workers;
+                    target -= int64_t(p.lock_slack) * n_workers;
                     __threadfence();
                     atomicAdd(p.lockstep, 1u);
                     while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
@@ -577,6 +583,7 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const int64_t last_count = p.units - full_rounds * n_workers;
                     int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
                     if (round > full_rounds - 1) target += last_count;
+                    target -= int64_t(p.lock_slack) * n_workers;
                     __threadfence();
                     atomicAdd(p.lockstep, 1u);
                     while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
@@ -585,7 +592,7 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), m0);
-                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), n0);
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -678,6 +685,7 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, uint32_t v) {
 }
 // block-scaled instruction descriptor, kind::mxf4: A/B = E2M1 (1 at [7,10) / [10,13)), K-major,
 // N>>3 at [17,23), scale format UE8M0 (1 at bit 23), M>>4 at [24,29), scale-factor ids 0, K64 dense
+constexpr uint32_t kNegateA = 1u << 13;                     // instruction descriptor: use -A
 __host__ __device__ constexpr uint32_t make_mxf4_idesc(int M, int N) {
     return (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (1u << 23) | (uint32_t(M >> 4) << 24);
 }
@@ -745,6 +753,7 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     const int64_t last_count = p.units - full_rounds * n_workers;
                     int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
                     if (round > full_rounds - 1) target += last_count;
+                    target -= int64_t(p.lock_slack) * n_workers;
                     __threadfence();
                     atomicAdd(p.lockstep, 1u);
                     while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
@@ -753,14 +762,14 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), int(m0));
-                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), int(n0));
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * kBlockK), int(n0));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_mxf4_idesc(128, kAccCols);
+        constexpr uint32_t idesc0 = make_mxf4_idesc(128, kAccCols);
         int stage = 0;
         uint32_t phase = 0;
         int64_t it = 0;
@@ -771,6 +780,7 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (elect_one()) {
+                    const uint32_t idesc = idesc0 | ((kb >= p.neg_from && p.b_shift == 0) ? kNegateA : 0u);
                     const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
                     const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
@@ -813,6 +823,7 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // come from a host-built work list in row-band order; cells are written where column >= row and
 // mirrored where column > row, so any set of whole block rows covers exactly the same cells as the
 // square-tile enumeration.
+constexpr int kUnitColMask = 0xffff, kUnitPrefA = 1 << 16, kUnitPrefB = 1 << 17;   // work-list entry .y
 struct Fp4TileCfg {
     static constexpr int kBN = 240;
     static constexpr int kABytes = 256 * kBlockK;                     // 32 KB
@@ -820,7 +831,14 @@ struct Fp4TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB (multiple of 1024)
     static constexpr int kStages = 3;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kPrefetch = 0;                               // K blocks the optional L2 prefetch runs ahead (measured: no gain,
+                                                                      // the kernel sits at the L2 -> SM throughput cap, not on DRAM latency)
 };
+
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -867,37 +885,57 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            const int64_t pf = p.prefetch;
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 const int2 w = p.worklist[u];
-                const int m0 = w.x * BTB_TILE, n0 = w.y * Cfg::kBN;
+                const int m0 = w.x * BTB_TILE, n0 = (w.y & kUnitColMask) * Cfg::kBN;
+                // next unit of this CTA: its first K blocks are prefetched while this unit finishes
+                const int2 wn = u + n_workers < p.units ? p.worklist[u + n_workers] : make_int2(0, 0);
+                if (u == worker)
+                    for (int64_t kb = 0; kb < pf && kb < p.k_blocks; ++kb) {
+                        if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(kb * kBlockK), m0);
+                        if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int(kb * kBlockK), n0);
+                    }
                 if (p.lockstep && u != worker) {                 // see dist_umma_kernel
                     const int64_t round = (u - worker) / n_workers;
                     const int64_t full_rounds = p.units / n_workers;
                     const int64_t last_count = p.units - full_rounds * n_workers;
                     int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
                     if (round > full_rounds - 1) target += last_count;
+                    target -= int64_t(p.lock_slack) * n_workers;
                     __threadfence();
                     atomicAdd(p.lockstep, 1u);
                     while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
                 }
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    if (pf) {
+                        const int64_t ka = kb + pf;
+                        if (ka < p.k_blocks) {
+                            if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(ka * kBlockK), m0);
+                            if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka + (ka >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
+                        } else if (ka - p.k_blocks < p.k_blocks) {
+                            if (wn.y & kUnitPrefA) tma_prefetch_2d(&map_a, int((ka - p.k_blocks) * kBlockK), wn.x * BTB_TILE);
+                            if (wn.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka - p.k_blocks) * kBlockK), (wn.y & kUnitColMask) * Cfg::kBN);
+                        }
+                    }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), m0);
-                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int(kb * kBlockK), n0);
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_mxf4_idesc(128, Cfg::kBN);
+        constexpr uint32_t idesc0 = make_mxf4_idesc(128, Cfg::kBN);
         int stage = 0;
         uint32_t phase = 0;
         int64_t it = 0;
         for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
             const uint32_t drained = (uint32_t(it) & 1u) ^ 1u;
             for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                const uint32_t idesc = idesc0 | ((kb >= p.neg_from && p.b_shift == 0) ? kNegateA : 0u);
                 mbar_wait(full_bar(stage), phase);
                 if (kb == 0) mbar_wait(tempty_bar(0), drained);
                 tc_fence_after();
@@ -930,7 +968,7 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         int64_t it = 0;
         for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
             const int2 w = p.worklist[u];
-            const int64_t n0 = int64_t(w.y) * Cfg::kBN;
+            const int64_t n0 = int64_t(w.y & kUnitColMask) * Cfg::kBN;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 mbar_wait(tfull_bar(h), uint32_t(it) & 1u);
@@ -984,9 +1022,12 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 }
 
 int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
-int g_umma_fp4 = 1;            // kind::mxf4 path for dense alignments (see common.cuh); 0 = int8 only
+int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
+int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
+int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
+int g_umma_dbg_negate = 0;     // experiment: negate every K block of the FP4 kernels (probes the descriptor bit)
 int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
-int g_umma_lockstep = 1;       // producers of all CTAs start each unit together (L2 reuse), cooperative launch
+int g_umma_lockstep = 1;       // 0: off; k >= 1: producers of all CTAs start each unit at most k-1 rounds apart (L2 reuse), cooperative launch
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
@@ -1017,7 +1058,7 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     if (g_umma_lockstep && p.units > ctas / (CG == 2 ? 2 : 1) && dev < 16) {
         if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
         BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        q.lockstep = d_lock[dev];
+        q.lockstep = d_lock[dev]; q.lock_slack = g_umma_lockstep - 1;
         attrs2[0] = attr[0];
         attrs2[1].id = cudaLaunchAttributeCooperative;
         attrs2[1].val.cooperative = 1;
@@ -1067,7 +1108,7 @@ static int launch_umma_tile(const CUtensorMap &ma, const CUtensorMap &mb, const 
     if (g_umma_lockstep && p.units > ctas && dev < 16) {
         if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
         BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        q.lockstep = d_lock[dev];
+        q.lockstep = d_lock[dev]; q.lock_slack = g_umma_lockstep - 1;
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
@@ -1135,6 +1176,21 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
                 for (int64_t I = r0; I < r1; ++I)
                     if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h.push_back(make_int2(int(I), int(j)));
         }
+        // L2 prefetch duty: the grid runs the list in rounds of one unit per SM; within a round the
+        // first unit that touches an A panel (block row) / a B panel (column block) prefetches it
+        int sms = 0;
+        BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        for (size_t r0 = 0; r0 < h.size(); r0 += size_t(sms)) {
+            const size_t r1 = std::min(h.size(), r0 + size_t(sms));
+            for (size_t a = r0; a < r1; ++a) {
+                bool first_a = true, first_b = true;
+                for (size_t b = r0; b < a; ++b) {
+                    if (h[b].x == h[a].x) first_a = false;
+                    if ((h[b].y & kUnitColMask) == (h[a].y & kUnitColMask)) first_b = false;
+                }
+                h[a].y |= (first_a ? kUnitPrefA : 0) | (first_b ? kUnitPrefB : 0);
+            }
+        }
     }
     DevList e{n, lo, hi, kind, nullptr, int64_t(h.size())};
     BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&e.d), std::max<size_t>(h.size(), 1) * sizeof(int2)));
@@ -1147,7 +1203,7 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
 
 // FP4 full-tile kernel over the block rows [row_lo, row_hi); *launched = 0 when the range is too
 // small to fill the GPU twice (the caller then uses the half-tile kernel)
-static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t row_lo, int64_t row_hi, void *d_out,
+static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_from, int64_t row_lo, int64_t row_hi, void *d_out,
                            int out_elem_bytes, int64_t out_ld, int mirror, cudaStream_t stream, int *launched) {
     *launched = 0;
     int dev = 0, sms = 0;
@@ -1164,8 +1220,11 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t row_
     p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
     p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
     p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
-    p.dense = 3; p.bias = 0;
+    p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;            // tetrahedron code (row sums) / V - X planes
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+    if (neg_from >= 0) p.neg_from = neg_from;
+    if (g_umma_dbg_negate) p.neg_from = 0;
+    p.prefetch = g_umma_prefetch;
     const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -1178,7 +1237,7 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t row_
     if (g_umma_lockstep && p.units > ctas) {
         if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
         BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        p.lockstep = d_lock[dev];
+        p.lockstep = d_lock[dev]; p.lock_slack = g_umma_lockstep - 1;
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
@@ -1205,6 +1264,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const uint8_t *A = static_cast<const uint8_t *>(d_operands);
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
+    const int64_t neg_from = umma_fp4_general(sigma, len) ? umma_fp4_plane_bytes(len) / kBlockK : -1;
     CUtensorMap ma, mb;
     if (!sq_list && umma_use_fp4(sigma, len) && g_umma_tile_mode == 1 && out_mode == 0) {
         // whole bands of block rows (the full matrix, the level-1/2 band launches): rectangular full tiles
@@ -1217,7 +1277,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         }
         if (rb0 >= 0 && rb1 > rb0) {
             int launched = 0;
-            BTB_TRY(launch_fp4_rows(A, n, kb, rb0, rb1, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
+            BTB_TRY(launch_fp4_rows(A, n, kb, neg_from, rb0, rb1, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
             if (launched) return BTB_OK;
         }
     }
@@ -1228,8 +1288,10 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles * 2;
         p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
         p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr; p.sq_list = sq_list;
-        p.dense = 3; p.bias = 0;
+        p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;
         p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+        if (neg_from >= 0) p.neg_from = neg_from;
+        if (g_umma_dbg_negate) p.neg_from = 0;
         int dev = 0, sms = 0;
         BTB_CUDA(cudaGetDevice(&dev));
         BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1245,7 +1307,7 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         if (g_umma_lockstep && p.units > ctas && dev < 16) {
             if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
             BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-            p.lockstep = d_lock[dev];
+            p.lockstep = d_lock[dev]; p.lock_slack = g_umma_lockstep - 1;
             attr[0].id = cudaLaunchAttributeCooperative;
             attr[0].val.cooperative = 1;
             cfg.attrs = attr;
@@ -1318,7 +1380,8 @@ int distance_rows_umma(const void *d_operands, int64_t n, int64_t len, int sigma
     const uint8_t *A = static_cast<const uint8_t *>(d_operands);
     if (umma_use_fp4(sigma, len) && g_umma_tile_mode == 1) {
         int launched = 0;
-        BTB_TRY(launch_fp4_rows(A, n, kb, row_lo, row_hi, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
+        const int64_t neg_from = umma_fp4_general(sigma, len) ? umma_fp4_plane_bytes(len) / kBlockK : -1;
+        BTB_TRY(launch_fp4_rows(A, n, kb, neg_from, row_lo, row_hi, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));
         if (launched) return BTB_OK;
     }
     const int2 *d_list = nullptr;

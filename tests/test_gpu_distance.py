@@ -88,11 +88,32 @@ def test_kernel_variants_agree(capi, oracle):
                 for cg in (1, 2):
                     plan, got = gpu_matrix(capi, dense, 1, cg)
                     assert plan.sigma == capi.SIGMA_DENSE4 and (got == want_d).all(), (fp4, code, cg)
-        for tile_mode in (0, 1):                             # half-tile units / one CTA per full tile (int8)
+        big = synth.snp_alignment(6400, 777, seed=14, heavy_n=0.05)    # 325 tiles >= 2 per SM: the full-tile kernels engage
+        iupac = synth.snp_alignment(900, 2500, seed=15, heavy_n=0.2, lower=0.01)
+        iupac[::7, ::5] = ord("R"); iupac[::11, ::3] = ord("y"); iupac[::13, ::17] = ord("-"); iupac[5::9, 1::4] = ord("K")
+        want_big = oracle.snp_dists_rows(big, threads=8)
+        big_dense = synth.snp_alignment(6400, 777, seed=14)
+        want_big_dense = oracle.snp_dists_rows(big_dense, threads=8)
+        for tile_mode in (0, 1):
             capi.check(lib.btb_set_option(b"umma_tile_mode", tile_mode))
-            big = synth.snp_alignment(6400, 777, seed=14)    # 325 tiles >= 2 per SM: the full-tile kernel engages
-            _, got = gpu_matrix(capi, big, 1, 1)
-            assert (got == oracle.snp_dists_rows(big, threads=8)).all(), tile_mode
+            for fp4 in (1, 0):
+                capi.check(lib.btb_set_option(b"umma_fp4", fp4))
+                plan, got = gpu_matrix(capi, big_dense, 1, 1)
+                assert plan.sigma == capi.SIGMA_DENSE4 and (got == want_big_dense).all(), (tile_mode, fp4)
+        capi.check(lib.btb_set_option(b"umma_fp4", 1))
+        want_iupac = oracle.snp_dists_rows(iupac, allchars=True, threads=8)
+        for general_fp4 in (1, 0):                           # V - X nibble planes on kind::mxf4 / int8 one-hot x complement
+            capi.check(lib.btb_set_option(b"umma_fp4_general", general_fp4))
+            for tile_mode in (0, 1):                         # half-tile units / one CTA per full tile
+                capi.check(lib.btb_set_option(b"umma_tile_mode", tile_mode))
+                plan, got = gpu_matrix(capi, big, 1, 1)
+                assert plan.sigma == 4 and (got == want_big).all(), (general_fp4, tile_mode)
+                plan, got = gpu_matrix(capi, iupac, 1, 1, allchars=True)
+                assert plan.sigma > 4 and (got == want_iupac).all(), (general_fp4, tile_mode, plan.sigma)
+                _, got = gpu_matrix(capi, general, 1, 1)
+                assert (got == want_g).all(), (general_fp4, tile_mode)
+        capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
+        capi.check(lib.btb_set_option(b"umma_fp4_general", 0))   # the CTA-pair variants are int8 kernels
         capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
         for variant in (0, 1, 2, 3):
             capi.check(lib.btb_set_option(b"umma_cg2_variant", variant))
@@ -103,6 +124,7 @@ def test_kernel_variants_agree(capi, oracle):
     finally:
         capi.check(lib.btb_set_option(b"umma_dense_simplex", 2))
         capi.check(lib.btb_set_option(b"umma_fp4", 1))
+        capi.check(lib.btb_set_option(b"umma_fp4_general", 1))
         capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
         capi.check(lib.btb_set_option(b"umma_cg2_variant", 0))
         capi.check(lib.btb_set_option(b"umma_cta_group", 1))
