@@ -41,6 +41,9 @@ extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
 extern int g_umma_dbg_negate;
 extern int g_umma_prefetch;
+void set_ingest_predict(int v);
+int get_ingest_predict();
+int get_ingest_last();
 extern int g_umma_tile_mode;
 extern int g_pack_wpt;
 int umma_max_active_clusters(int cg, int *out);
@@ -110,6 +113,7 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
+    if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_dbg_negate")) { g_umma_dbg_negate = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
@@ -128,6 +132,8 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
     if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
     if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
+    if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }
+    if (!strcmp(key, "ingest_last_predicted")) { *value = get_ingest_last(); return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
 }
 

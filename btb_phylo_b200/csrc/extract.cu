@@ -122,10 +122,14 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     const uint32_t c = cb + 32u * kPackWordsPerThread * threadIdx.x;
     uint32_t out_v[kPackWordsPerThread], out_0[kPackWordsPerThread], out_1[kPackWordsPerThread];
     uint32_t nonctl = 0x80808080u;
-    bool irregular = false;
+    bool irregular = false, marker = false;
     const uint32_t line = (W && c < ce) ? c / W : 0u;
     uint32_t pos = W ? c - line * W : 0u;                  // column inside the current line
     uint32_t o = uint32_t(rec + int64_t(c) + int64_t(line) * e - alo);      // byte offset inside the staged span
+    // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the
+    // parser the tools share (it opens the next record / a quality block): the host must re-index
+    auto is_marker = [](uint8_t b) { return b == '>' || b == '@' || b == '+'; };
+    if (c < ce && pos == 0 && (W || c == 0)) marker = is_marker(stage[skew<kSkew>(o)]);
 #pragma unroll
     for (int wi = 0; wi < kPackWordsPerThread; ++wi) {
         uint32_t fv = 0, f0 = 0, f1 = 0;
@@ -168,6 +172,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
                     const uint32_t t = o + rem;
                     if (e == 1) irregular |= stage[skew<kSkew>(t)] != '\n';
                     else irregular |= (stage[skew<kSkew>(t)] != '\r') | (stage[skew<kSkew>(t + 1)] != '\n');
+                    marker |= is_marker(stage[skew<kSkew>(t + e)]);      // first byte of the next line
                 }
                 o += 32u + e;
                 pos = 32u - rem;
@@ -189,6 +194,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         }
     }
     if (irregular || (nonctl & 0x80808080u) != 0x80808080u) atomicOr(&flags[i], 1);
+    if (marker) atomicOr(&flags[i], 2);
 }
 
 // ------------------------------------------------------------------------------------------ k2

@@ -244,6 +244,123 @@ int index_fasta(const FileBytes &fb, std::vector<FastaRecord> &recs, int threads
     return BTB_OK;
 }
 
+// ------------------------------------------------------------------------------ predicted framing
+SourceFile::~SourceFile() { if (fd >= 0) close(fd); }
+
+int open_sources(const char *const *paths, int64_t n_paths, std::vector<SourceFile> &files) {
+    files.clear();
+    files.reserve(size_t(n_paths));
+    for (int64_t i = 0; i < n_paths; ++i) {
+        SourceFile f;
+        f.path = paths[i];
+        f.fd = open(paths[i], O_RDONLY);
+        struct stat st;
+        if (f.fd < 0 || fstat(f.fd, &st) != 0) return fail(BTB_EIO, "ERROR: Could not open filename '%s'", paths[i]);
+        f.size = size_t(st.st_size);
+        files.push_back(std::move(f));
+    }
+    return BTB_OK;
+}
+
+int read_exact(const SourceFile &f, size_t off, size_t len, uint8_t *dst) {
+    while (len) {
+        const ssize_t k = pread(f.fd, dst, len, off_t(off));
+        if (k <= 0) return fail(BTB_EIO, "ERROR: short read from '%s'", f.path.c_str());
+        dst += k; off += size_t(k); len -= size_t(k);
+    }
+    return BTB_OK;
+}
+
+int frame_predicted(const std::vector<SourceFile> &files, std::vector<FastaRecord> &recs, bool *fast) {
+    recs.clear();
+    *fast = false;
+    constexpr size_t kHead = 4096, kScan = size_t(1) << 20, kMaxFirst = size_t(1) << 30;
+    bool have_tpl = false, open_end = false;      // open_end: the previous record had no final terminator
+    FastaRecord tpl;
+    size_t tpl_trail = 0;                          // terminator bytes that close the template record
+    std::vector<uint8_t> head(kHead + 2), first;
+    for (size_t fi = 0; fi < files.size(); ++fi) {
+        const SourceFile &f = files[fi];
+        size_t pos = 0;
+        while (pos < f.size) {
+            if (open_end) return BTB_OK;           // bytes follow an unterminated line: they would join it
+            const size_t hn = std::min(kHead, f.size - pos);
+            BTB_TRY(read_exact(f, pos, hn, head.data()));
+            if (head[0] != '>') return BTB_OK;     // gzip, FASTQ, leading junk, ...
+            const void *nl = memchr(head.data(), '\n', hn);
+            if (!nl) return BTB_OK;
+            const size_t hl = size_t(static_cast<const uint8_t *>(nl) - head.data());
+            FastaRecord r;
+            size_t ne = 1;
+            while (ne < hl && !is_space(head[ne])) ++ne;
+            r.name.assign(reinterpret_cast<const char *>(head.data() + 1), ne - 1);
+            r.file = int32_t(fi);
+            r.seq_off = pos + hl + 1;
+            if (!have_tpl) {
+                // the first record is framed exactly: read on until a line starts with a marker
+                first.clear();
+                size_t at = r.seq_off, end = f.size;
+                bool found = false;
+                while (at < f.size && !found) {
+                    const size_t n = std::min(kScan, f.size - at), base = first.size();
+                    if (base + n > kMaxFirst) return BTB_OK;
+                    first.resize(base + n);
+                    BTB_TRY(read_exact(f, at, n, first.data() + base));
+                    for (size_t k = base; k < base + n; ++k) {
+                        const uint8_t c = first[k];
+                        if ((c == '>' || c == '@' || c == '+') && (k == 0 || first[k - 1] == '\n')) {
+                            if (c != '>') return BTB_OK;           // FASTQ-style input
+                            end = r.seq_off + k;
+                            first.resize(k);
+                            found = true;
+                            break;
+                        }
+                    }
+                    at += n;
+                }
+                r.raw_len = end - r.seq_off;
+                FileBytes view;
+                view.data = first.data();
+                view.size = first.size();
+                FastaRecord probe = r;
+                probe.seq_off = 0;
+                describe_layout(view, probe);
+                if (!probe.regular || probe.seq_len <= 0 || (probe.line_w > 0 && probe.line_w < 32)) return BTB_OK;
+                size_t R = r.raw_len;
+                while (R > 0 && (first[R - 1] == '\n' || first[R - 1] == '\r')) --R;
+                tpl_trail = r.raw_len - R;
+                if (tpl_trail != 0 && tpl_trail != size_t(probe.eol)) return BTB_OK;     // blank lines at the end
+                if (tpl_trail == 0 && end != f.size) return BTB_OK;
+                r.line_w = probe.line_w; r.eol = probe.eol; r.seq_len = probe.seq_len; r.regular = true;
+                tpl = r;
+                tpl.raw_len = R;                   // template length without the closing terminator
+                if (tpl_trail == 0) { tpl_trail = size_t(probe.eol); open_end = true; }
+                have_tpl = true;
+                pos = end;
+            } else {
+                size_t end = r.seq_off + tpl.raw_len + tpl_trail;
+                if (end > f.size) {
+                    if (r.seq_off + tpl.raw_len != f.size) return BTB_OK;
+                    end = f.size;                  // last line not terminated
+                    open_end = true;
+                } else {
+                    uint8_t t[3] = {0, 0, 0};      // closing terminator, then the next header (or the end)
+                    const size_t tn = std::min<size_t>(tpl_trail + 1, f.size - (end - tpl_trail));
+                    BTB_TRY(read_exact(f, end - tpl_trail, tn, t));
+                    if (t[tpl_trail - 1] != '\n' || (tpl_trail == 2 && t[0] != '\r')) return BTB_OK;
+                    if (tn > tpl_trail && t[tpl_trail] != '>') return BTB_OK;
+                }
+                r.raw_len = end - r.seq_off;
+                r.line_w = tpl.line_w; r.eol = tpl.eol; r.seq_len = tpl.seq_len; r.regular = true;
+                pos = end;
+            }
+            recs.push_back(std::move(r));
+        }
+    }
+    *fast = !recs.empty();
+    return BTB_OK;
+}
+
 // ------------------------------------------------------------------------------ decimal output
 namespace {
 struct DigitLut {

@@ -31,12 +31,38 @@ struct FastaRecord {
     int32_t line_w = 0;      // bases per line (0 = single line)
     int32_t eol = 1;         // line terminator bytes (1 = "\n", 2 = "\r\n")
     bool regular = false;    // every line but the last has line_w bases followed by eol bytes
+    int32_t file = 0;        // predicted framing: index of the SourceFile the offsets refer to
 };
 
 // Finds the records (kseq framing: a record starts at '>' or '@' that is the first byte of a line,
 // the first one at the first marker anywhere).  Fills name / seq_off / raw_len and, by looking at
 // the first line and the region length only, the tentative regular layout.
 int index_fasta(const FileBytes &fb, std::vector<FastaRecord> &recs, int threads);
+
+// ---- predicted framing (the fast ingest path of btb_snp_sites) ----------------------------------
+// Consensus FASTA files are N records of one layout: same genome length, same line width, same
+// terminators.  Instead of scanning every byte for record markers, frame the first record exactly
+// and PREDICT the others: record i+1's header must start where record i's region ends, its region
+// has the same byte length.  The host checks the header byte and the terminator at each predicted
+// boundary; everything in between is checked by the pack kernel, which reads every byte anyway
+// (flag 1: a terminator is missing or a control byte sits among the bases, flag 2: a line starts
+// with '>', '@' or '+').  Any failed check sends the whole call through the exact path
+// (load_file + index_fasta), so results never depend on the prediction.
+struct SourceFile {
+    std::string path;
+    int fd = -1;
+    size_t size = 0;
+    SourceFile() = default;
+    SourceFile(const SourceFile &) = delete;
+    SourceFile &operator=(const SourceFile &) = delete;
+    SourceFile(SourceFile &&o) noexcept : path(std::move(o.path)), fd(o.fd), size(o.size) { o.fd = -1; }
+    ~SourceFile();
+};
+int open_sources(const char *const *paths, int64_t n_paths, std::vector<SourceFile> &files);   // BTB_EIO on failure
+// *fast = false: not predictable (gzip, FASTQ, irregular or mixed layouts, ...) -- use the exact path.
+int frame_predicted(const std::vector<SourceFile> &files, std::vector<FastaRecord> &recs, bool *fast);
+// pread that loops until len bytes are in (BTB_EIO on a short file)
+int read_exact(const SourceFile &f, size_t off, size_t len, uint8_t *dst);
 
 // Exact kseq-style walk of one record's sequence region: appends the kept bytes to `out`
 // (or only counts them when out == nullptr).  Returns the sequence length.

@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -133,6 +134,14 @@ extern "C" int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64
 
 namespace {
 
+// Where the record bytes come from: the mapped / inflated file of the exact path, or the open files
+// of the predicted framing (pread straight into the pinned staging buffers).
+struct ByteSource {
+    const FileBytes *fb = nullptr;
+    const std::vector<SourceFile> *files = nullptr;
+};
+constexpr int kRetryExact = 1000;      // internal: the predicted framing did not hold, run the exact path
+
 // One device's share of the extraction stage: samples [s0, s1) of the file, their planes and the
 // staging pipeline (host threads copy record bytes into pinned chunks, H2D, k1).
 struct ExtractCtx {
@@ -182,7 +191,7 @@ struct ExtractCtx {
     }
 
     // stage records [i0, i1) (global indices) into buffer b; `force_walk` re-stages with the exact walk
-    int run_chunk(const FileBytes &fb, const std::vector<FastaRecord> &recs, int64_t G, int b, int64_t i0, int64_t i1, bool force_walk) {
+    int run_chunk(const ByteSource &src, const std::vector<FastaRecord> &recs, int64_t G, int b, int64_t i0, int64_t i1, bool force_walk) {
         if (used[b]) BTB_CUDA(cudaEventSynchronize(done[b]));
         uint8_t *dst = h_text[b].as<uint8_t>();
         size_t pos = 0;
@@ -198,13 +207,38 @@ struct ExtractCtx {
             pos = (pos + 15) & ~size_t(15);
         }
         const size_t total = pos;
-        parallel_for(i1 - i0, threads, [&](int64_t lo, int64_t hi) {
-            for (int64_t k = lo; k < hi; ++k) {
+        if (src.fb) {
+            const FileBytes &fb = *src.fb;
+            parallel_for(i1 - i0, threads, [&](int64_t lo, int64_t hi) {
+                for (int64_t k = lo; k < hi; ++k) {
+                    const FastaRecord &r = recs[size_t(i0 + k)];
+                    if (force_walk || !r.regular) walk_record(fb, r, dst + at[size_t(k)]);
+                    else memcpy(dst + at[size_t(k)], fb.data + r.seq_off, r.raw_len);
+                }
+            });
+        } else {
+            // predicted framing: the record regions are read straight into the pinned buffer, in
+            // pieces of <= 2 MB so that every host thread has work whatever the record size
+            struct Piece { int32_t file; size_t src, len, dst; };
+            std::vector<Piece> pieces;
+            constexpr size_t kPiece = size_t(2) << 20;
+            for (int64_t k = 0; k < i1 - i0; ++k) {
                 const FastaRecord &r = recs[size_t(i0 + k)];
-                if (force_walk || !r.regular) walk_record(fb, r, dst + at[size_t(k)]);
-                else memcpy(dst + at[size_t(k)], fb.data + r.seq_off, r.raw_len);
+                for (size_t o = 0; o < r.raw_len; o += kPiece)
+                    pieces.push_back({r.file, r.seq_off + o, std::min(kPiece, r.raw_len - o), at[size_t(k)] + o});
             }
-        });
+            std::atomic<int> bad{BTB_OK};
+            std::string bad_text;
+            std::mutex bad_mutex;
+            parallel_for(int64_t(pieces.size()), threads, [&](int64_t lo, int64_t hi) {
+                for (int64_t k = lo; k < hi; ++k) {
+                    const Piece &pc = pieces[size_t(k)];
+                    const int rc = read_exact((*src.files)[size_t(pc.file)], pc.src, pc.len, dst + pc.dst);
+                    if (rc != BTB_OK) { std::lock_guard<std::mutex> lock(bad_mutex); bad = rc; bad_text = last_error(); }
+                }
+            });
+            if (bad != BTB_OK) return fail(bad, "%s", bad_text.c_str());
+        }
         const int64_t l0 = i0 - s0, cnt = i1 - i0;
         BTB_CUDA(cudaMemcpyAsync(d_text[b].p, dst, total + 16, cudaMemcpyHostToDevice, st.s));
         BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + l0, h_off.data() + l0, size_t(cnt) * 8, cudaMemcpyHostToDevice, st.s));
@@ -218,8 +252,9 @@ struct ExtractCtx {
     }
 
     // packs every sample of this device; *bad gets the global index of a record whose exact length
-    // turned out different from G (reported by the caller in file order)
-    int pack_all(const FileBytes &fb, std::vector<FastaRecord> &recs, int64_t G, int64_t *bad) {
+    // turned out different from G (reported by the caller in file order).  With predicted framing any
+    // flagged record means the prediction was wrong somewhere: kRetryExact.
+    int pack_all(const ByteSource &src, std::vector<FastaRecord> &recs, int64_t G, int64_t *bad) {
         int b = 0;
         for (int64_t i0 = s0; i0 < s1;) {
             size_t bytes = 0;
@@ -231,7 +266,7 @@ struct ExtractCtx {
                 bytes += need;
                 ++i1;
             }
-            BTB_TRY(run_chunk(fb, recs, G, b, i0, i1, false));
+            BTB_TRY(run_chunk(src, recs, G, b, i0, i1, false));
             b ^= 1;
             i0 = i1;
         }
@@ -241,11 +276,12 @@ struct ExtractCtx {
         BTB_CUDA(cudaStreamSynchronize(st.s));
         for (int64_t i = s0; i < s1; ++i) {
             if (!h_flags[size_t(i - s0)]) continue;
+            if (!src.fb) return kRetryExact;
             FastaRecord &r = recs[size_t(i)];
-            r.seq_len = walk_record(fb, r, nullptr);
+            r.seq_len = walk_record(*src.fb, r, nullptr);
             r.regular = false;
             if (r.seq_len != G) { *bad = i; return BTB_OK; }
-            BTB_TRY(run_chunk(fb, recs, G, b, i, i + 1, true));
+            BTB_TRY(run_chunk(src, recs, G, b, i, i + 1, true));
             b ^= 1;
         }
         BTB_CUDA(cudaStreamSynchronize(st.s));
@@ -256,28 +292,21 @@ struct ExtractCtx {
 }  // namespace
 
 // =============================================================================== level 1
-extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode, int n_gpus,
-                             int host_threads, int64_t *n_samples, int64_t *genome_len, int64_t *n_snps) {
-    if (!in_fasta || !out_fasta) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
-    if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
-    const int threads = std::max(1, host_threads);
-    StageTimer timer("btb_snp_sites");
-    BTB_TRY(require_device(0));
-    timer.mark("device init");
-    FileBytes fb;
-    BTB_TRY(load_file(in_fasta, fb));
-    std::vector<FastaRecord> recs;
-    BTB_TRY(index_fasta(fb, recs, threads));
-    timer.mark("map + index records");
+namespace {
+
+int g_ingest_predict = 1;      // "ingest_predict": try the predicted framing first (see host_io.h)
+int g_ingest_last = -1;        // "ingest_last_predicted": 1 if the last btb_snp_sites call completed on the predicted framing
+
+int no_snps() {
+    fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
+    return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
+}
+
+// Framed records -> snps.fas.  Shared by the exact and the predicted framing.
+int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, const char *in_fasta, const char *out_fasta,
+                     int pure_mode, int n_gpus, int threads, StageTimer &timer, int64_t *n_samples,
+                     int64_t *genome_len, int64_t *n_snps) {
     const int64_t n = int64_t(recs.size());
-    if (n == 0) {
-        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
-        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
-    }
-    // Records the GPU cannot address with (line width, terminator length) go through the exact walk.
-    auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 32); };
-    for (auto &r : recs)
-        if (needs_walk(r)) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
     const int64_t G = recs[0].seq_len;
     auto unequal = [&](const FastaRecord &r) {
         fprintf(stderr, "Alignment %s contains sequences of unequal length. Expected length is %i but got %i in sequence %s\n\n",
@@ -289,10 +318,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
         if (r.seq_len != G) return unequal(r);
     if (n_samples) *n_samples = n;
     if (genome_len) *genome_len = G;
-    if (G == 0) {
-        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
-        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
-    }
+    if (G == 0) return no_snps();
 
     // ---- devices: samples are dealt to the GPUs as contiguous record ranges of equal bytes ---------
     int usable = 0;
@@ -337,7 +363,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
         BTB_TRY(require_device(c.dev));
         BTB_TRY(c.setup(recs, G, words));
         int64_t bad = -1;
-        BTB_TRY(c.pack_all(fb, recs, G, &bad));
+        BTB_TRY(c.pack_all(src, recs, G, &bad));
         if (bad >= 0) { std::lock_guard<std::mutex> lock(bad_mutex); if (bad_record < 0 || bad < bad_record) bad_record = int(bad); return BTB_OK; }
         BTB_TRY(btb_column_mask(c.planes.as<uint32_t>(), c.nloc, c.nloc, G, c.state.as<uint32_t>(), 0, c.st.s));
         BTB_CUDA(cudaMemcpyAsync(h_state[size_t(c.dev)].data(), c.state.p, size_t(5 * words * 4), cudaMemcpyDeviceToHost, c.st.s));
@@ -367,10 +393,7 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     L = ctx[0].L;
     timer.mark("exchange + k3 select");
     if (n_snps) *n_snps = L;
-    if (L == 0) {
-        fprintf(stderr, "Warning: No SNPs were detected so there is nothing to output.\n");
-        return fail(BTB_ENOSNPS, "Warning: No SNPs were detected so there is nothing to output.");
-    }
+    if (L == 0) return no_snps();
 
     // phase 3: gather the kept columns of every sample into one pinned host matrix
     const int64_t ld = (L + 15) / 16 * 16;
@@ -406,3 +429,70 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     if (rc != BTB_OK) remove(tmp_path.c_str());
     return rc;
 }
+
+}  // namespace
+
+extern "C" int btb_snp_sites_files(const char *const *in_fastas, int64_t n_files, const char *alignment_name,
+                                   const char *out_fasta, int pure_mode, int n_gpus, int host_threads,
+                                   int64_t *n_samples, int64_t *genome_len, int64_t *n_snps) {
+    if (!in_fastas || n_files <= 0 || !out_fasta) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
+    for (int64_t i = 0; i < n_files; ++i)
+        if (!in_fastas[i]) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
+    if (!pure_mode) return fail(BTB_EINVAL, "only snp-sites -c (pure mode) is implemented on the GPU");
+    const char *shown = alignment_name ? alignment_name : in_fastas[0];
+    const int threads = std::max(1, host_threads);
+    StageTimer timer("btb_snp_sites");
+    BTB_TRY(require_device(0));
+    timer.mark("device init");
+    std::vector<FastaRecord> recs;
+    if (g_ingest_predict) {
+        std::vector<SourceFile> files;
+        BTB_TRY(open_sources(in_fastas, n_files, files));
+        bool fast = false;
+        BTB_TRY(frame_predicted(files, recs, &fast));
+        timer.mark("open + predicted framing");
+        if (fast) {
+            ByteSource src;
+            src.files = &files;
+            const int rc = extract_pipeline(src, recs, shown, out_fasta, pure_mode, n_gpus, threads, timer, n_samples, genome_len, n_snps);
+            if (rc != kRetryExact) { g_ingest_last = 1; return rc; }
+            timer.mark("predicted framing rejected by the device checks");
+        }
+    }
+    // exact framing: every byte is scanned for record markers (several files: as if concatenated)
+    g_ingest_last = 0;
+    FileBytes fb;
+    if (n_files == 1) {
+        BTB_TRY(load_file(in_fastas[0], fb));
+    } else {
+        for (int64_t i = 0; i < n_files; ++i) {
+            FileBytes one;
+            BTB_TRY(load_file(in_fastas[i], one));
+            fb.owned.insert(fb.owned.end(), one.data, one.data + one.size);
+        }
+        fb.data = fb.owned.data();
+        fb.size = fb.owned.size();
+    }
+    BTB_TRY(index_fasta(fb, recs, threads));
+    timer.mark("map + index records");
+    if (recs.empty()) return no_snps();
+    // Records the GPU cannot address with (line width, terminator length) go through the exact walk.
+    auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 32); };
+    for (auto &r : recs)
+        if (needs_walk(r)) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
+    ByteSource src;
+    src.fb = &fb;
+    return extract_pipeline(src, recs, shown, out_fasta, pure_mode, n_gpus, threads, timer, n_samples, genome_len, n_snps);
+}
+
+extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode, int n_gpus,
+                             int host_threads, int64_t *n_samples, int64_t *genome_len, int64_t *n_snps) {
+    if (!in_fasta || !out_fasta) return fail(BTB_EINVAL, "btb_snp_sites: NULL path");
+    return btb_snp_sites_files(&in_fasta, 1, in_fasta, out_fasta, pure_mode, n_gpus, host_threads, n_samples, genome_len, n_snps);
+}
+
+namespace btb {
+void set_ingest_predict(int v) { g_ingest_predict = v ? 1 : 0; }
+int get_ingest_predict() { return g_ingest_predict; }
+int get_ingest_last() { return g_ingest_last; }
+}  // namespace btb

@@ -18,7 +18,7 @@ import re
 
 from . import _capi
 
-__all__ = ["snp_sites", "build_snp_matrix", "post_process_snps_csv", "post_process_snps_df",
+__all__ = ["snp_sites", "build_snp_matrix", "build_multi_fasta", "post_process_snps_csv", "post_process_snps_df",
            "process_sample_name", "extract_submission_no", "PhylogenyError"]
 
 
@@ -55,14 +55,26 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=1):
     Writes `snp_sites_outpath` (one unwrapped record per sample) and returns
     {"number_of_snps": L}.  `threads` (host staging threads) is optional; the reference
     signature has two positional arguments and those keep working.
+
+    `multi_fasta_path` may also be a list / tuple of per-sample consensus FASTA paths: they are
+    taken as if concatenated in that order -- the file build_multi_fasta (phylogeny.py:48-88) would
+    have written -- without writing or re-reading it.
     """
     n = ctypes.c_int64(0)
     g = ctypes.c_int64(0)
     l = ctypes.c_int64(0)
-    rc = _capi.lib().btb_snp_sites(os.fsencode(multi_fasta_path), os.fsencode(snp_sites_outpath), 1,
-                                   _gpus(), int(threads), ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
+    if isinstance(multi_fasta_path, (list, tuple)):
+        paths = [os.fsencode(x) for x in multi_fasta_path]
+        shown = "<%d consensus files>" % len(paths)
+        arr = (ctypes.c_char_p * max(1, len(paths)))(*paths)
+        rc = _capi.lib().btb_snp_sites_files(arr, len(paths), shown.encode(), os.fsencode(snp_sites_outpath), 1,
+                                             _gpus(), int(threads), ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
+    else:
+        shown = multi_fasta_path
+        rc = _capi.lib().btb_snp_sites(os.fsencode(multi_fasta_path), os.fsencode(snp_sites_outpath), 1,
+                                       _gpus(), int(threads), ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
     if rc != _capi.OK:
-        _raise_like_run("snp-sites %s -c -o %s" % (multi_fasta_path, snp_sites_outpath), _capi.last_error())
+        _raise_like_run("snp-sites %s -c -o %s" % (shown, snp_sites_outpath), _capi.last_error())
     # read the number of snps for metadata exactly as the reference does (phylogeny.py:136-140)
     with open(snp_sites_outpath, "r") as f:
         next(f)
@@ -70,6 +82,21 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=1):
             metadata = {"number_of_snps": len(line) - 1}
             break
     return metadata
+
+
+def build_multi_fasta(multi_fasta_path, consensus_paths):
+    """The local half of the reference's build_multi_fasta (phylogeny.py:48-88): append the consensus
+    files, in order, to `multi_fasta_path` (the S3 download half, phylogeny.py:26-45, is the control
+    plane and out of scope).  Only needed when the multi-FASTA itself is wanted (light_mode=False,
+    btb_phylo.py:402-403); snp_sites() takes the list of consensus files directly."""
+    with open(multi_fasta_path, "wb") as out:
+        for path in consensus_paths:
+            with open(path, "rb") as f:
+                while True:
+                    block = f.read(1 << 24)
+                    if not block:
+                        break
+                    out.write(block)
 
 
 def build_snp_matrix(snp_dists_outpath, snp_sites_outpath, threads=1, post_process=False):

@@ -79,6 +79,15 @@ int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pure_mode,
                   int n_gpus, int host_threads,
                   int64_t *n_samples, int64_t *genome_len, int64_t *n_snps);
 
+/* The same stage over SEVERAL input files taken as if concatenated in the given order -- what
+ * btbphylo/phylogeny.py:48-88 build_multi_fasta produces by appending every sample's consensus
+ * file to multi_fasta.fas before snp-sites reads it back: here the per-sample
+ * files are staged straight into the pinned upload buffers and the multi-FASTA never has to be
+ * written.  alignment_name (may be NULL) is the file name shown in the unequal-length message. */
+int btb_snp_sites_files(const char *const *in_fastas, int64_t n_files, const char *alignment_name,
+                        const char *out_fasta, int pure_mode, int n_gpus, int host_threads,
+                        int64_t *n_samples, int64_t *genome_len, int64_t *n_snps);
+
 /* snp-dists [-a] [-k] [-m] [-c] [-b] [-q] -j T <in_fasta> > <out_path>   (phylogeny.py:149).
  * sep is ',' for -c else '\t'; corner = 0 is -b; the three banner lines go to stderr unless
  * quiet.  The file holds the full square, byte-identical with snp-dists 0.8.2. */
@@ -126,8 +135,10 @@ int64_t btb_plane_words(int64_t G);
  * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 32).  Writes three
  * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
  * sample i at d_planes + ((p * n_total + first + i) * words); column c = 32 w + cl is bit
- * 8 (cl & 3) + (cl >> 2) of word w (the order a 4-byte SWAR classification produces).  d_flags[i] is OR-ed with 1 when a
- * line terminator is not where the layout says (the caller then re-stages that record unwrapped). */
+ * 8 (cl & 3) + (cl >> 2) of word w (the order a 4-byte SWAR classification produces).  d_flags[i] is
+ * OR-ed with 1 when a line terminator is not where the layout says or a control byte sits among the
+ * bases (the caller then re-stages that record unwrapped), and with 2 when a line of the region starts
+ * with '>', '@' or '+' (the region is then not one record: the caller must frame the file again). */
 int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
                     const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
                     int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream);

@@ -185,3 +185,137 @@ def test_multi_gpu_snp_sites_same_bytes(capi, oracle, tmp_path):
     o_sf = tmp_path / "o.fas"
     assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
     assert outs[0] == outs[1] == o_sf.read_bytes()
+
+
+def _last_predicted(capi):
+    v = ctypes.c_int64(-2)
+    capi.check(capi.lib().btb_query(b"ingest_last_predicted", ctypes.byref(v)))
+    return v.value
+
+
+def test_predicted_framing_is_used_and_equals_exact(ph, capi, oracle, tmp_path):
+    """Equal-layout records take the predicted framing (no byte scan for markers); switching it off
+    gives the same bytes; so do the oracle tools."""
+    n, G = 90, 30017
+    names = synth.sample_names(n)
+    aln = synth.genome_alignment(n, G, 1200, seed=41, n_frac=0.02, lower=0.01)
+    o_sf = tmp_path / "o.fas"
+    for wrap, eol, tail in ((60, b"\n", True), (70, b"\r\n", True), (0, b"\n", True), (60, b"\n", False)):
+        mf = tmp_path / "multi_fasta.fas"
+        data = synth.fasta_bytes(names, aln, wrap=wrap, eol=eol, comments=["x=%d" % G, "", "a b c"])
+        mf.write_bytes(data if tail else data[: -len(eol)])
+        assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
+        out = {}
+        for predict in (1, 0):
+            capi.check(capi.lib().btb_set_option(b"ingest_predict", predict))
+            sf = tmp_path / ("snps%d.fas" % predict)
+            try:
+                ph.snp_sites(str(sf), str(mf), threads=3)
+            finally:
+                capi.check(capi.lib().btb_set_option(b"ingest_predict", 1))
+            assert _last_predicted(capi) == predict, (wrap, eol, tail)
+            out[predict] = sf.read_bytes()
+        assert out[1] == out[0] == o_sf.read_bytes(), (wrap, eol, tail)
+
+
+def test_predicted_framing_traps_fall_back_to_the_exact_path(ph, capi, oracle, tmp_path):
+    """Inputs that pass the host's boundary checks but are not what the prediction assumes: the pack
+    kernel's flags catch them and the call is redone with exact framing."""
+    rng = np.random.default_rng(3)
+    G, W, n = 6000, 60, 12
+    base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), G)
+    rows = []
+    for i in range(n):
+        r = base.copy()
+        r[rng.integers(0, G, 40)] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 40)
+        rows.append(r.tobytes())
+
+    def record(i, lines):
+        return b">s%d\n" % i + b"".join(l + b"\n" for l in lines)
+
+    def even(seq):
+        return [seq[k:k + W] for k in range(0, G, W)]
+
+    # (a) one record has a 61-base line followed by a 59-base line: same byte count, terminators shifted
+    recs = [record(i, even(rows[i])) for i in range(n)]
+    lines = even(rows[5])
+    moved = lines[:10] + [lines[10] + lines[11][:1], lines[11][1:]] + lines[12:]
+    recs[5] = record(5, moved)
+    assert len(recs[5]) == len(recs[4])
+    mf, sf, o_sf = tmp_path / "a.fa", tmp_path / "a.fas", tmp_path / "o.fas"
+    mf.write_bytes(b"".join(recs))
+    assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
+    ph.snp_sites(str(sf), str(mf))
+    assert _last_predicted(capi) == 0 and sf.read_bytes() == o_sf.read_bytes()
+
+    # (b) a line inside a record starts with '>': for the parser that is a new (short) record -> unequal lengths
+    recs = [record(i, even(rows[i])) for i in range(n)]
+    lines = even(rows[7])
+    lines[20] = b">" + lines[20][1:]
+    recs[7] = record(7, lines)
+    mf.write_bytes(b"".join(recs))
+    r = oracle.run_snp_sites(str(mf), str(o_sf))
+    assert r.returncode != 0 and b"unequal length" in (r.stderr if isinstance(r.stderr, bytes) else r.stderr.encode())
+    with pytest.raises(Exception) as e:
+        ph.snp_sites(str(sf), str(mf))
+    assert _last_predicted(capi) == 0 and "unequal length" in str(e.value)
+    # ... unless the pieces happen to be records of the right length themselves
+    half = [record(i, even(rows[i])) for i in range(4)]
+    tricky = b">t\n" + b"".join(l + b"\n" for l in even(rows[4])[: G // W - 1])       # one line short ...
+    tricky = tricky + b">" + b"u" * (W - 1) + b"\n"                                     # ... made up by a header-looking line
+    assert len(tricky) == len(half[0]) + (len(b">t\n") - len(b">s0\n"))
+    mf.write_bytes(b"".join(half) + tricky)
+    r = oracle.run_snp_sites(str(mf), str(o_sf))
+    with pytest.raises(Exception) as e:
+        ph.snp_sites(str(sf), str(mf))
+    assert r.returncode != 0 and _last_predicted(capi) == 0
+
+    # (c) a control byte among the bases (a tab) keeps the prediction off but is plain data for the parser
+    recs = [record(i, even(rows[i])) for i in range(n)]
+    lines = even(rows[2])
+    lines[3] = lines[3][:7] + b"\t" + lines[3][8:]
+    recs[2] = record(2, lines)
+    mf.write_bytes(b"".join(recs))
+    assert oracle.run_snp_sites(str(mf), str(o_sf)).returncode == 0
+    ph.snp_sites(str(sf), str(mf))
+    assert _last_predicted(capi) == 0 and sf.read_bytes() == o_sf.read_bytes()
+
+
+def test_consensus_file_lists_equal_the_concatenated_multi_fasta(ph, capi, oracle, tmp_path):
+    """snp_sites() over per-sample consensus files == build_multi_fasta + snp_sites."""
+    text = golden("c1_multi_fasta.fas")
+    parts = [b">" + p for p in text.split(b">") if p]
+    paths = []
+    for i, p in enumerate(parts):
+        f = tmp_path / ("s%d.fas" % i)
+        f.write_bytes(p)
+        paths.append(str(f))
+    sf = tmp_path / "snps.fas"
+    assert ph.snp_sites(str(sf), paths) == json.loads(golden("c1_meta.json"))
+    assert sf.read_bytes() == golden("c1_snps.fas") and _last_predicted(capi) == 1
+    # the reference's way: concatenate, then run
+    mf = tmp_path / "multi_fasta.fas"
+    ph.build_multi_fasta(str(mf), paths)
+    assert mf.read_bytes() == text
+    # gzip members and an empty file in the list; a file without its final newline in the middle
+    gz = tmp_path / "s1.fas.gz"
+    gz.write_bytes(gzip.compress(parts[1]))
+    empty = tmp_path / "empty.fas"
+    empty.write_bytes(b"")
+    assert ph.snp_sites(str(sf), [paths[0], str(gz), str(empty)] + paths[2:]) == json.loads(golden("c1_meta.json"))
+    assert sf.read_bytes() == golden("c1_snps.fas") and _last_predicted(capi) == 0
+    cut = tmp_path / "cut.fas"
+    cut.write_bytes(parts[1][:-1])
+    odd = [paths[0], str(cut)] + paths[2:]
+    ph.build_multi_fasta(str(mf), odd)
+    o_sf = tmp_path / "o.fas"
+    r = oracle.run_snp_sites(str(mf), str(o_sf))
+    if r.returncode == 0:
+        ph.snp_sites(str(sf), odd)
+        assert sf.read_bytes() == o_sf.read_bytes()
+    else:
+        with pytest.raises(Exception):
+            ph.snp_sites(str(sf), odd)
+    with pytest.raises(Exception) as e:
+        ph.snp_sites(str(sf), [paths[0], str(tmp_path / "missing.fas")])
+    assert "Could not open filename" in str(e.value)
