@@ -40,6 +40,9 @@ extern int g_umma_cta_group;
 extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
 extern int g_umma_dbg_negate;
+extern int g_umma_dbg_max_ctas;
+extern int g_umma_tile_bk;
+extern int g_umma_dbg_stages;
 extern int g_umma_prefetch;
 void set_ingest_predict(int v);
 int get_ingest_predict();
@@ -47,6 +50,14 @@ int get_ingest_last();
 extern int g_umma_tile_mode;
 extern int g_pack_wpt;
 int umma_max_active_clusters(int cg, int *out);
+int dist_presence_async(const uint8_t *, int64_t, int64_t, int64_t, uint32_t *, cudaStream_t);
+int dist_encode_fp4_dense_rows(const uint8_t *, int64_t, int64_t, int64_t, const uint8_t *, int64_t, uint8_t *, int32_t *,
+                               cudaStream_t);
+int g_host_stream_last = -1;    // "host_stream_last": 1 if the last level-2 call completed on the streamed path
+int g_host_stream_rows = 64;    // "host_stream_rows": block rows per streamed band (narrow strips copy slowly)
+int g_host_stream = 0;         // "host_stream": level 2 uploads, computes and downloads band by band (see streamed_matrix).
+                               // Off by default: measured 0.126-0.136 s against 0.131-0.140 s per C4 call -- the call is bound
+                               // by the 5 GB download either way, and an upload running beside it slows the download down.
 
 int require_device(int device) {
     int count = 0;
@@ -113,8 +124,13 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
+    if (key && !strcmp(key, "host_stream")) { g_host_stream = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "host_stream_rows")) { g_host_stream_rows = value < 8 ? 8 : value; return BTB_OK; }
     if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_tile_bk")) { g_umma_tile_bk = value == 64 ? 64 : 128; return BTB_OK; }
+    if (key && !strcmp(key, "umma_dbg_max_ctas")) { g_umma_dbg_max_ctas = value; return BTB_OK; }
+    if (key && !strcmp(key, "umma_dbg_stages")) { g_umma_dbg_stages = value; return BTB_OK; }
     if (key && !strcmp(key, "umma_dbg_negate")) { g_umma_dbg_negate = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value < 0 ? 0 : value; return BTB_OK; }
@@ -132,7 +148,10 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
     if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
     if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
+    if (!strcmp(key, "umma_tile_bk")) { *value = g_umma_tile_bk; return BTB_OK; }
     if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }
+    if (!strcmp(key, "host_stream")) { *value = g_host_stream; return BTB_OK; }
+    if (!strcmp(key, "host_stream_last")) { *value = g_host_stream_last; return BTB_OK; }
     if (!strcmp(key, "ingest_last_predicted")) { *value = get_ingest_last(); return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
 }
@@ -204,10 +223,13 @@ namespace {
 // Device buffers of btb_dist_matrix_host are kept between calls (one set per device): a weekly
 // production run calls once, a benchmark loop many times; cudaMalloc of ~20 GB is not free.
 struct Workspace {
-    void *p[3] = {nullptr, nullptr, nullptr};
-    size_t cap[3] = {0, 0, 0};
-    cudaStream_t st = nullptr, st2 = nullptr;
+    void *p[4] = {nullptr, nullptr, nullptr, nullptr};      // sequences, operands, matrix, small scratch
+    size_t cap[4] = {0, 0, 0, 0};
+    cudaStream_t st = nullptr, st2 = nullptr, st_in = nullptr;
     cudaEvent_t ev = nullptr;
+    std::vector<cudaEvent_t> band_ev;     // streamed path: chunk uploaded + scanned
+    uint32_t *h_present = nullptr;        // pinned: one 256-bit byte-presence map per band
+    size_t h_present_bands = 0;
     int ensure(int k, size_t bytes, void **out) {
         bytes = std::max<size_t>(bytes, 16);
         if (cap[k] < bytes) {
@@ -220,11 +242,16 @@ struct Workspace {
         return BTB_OK;
     }
     void release() {
-        for (int k = 0; k < 3; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+        for (int k = 0; k < 4; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
         if (st) cudaStreamDestroy(st);
         if (st2) cudaStreamDestroy(st2);
+        if (st_in) cudaStreamDestroy(st_in);
         if (ev) cudaEventDestroy(ev);
-        st = st2 = nullptr;
+        for (auto e : band_ev) cudaEventDestroy(e);
+        band_ev.clear();
+        if (h_present) cudaFreeHost(h_present);
+        h_present = nullptr; h_present_bands = 0;
+        st = st2 = st_in = nullptr;
         ev = nullptr;
     }
 };
@@ -242,6 +269,97 @@ extern "C" int btb_release_workspace(void) {
     return BTB_OK;
 }
 
+namespace {
+// Level 2, one GPU, default mode, dense input (every snp-sites -c output): upload, GEMM and download
+// overlap.  The bands of block rows are computed LAST TO FIRST: the last band only needs the last
+// samples, every earlier band needs its own samples plus the ones already on the device, so the
+// samples are uploaded from the end of the alignment backwards while the tensor cores already run.
+// After band b the square of all rows and columns >= its first row is final (mirrored writes), and
+// the two newly finished strips are copied to the host while earlier bands are still computed.
+// The input is assumed dense (ACGTacgt only) -- what the per-band byte-presence maps check; the
+// first band that is not sends the whole call down the general path (*done = false).
+int streamed_matrix(Workspace &ws, const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride, void *out,
+                    int out_elem_bytes, int64_t out_ld, bool *done) {
+    *done = false;
+    const int sigma = BTB_SIGMA_DENSE4;
+    const int64_t T = tiles_per_dim(n);
+    const int64_t SB = std::max<int64_t>(kBand, int64_t(g_host_stream_rows) / kBand * kBand);   // block rows per streamed band
+    const int64_t bands = (T + SB - 1) / SB;
+    const int64_t d_stride = (len + 15) / 16 * 16, d_ld = (n + 7) / 8 * 8;
+    const int64_t kb = btb_dist_operand_bytes(BTB_ENGINE_UMMA, 1, len, sigma) - 4;      // operand bytes per row
+    const size_t eb = size_t(out_elem_bytes);
+    uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr, *d_small = nullptr;
+    BTB_TRY(ws.ensure(0, size_t(n * d_stride), reinterpret_cast<void **>(&d_seqs)));
+    BTB_TRY(ws.ensure(1, size_t(btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma)), reinterpret_cast<void **>(&d_ops)));
+    BTB_TRY(ws.ensure(2, size_t(n * d_ld) * eb, reinterpret_cast<void **>(&d_out)));
+    BTB_TRY(ws.ensure(3, size_t(256 + bands * 32), reinterpret_cast<void **>(&d_small)));
+    if (!ws.st2) BTB_CUDA(cudaStreamCreateWithFlags(&ws.st2, cudaStreamNonBlocking));
+    if (!ws.st_in) BTB_CUDA(cudaStreamCreateWithFlags(&ws.st_in, cudaStreamNonBlocking));
+    if (!ws.ev) BTB_CUDA(cudaEventCreateWithFlags(&ws.ev, cudaEventDisableTiming));
+    while (int64_t(ws.band_ev.size()) < bands) {
+        cudaEvent_t e;
+        BTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ws.band_ev.push_back(e);
+    }
+    if (ws.h_present_bands < size_t(bands)) {
+        if (ws.h_present) cudaFreeHost(ws.h_present);
+        ws.h_present = nullptr;
+        BTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ws.h_present), size_t(bands) * 32));
+        ws.h_present_bands = size_t(bands);
+    }
+    uint8_t table[256];
+    int s4 = 0;
+    BTB_TRY(btb_dist_alphabet(nullptr, n, len, d_stride, 0, 0, table, &s4, ws.st));        // default-mode table, no scan
+    uint8_t *d_table = d_small;
+    uint32_t *d_present = reinterpret_cast<uint32_t *>(d_small + 256);
+    int32_t *rowsum = reinterpret_cast<int32_t *>(d_ops + n * kb);
+    BTB_CUDA(cudaMemcpyAsync(d_table, table, 256, cudaMemcpyHostToDevice, ws.st_in));
+    BTB_CUDA(cudaMemsetAsync(d_present, 0, size_t(bands) * 32, ws.st_in));
+    BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, ws.st_in));
+    // every upload is queued now, last band first; each is followed by its presence scan and encode
+    for (int64_t b = bands - 1; b >= 0; --b) {
+        const int64_t row0 = b * SB * BTB_TILE, row1 = std::min<int64_t>(n, row0 + SB * BTB_TILE);
+        BTB_CUDA(cudaMemcpy2DAsync(d_seqs + row0 * d_stride, size_t(d_stride), seqs + row0 * row_stride, size_t(row_stride),
+                                   size_t(len), size_t(row1 - row0), cudaMemcpyHostToDevice, ws.st_in));
+        BTB_TRY(dist_presence_async(d_seqs + row0 * d_stride, row1 - row0, len, d_stride, d_present + b * 8, ws.st_in));
+        BTB_CUDA(cudaMemcpyAsync(ws.h_present + b * 8, d_present + b * 8, 32, cudaMemcpyDeviceToHost, ws.st_in));
+        BTB_TRY(dist_encode_fp4_dense_rows(d_seqs + row0 * d_stride, row1 - row0, len, d_stride, d_table, kb,
+                                           d_ops + row0 * kb, rowsum + row0, ws.st_in));
+        BTB_CUDA(cudaEventRecord(ws.band_ev[size_t(b)], ws.st_in));
+    }
+    char *ho = static_cast<char *>(out);
+    auto copy2d = [&](int64_t r0, int64_t r1, int64_t c0, int64_t c1) -> cudaError_t {
+        if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+        return cudaMemcpy2DAsync(ho + (r0 * out_ld + c0) * eb, size_t(out_ld) * eb, d_out + (r0 * d_ld + c0) * eb,
+                                 size_t(d_ld) * eb, size_t(c1 - c0) * eb, size_t(r1 - r0), cudaMemcpyDeviceToHost, ws.st2);
+    };
+    for (int64_t b = bands - 1; b >= 0; --b) {
+        const int64_t row0 = b * SB * BTB_TILE, row1 = std::min<int64_t>(n, row0 + SB * BTB_TILE);
+        BTB_CUDA(cudaEventSynchronize(ws.band_ev[size_t(b)]));
+        bool dense = true;                         // only bytes the default-mode table maps to a base
+        for (int v = 0; v < 256 && dense; ++v)
+            if ((ws.h_present[b * 8 + (v >> 5)] >> (v & 31) & 1u) && table[v] == 0xff) dense = false;
+        if (!dense) {
+            BTB_CUDA(cudaStreamSynchronize(ws.st_in));
+            BTB_CUDA(cudaStreamSynchronize(ws.st));
+            BTB_CUDA(cudaStreamSynchronize(ws.st2));
+            return BTB_OK;
+        }
+        BTB_CUDA(cudaStreamWaitEvent(ws.st, ws.band_ev[size_t(b)], 0));
+        BTB_TRY(btb_distance_rows(BTB_ENGINE_UMMA, d_ops, n, len, sigma, b * SB, std::min<int64_t>(T, (b + 1) * SB),
+                                  d_out, out_elem_bytes, d_ld, 1, ws.st));
+        BTB_CUDA(cudaEventRecord(ws.ev, ws.st));
+        BTB_CUDA(cudaStreamWaitEvent(ws.st2, ws.ev, 0));
+        BTB_CUDA(copy2d(row0, row1, row0, n));     // the band's rows from the diagonal on
+        BTB_CUDA(copy2d(row1, n, row0, row1));     // their mirror images below
+    }
+    BTB_CUDA(cudaStreamSynchronize(ws.st2));
+    BTB_CUDA(cudaStreamSynchronize(ws.st));
+    *done = true;
+    return BTB_OK;
+}
+}  // namespace
+
 extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
                                     int allchars, int keepcase, int engine, int device, int rank, int world,
                                     void *out, int out_elem_bytes, int64_t out_ld) {
@@ -256,6 +374,18 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
     if (!ws.st) BTB_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
     cudaStream_t st = ws.st;
     int rc = BTB_OK;
+    g_host_stream_last = 0;
+    if (world == 1 && g_host_stream && !allchars && !keepcase && engine != BTB_ENGINE_POPC && len > 0 &&
+        umma_fp4_dense(BTB_SIGMA_DENSE4, len) && tiles_per_dim(n) >= 2 * kBand) {
+        size_t free_b = 0, total_b = 0;
+        const size_t need = size_t(btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, BTB_SIGMA_DENSE4)) + size_t(n) * size_t((len + 15) / 16 * 16) +
+                            size_t(n) * size_t((n + 7) / 8 * 8) * size_t(out_elem_bytes);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need < free_b + ws.cap[0] + ws.cap[1] + ws.cap[2]) {
+            bool done = false;
+            BTB_TRY(streamed_matrix(ws, seqs, n, len, row_stride, out, out_elem_bytes, out_ld, &done));
+            if (done) { g_host_stream_last = 1; return BTB_OK; }
+        }
+    }
     uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
     const int64_t d_stride = (len + 15) / 16 * 16;
     const int64_t d_ld = (n + 7) / 8 * 8;

@@ -28,27 +28,31 @@ namespace btb {
 // ------------------------------------------------------------------ alphabet scan (-a mode)
 __global__ void presence_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len,
                                 int64_t row_stride, uint32_t *__restrict__ present /*[8]*/) {
-    __shared__ uint32_t s_present[8];
-    if (threadIdx.x < 8) s_present[threadIdx.x] = 0;
+    // one flag byte per byte value in shared memory: marking a value is a single (racy but idempotent)
+    // store, so the scan runs at load speed; 16-byte loads when the rows allow it
+    __shared__ uint8_t seen[256];
+    seen[threadIdx.x] = 0;                                  // blockDim.x == 256
     __syncthreads();
-    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool vec = (reinterpret_cast<uintptr_t>(seqs) % 16 == 0) && (row_stride % 16 == 0);
+    const int64_t chunks = vec ? len / 16 : 0;
     for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
         const uint8_t *p = seqs + row * row_stride;
-        for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < len;
+        for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < chunks;
              k += (int64_t)gridDim.x * blockDim.x) {
-            uint32_t b = p[k];
-            loc[b >> 5] |= 1u << (b & 31);
+            const uint4 v = *reinterpret_cast<const uint4 *>(p + 16 * k);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                seen[w[q] & 0xff] = 1; seen[(w[q] >> 8) & 0xff] = 1;
+                seen[(w[q] >> 16) & 0xff] = 1; seen[w[q] >> 24] = 1;
+            }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        uint32_t v = loc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_present[i], v);
+        for (int64_t k = chunks * 16 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < len;
+             k += (int64_t)gridDim.x * blockDim.x)
+            seen[p[k]] = 1;
     }
     __syncthreads();
-    if (threadIdx.x < 8 && s_present[threadIdx.x]) atomicOr(&present[threadIdx.x], s_present[threadIdx.x]);
+    if (seen[threadIdx.x]) atomicOr(&present[threadIdx.x >> 5], 1u << (threadIdx.x & 31));
 }
 
 // ------------------------------------------------------------------ POPC planes
@@ -352,6 +356,29 @@ encode_fp4_planes_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t le
             }
         }
     }
+}
+
+// ---- pieces of the C-ABI calls, for the streamed level-2 path (capi.cu) ------------------------
+// ORs the byte values that occur in rows [0, n) into the 256-bit map d_present8
+int dist_presence_async(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride, uint32_t *d_present8,
+                        cudaStream_t stream) {
+    if (n <= 0 || len <= 0) return BTB_OK;
+    dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 2048));
+    presence_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_present8);
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
+}
+
+// dense FP4 operand rows (tetrahedron nibbles) of `rows` sequences; rowsum_rows must be zero
+int dist_encode_fp4_dense_rows(const uint8_t *d_seqs, int64_t rows, int64_t len, int64_t row_stride,
+                               const uint8_t *d_table, int64_t kb, uint8_t *A_rows, int32_t *rowsum_rows,
+                               cudaStream_t stream) {
+    if (rows <= 0) return BTB_OK;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_seqs) % 4 == 0) && (row_stride % 4 == 0);
+    dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(rows, 65535));
+    encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, kb, A_rows, aligned ? 1 : 0, rowsum_rows);
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
 }
 
 }  // namespace btb

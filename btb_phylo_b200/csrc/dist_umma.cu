@@ -183,6 +183,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// same for rows of 64 bytes, 64-byte swizzle: 8-row atoms of 512 B, layout type 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t(512 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(4) << 61;
+    return d;
+}
+
 // instruction descriptor, kind::i8: D = S32 (2 at [4,6)), A/B = signed 8-bit (1 at [7,10) / [10,13)),
 // both K-major (0 at 15 / 16), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
@@ -824,13 +834,22 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // mirrored where column > row, so any set of whole block rows covers exactly the same cells as the
 // square-tile enumeration.
 constexpr int kUnitColMask = 0xffff, kUnitPrefA = 1 << 16, kUnitPrefB = 1 << 17;   // work-list entry .y
-struct Fp4TileCfg {
+// BK = K bytes per pipeline stage: 128 (3 stages x 62 KB, 128-byte swizzle) or 64 (6 stages x 31 KB,
+// 64-byte swizzle).  The ring is refilled at the pace  (load latency + consume time) / stages  per
+// stage; measured on C4 the load latency of a 62 KB stage is ~2,550 clk against 960 clk of MMA work,
+// so three stages starve the tensor pipe (80 % active; two stages: 56 %) while the same 186 KB cut
+// into six stages keep five of them in flight.
+template <int BK>
+struct Fp4TileCfgT {
     static constexpr int kBN = 240;
-    static constexpr int kABytes = 256 * kBlockK;                     // 32 KB
-    static constexpr int kBBytes = kBN * kBlockK;                     // 30 KB
-    static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB (multiple of 1024)
-    static constexpr int kStages = 3;
+    static constexpr int kBK = BK;
+    static constexpr int kABytes = 256 * BK;                          // 32 KB / 16 KB
+    static constexpr int kBBytes = kBN * BK;                          // 30 KB / 15 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB / 31 KB (multiples of 1024)
+    static constexpr int kStages = BK == 128 ? 3 : 6;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+struct Fp4TileCfg : Fp4TileCfgT<128> {
     static constexpr int kPrefetch = 0;                               // K blocks the optional L2 prefetch runs ahead (measured: no gain,
                                                                       // the kernel sits at the L2 -> SM throughput cap, not on DRAM latency)
 };
@@ -840,12 +859,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, 
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <typename OutT>
+template <typename OutT, int kStages = Fp4TileCfg::kStages, int BK = 128>
 __global__ void __launch_bounds__(kThreads, 1)
 dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const UmmaParams p) {
-    using Cfg = Fp4TileCfg;
-    constexpr int kStages = Cfg::kStages;
+    using Cfg = Fp4TileCfgT<BK>;
+    auto make_desc = [](uint32_t addr) { return BK == 128 ? make_kmajor_sw128_desc(addr) : make_kmajor_sw64_desc(addr); };
     constexpr uint32_t kHalf1Col = 256, kSfCol = 496;         // accumulators at 0..239 and 256..495, scale factors 496..511
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -893,8 +912,8 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const int2 wn = u + n_workers < p.units ? p.worklist[u + n_workers] : make_int2(0, 0);
                 if (u == worker)
                     for (int64_t kb = 0; kb < pf && kb < p.k_blocks; ++kb) {
-                        if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(kb * kBlockK), m0);
-                        if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int(kb * kBlockK), n0);
+                        if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(kb * BK), m0);
+                        if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int(kb * BK), n0);
                     }
                 if (p.lockstep && u != worker) {                 // see dist_umma_kernel
                     const int64_t round = (u - worker) / n_workers;
@@ -911,17 +930,17 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     if (pf) {
                         const int64_t ka = kb + pf;
                         if (ka < p.k_blocks) {
-                            if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(ka * kBlockK), m0);
-                            if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka + (ka >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
+                            if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(ka * BK), m0);
+                            if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka + (ka >= p.neg_from ? p.b_shift : 0)) * BK), n0);
                         } else if (ka - p.k_blocks < p.k_blocks) {
-                            if (wn.y & kUnitPrefA) tma_prefetch_2d(&map_a, int((ka - p.k_blocks) * kBlockK), wn.x * BTB_TILE);
-                            if (wn.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka - p.k_blocks) * kBlockK), (wn.y & kUnitColMask) * Cfg::kBN);
+                            if (wn.y & kUnitPrefA) tma_prefetch_2d(&map_a, int((ka - p.k_blocks) * BK), wn.x * BTB_TILE);
+                            if (wn.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka - p.k_blocks) * BK), (wn.y & kUnitColMask) * Cfg::kBN);
                         }
                     }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * kBlockK), m0);
-                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
+                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * BK), m0);
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * BK), n0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -940,20 +959,20 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 if (kb == 0) mbar_wait(tempty_bar(0), drained);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
-                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+                    const uint64_t a_desc = make_desc(smem_a(stage));
+                    const uint64_t b_desc = make_desc(smem_b(stage));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < BK / 32; ++k)
                         umma_mxf4(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
                                   tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 __syncwarp();
                 if (kb == 0) { mbar_wait(tempty_bar(1), drained); tc_fence_after(); }
                 if (elect_one()) {
-                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + 128 * kBlockK);
-                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+                    const uint64_t a_desc = make_desc(smem_a(stage) + 128 * BK);
+                    const uint64_t b_desc = make_desc(smem_b(stage));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < BK / 32; ++k)
                         umma_mxf4(tmem_base + kHalf1Col, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
                                   tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
                     umma_commit<1>(empty_bar(stage));
@@ -1007,15 +1026,15 @@ static int get_encode_fn(EncodeTiledFn *fn) {
 }
 
 // 2-D uint8 tensor [rows][kbytes], box = 128 K-bytes x box_rows rows, 128B swizzle, OOB rows read as 0
-static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int64_t kbytes, int box_rows) {
+static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int64_t kbytes, int box_rows, int box_k = kBlockK) {
     EncodeTiledFn enc;
     BTB_TRY(get_encode_fn(&enc));
     cuuint64_t dims[2] = {cuuint64_t(kbytes), cuuint64_t(rows)};
     cuuint64_t strides[1] = {cuuint64_t(kbytes)};
-    cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+    cuuint32_t box[2] = {cuuint32_t(box_k), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(BTB_ECUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
     return BTB_OK;
@@ -1025,6 +1044,9 @@ int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 te
 int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
 int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
 int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
+int g_umma_tile_bk = 128;      // "umma_tile_bk": K bytes per stage of the FP4 full-tile kernel (128: 3 stages; 64: 6 stages -- measured equal)
+int g_umma_dbg_max_ctas = 0;   // experiment: cap the grid of the FP4 full-tile kernel (0 = one CTA per SM)
+int g_umma_dbg_stages = 0;     // experiment: 2 = run the FP4 full-tile kernel with two pipeline stages
 int g_umma_dbg_negate = 0;     // experiment: negate every K block of the FP4 kernels (probes the descriptor bit)
 int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
 int g_umma_lockstep = 1;       // 0: off; k >= 1: producers of all CTAs start each unit at most k-1 rounds apart (L2 reuse), cooperative launch
@@ -1214,18 +1236,20 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
     BTB_TRY(get_rows_list(n, row_lo, row_hi, 1, &d_units, &n_units));
     if (n_units < 2 * int64_t(sms) || dev >= 16) return BTB_OK;
     CUtensorMap ma, mb;
-    BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
-    BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN));
+    const int bk = (g_umma_tile_bk == 64 && out_elem_bytes == 2 && g_umma_dbg_stages != 2) ? 64 : 128;
+    BTB_TRY(make_operand_map(&ma, A, n, kb, 256, bk));
+    BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN, bk));
     UmmaParams p;
-    p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
+    p.n = n; p.k_blocks = kb / bk; p.tile_lo = 0; p.units = n_units;
     p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
     p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
     p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;            // tetrahedron code (row sums) / V - X planes
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-    if (neg_from >= 0) p.neg_from = neg_from;
+    if (neg_from >= 0) p.neg_from = neg_from * (kBlockK / bk);
     if (g_umma_dbg_negate) p.neg_from = 0;
     p.prefetch = g_umma_prefetch;
-    const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+    unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+    if (g_umma_dbg_max_ctas > 0) ctas = std::min<unsigned>(ctas, unsigned(g_umma_dbg_max_ctas));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     cfg.gridDim = dim3(ctas);
@@ -1243,7 +1267,13 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    if (out_elem_bytes == 2) {
+    if (bk == 64) {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t, 6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfgT<64>::kSmemBytes));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t, 6, 64>, ma, mb, p));
+    } else if (out_elem_bytes == 2 && g_umma_dbg_stages == 2) {
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t, 2>, ma, mb, p));
+    } else if (out_elem_bytes == 2) {
         BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
         BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t>, ma, mb, p));
     } else {

@@ -249,6 +249,45 @@ def test_level2_host_call(capi, oracle):
     assert (out == want).all()
 
 
+def test_level2_streamed_path(capi, oracle):
+    """n >= 16 block rows, default mode, dense input: the level-2 call uploads / computes / downloads
+    band by band in reverse order; a non-dense band sends the call down the general path.  Same
+    matrix either way, and with the streaming switched off."""
+    from btb_phylo_b200 import device
+    lib = capi.lib()
+
+    def last():
+        v = ctypes.c_int64(-2)
+        capi.check(lib.btb_query(b"host_stream_last", ctypes.byref(v)))
+        return v.value
+
+    n, L = 4500, 333
+    dense = synth.snp_alignment(n, L, seed=17)
+    dense[::5, ::3] |= 0x20                                  # lower case is still dense in default mode
+    want = oracle.snp_dists_rows(dense, threads=8)
+    assert (device.distance_matrix_host(dense) == want).all() and last() == 0       # off by default
+    try:
+        capi.check(lib.btb_set_option(b"host_stream", 1))
+        for rows in (8, 16, 64):
+            capi.check(lib.btb_set_option(b"host_stream_rows", rows))
+            for dtype in (np.uint16, np.uint32):
+                out = np.full((n, n + 8), 0xFFFF, dtype=dtype)[:, :n]   # a padded host matrix (ld > n)
+                device.distance_matrix_host(dense, out=out)
+                bad = np.argwhere(out != want)
+                assert last() == 1 and len(bad) == 0, (rows, dtype, len(bad), bad[:3], bad[-3:], out[tuple(bad[0])], want[tuple(bad[0])])
+        capi.check(lib.btb_set_option(b"host_stream_rows", 8))
+        for bad_row in (n - 1, 2100, 0):                     # the first / a middle / the last band to be checked
+            mixed = dense.copy()
+            mixed[bad_row, 7] = ord("N")
+            got = device.distance_matrix_host(mixed)
+            assert last() == 0 and (got == oracle.snp_dists_rows(mixed, threads=8)).all(), bad_row
+        assert (device.distance_matrix_host(dense) == want).all() and last() == 1
+        assert (device.distance_matrix_host(dense, allchars=True) == oracle.snp_dists_rows(dense, allchars=True, threads=8)).all() and last() == 0
+    finally:
+        capi.check(lib.btb_set_option(b"host_stream", 0))
+        capi.check(lib.btb_set_option(b"host_stream_rows", 64))
+
+
 def test_properties_at_scale(capi, oracle):
     """8192 x 30000 (BASELINE config 4 shape, cut to 8192 rows): symmetry, zero diagonal, engines
     agree everywhere, sampled rows equal the oracle."""

@@ -42,7 +42,7 @@ plan = device.DistancePlan(d, length=L, engine=1)
 plan.encode()
 out = plan.alloc_matrix()
 ref = None
-for key, values in ((b"umma_prefetch", (0, 2, 4, 8, 16, 32, 64, 0, 8)),):
+for key, values in ((b"umma_tile_bk", (128, 64, 128, 64)),):
     for v in values:
         _capi.check(lib.btb_set_option(key, v))
         plan.compute(out); torch.cuda.synchronize()
