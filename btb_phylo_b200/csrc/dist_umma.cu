@@ -1216,7 +1216,17 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
     }
     DevList e{n, lo, hi, kind, nullptr, int64_t(h.size())};
     BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&e.d), std::max<size_t>(h.size(), 1) * sizeof(int2)));
-    if (!h.empty()) BTB_CUDA(cudaMemcpy(e.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    if (!h.empty()) {
+        // A plain cudaMemcpy from pageable memory may return while its DMA is still in flight on the
+        // legacy stream, which the non-blocking launch streams do not wait for: copy on a stream of
+        // our own and wait for it, so the list is complete for every later launch on any stream.
+        cudaStream_t cs;
+        BTB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaError_t ce = cudaMemcpyAsync(e.d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, cs);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+        if (ce != cudaSuccess) { cudaFree(e.d); return fail(BTB_ECUDA, "work list upload failed: %s", cudaGetErrorString(ce)); }
+    }
     g_lists[dev].push_back(e);
     *d_out = e.d;
     *count = e.count;
