@@ -287,7 +287,9 @@ def gpu_arm(args):
     dense_code = _query(lib, b"umma_dense_simplex")
     planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
     nominal = 9000.0 if fp4 else 4500.0
-    roofline = {"bound": "tensor", "kernel": "dist_umma_fp4_tile_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)" if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
+    pair = bool(_query(lib, b"umma_fp4_pair")) and fp4
+    roofline = {"bound": "tensor", "kernel": ("dist_umma_fp4_pair_kernel (tcgen05.mma cta_group::2 kind::mxf4, exact 0/1 products)" if pair else
+                                              "dist_umma_fp4_tile_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)") if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
                 "achieved": achieved, "peak": peak, "peak_int8_basis": 2.0 * bf16, "frac_int8_basis": achieved / (2.0 * bf16),
                 "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
                 "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-element-per-site "
@@ -315,7 +317,7 @@ def gpu_arm(args):
         "metric": "pairwise SNP distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> fp32 (0/1 operands, exact integers)" if _query(lib, b"umma_fp4") else "int8 x int8 -> int32 (exact)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", _query(lib, b"umma_cta_group")), "options": os.environ.get("BTB_OPTIONS", ""),
+        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", 2 if (_query(lib, b"umma_fp4") and _query(lib, b"umma_fp4_pair")) else _query(lib, b"umma_cta_group")), "options": os.environ.get("BTB_OPTIONS", ""),
                    "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "block_rows_this_rank": [row_lo, row_hi], "sharding": "contiguous 256-row blocks with equal upper-triangle tile counts per rank, no collective",
                    "l2_policy": "operands (12 GB one-hot) and output (5 GB) exceed the 126 MB L2; no flush needed",
                    "timed_region": "operand encode + distance GEMM per step, CUDA events on the launching stream"},

@@ -42,6 +42,7 @@ extern int g_umma_lockstep;
 extern int g_umma_dbg_negate;
 extern int g_umma_dbg_max_ctas;
 extern int g_umma_tile_bk;
+extern int g_umma_fp4_pair;
 extern int g_umma_dbg_stages;
 extern int g_umma_prefetch;
 void set_ingest_predict(int v);
@@ -50,6 +51,7 @@ int get_ingest_last();
 extern int g_umma_tile_mode;
 extern int g_pack_wpt;
 int umma_max_active_clusters(int cg, int *out);
+int umma_probe(int cg, int every, int64_t *cycles_x100);
 int dist_presence_async(const uint8_t *, int64_t, int64_t, int64_t, uint32_t *, cudaStream_t);
 int dist_encode_fp4_dense_rows(const uint8_t *, int64_t, int64_t, int64_t, const uint8_t *, int64_t, uint8_t *, int32_t *,
                                cudaStream_t);
@@ -128,6 +130,7 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "host_stream_rows")) { g_host_stream_rows = value < 8 ? 8 : value; return BTB_OK; }
     if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_fp4_pair")) { g_umma_fp4_pair = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_bk")) { g_umma_tile_bk = value == 64 ? 64 : 128; return BTB_OK; }
     if (key && !strcmp(key, "umma_dbg_max_ctas")) { g_umma_dbg_max_ctas = value; return BTB_OK; }
     if (key && !strcmp(key, "umma_dbg_stages")) { g_umma_dbg_stages = value; return BTB_OK; }
@@ -142,6 +145,10 @@ extern "C" int btb_set_option(const char *key, int value) {
 extern "C" int btb_query(const char *key, int64_t *value) {
     if (!key || !value) return fail(BTB_EINVAL, "btb_query: NULL argument");
     int v = 0;
+    if (!strncmp(key, "probe_cg", 8) && strlen(key) >= 12) {       // probe_cg<1|2>_e<every>
+        BTB_TRY(umma_probe(key[8] - '0', atoi(key + 11), value));
+        return BTB_OK;
+    }
     if (!strcmp(key, "umma_max_active_clusters_cg2")) { BTB_TRY(umma_max_active_clusters(2, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_max_active_clusters_cg1")) { BTB_TRY(umma_max_active_clusters(1, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
@@ -149,6 +156,7 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
     if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
     if (!strcmp(key, "umma_tile_bk")) { *value = g_umma_tile_bk; return BTB_OK; }
+    if (!strcmp(key, "umma_fp4_pair")) { *value = g_umma_fp4_pair; return BTB_OK; }
     if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }
     if (!strcmp(key, "host_stream")) { *value = g_host_stream; return BTB_OK; }
     if (!strcmp(key, "host_stream_last")) { *value = g_host_stream_last; return BTB_OK; }
@@ -195,6 +203,8 @@ extern "C" int btb_dist_row_share(int64_t n, int rank, int world, int64_t *lo, i
         const int64_t want = total * r / world;
         int64_t acc = 0, I = 0;
         while (I < T && acc + (T - I) <= want) { acc += T - I; ++I; }
+        // shares start on even block rows when there is room: the CTA-pair kernel works on 512-row units
+        if ((I & 1) && I < T && T >= 4 * int64_t(world)) ++I;
         return I;
     };
     *lo = boundary(rank);

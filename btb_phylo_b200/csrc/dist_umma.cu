@@ -30,6 +30,7 @@ namespace btb {
 constexpr int kBlockK = 128;          // K bytes per pipeline stage = one 128B swizzle atom row
 constexpr int kUmmaK = 32;            // K per tcgen05.mma for 8-bit operands
 constexpr int kThreads = 256;
+constexpr int kThreadsWide = 384;     // FP4 full-tile kernels: a second group of epilogue warps, one group per accumulator half
 constexpr int kAccCols = 256;         // accumulator columns per stage (N of the MMA)
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -225,94 +226,130 @@ struct UmmaParams {
 
 // Epilogue of one 128-row x 256-column accumulator buffer: this thread owns matrix row `row`
 // (TMEM lane of `taddr`), reads 32 columns at a time and writes the tile (16-byte stores), its
-// mirror (lane-coalesced 2/4-byte stores) or the tile-packed slot.
+// mirror (lane-coalesced 2/4-byte stores) or the tile-packed slot.  The TMEM loads are software
+// pipelined (the next 32 columns are in flight while the current ones are converted and stored).
 // `valid_cols` < 256 and `tri` = true serve the rectangular 256 x 240 tiles of the FP4 full-tile
-// kernel: a cell is written where column >= row (mirrored where column > row), whatever tile it is in.
+// kernels: a cell is written where column >= row (mirrored where column > row), whatever tile it is
+// in.  `colsum` (shared memory, optional): the row sums of the unit's columns, staged by the caller.
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <typename OutT>
-__device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t taddr, int64_t row, int64_t n0,
-                                                  int row_in_tile, int64_t tile_slot, bool do_mirror,
-                                                  int valid_cols = kAccCols, bool tri = false) {
+__device__ __forceinline__ void emit_chunk(const UmmaParams &p, uint32_t (&v)[32], int c0, int64_t row, int64_t n0,
+                                           int row_in_tile, int64_t tile_slot, bool do_mirror, int valid_cols, bool tri,
+                                           int32_t cr, const int32_t *colsum) {
     OutT *out = static_cast<OutT *>(p.out);
-#pragma unroll 1
-    for (int c0 = 0; c0 < valid_cols; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + uint32_t(c0), v);
-        if (p.fp32acc) {
+    if (p.fp32acc) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = uint32_t(__float2int_rn(__uint_as_float(v[j])));
-        }
-        if (p.dense == 3) {
-            const int32_t cr = row < p.n ? p.rowsum[row] : 0;
+        for (int j = 0; j < 32; ++j) v[j] = uint32_t(__float2int_rn(__uint_as_float(v[j])));
+    }
+    if (p.dense == 3) {
+        if (colsum) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = uint32_t(cr + colsum[c0 + j] - int32_t(v[j]));
+        } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int64_t cj = n0 + c0 + j;
                 v[j] = uint32_t(cr + (cj < p.n ? p.rowsum[cj] : 0) - int32_t(v[j]));
             }
-        } else if (p.dense) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
         }
-        const int64_t col = n0 + c0;
-        if (tri) {
-            // rectangular tiles straddle the diagonal anywhere: per-cell rule
-            const int lim = valid_cols - c0 < 32 ? valid_cols - c0 : 32;
-            if (row < p.n) {
-                OutT *dst = out + row * p.ld + col;
-                if (lim == 32 && col >= row && col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-                    if constexpr (sizeof(OutT) == 2) {
+    } else if (p.dense) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
-                                               v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
-                    } else {
+        for (int j = 0; j < 32; ++j) v[j] = uint32_t(p.bias - int32_t(v[j])) >> (p.dense == 2 ? 2 : 0);
+    }
+    const int64_t col = n0 + c0;
+    if (tri) {
+        // rectangular tiles straddle the diagonal anywhere: per-cell rule
+        const int lim = valid_cols - c0 < 32 ? valid_cols - c0 : 32;
+        if (row < p.n) {
+            OutT *dst = out + row * p.ld + col;
+            if (lim == 32 && col >= row && col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
+                                           v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < lim && col + j >= row && col + j < p.n) dst[j] = OutT(v[j]);
+                    for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                if (do_mirror) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < lim && col + j > row && col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
-                }
-            }
-            continue;
-        }
-        if (p.out_mode == 1) {
-            OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
-                        (int64_t)row_in_tile * BTB_TILE + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = (row < p.n && col + j < p.n) ? OutT(v[j]) : OutT(0);
-        } else {
-            if (row < p.n) {
-                OutT *dst = out + row * p.ld + col;
-                if (col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    // interior: 32 consecutive outputs of this row as 16-byte stores
-                    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-                    if constexpr (sizeof(OutT) == 2) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
-                                               v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col + j < p.n) dst[j] = OutT(v[j]);
-                }
-            }
-            if (do_mirror && row < p.n) {
+            } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+                    if (j < lim && col + j >= row && col + j < p.n) dst[j] = OutT(v[j]);
             }
+            if (do_mirror) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < lim && col + j > row && col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+            }
+        }
+        return;
+    }
+    if (p.out_mode == 1) {
+        OutT *dst = out + tile_slot * (BTB_TILE * BTB_TILE) +
+                    (int64_t)row_in_tile * BTB_TILE + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = (row < p.n && col + j < p.n) ? OutT(v[j]) : OutT(0);
+    } else {
+        if (row < p.n) {
+            OutT *dst = out + row * p.ld + col;
+            if (col + 32 <= p.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                // interior: 32 consecutive outputs of this row as 16-byte stores
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        d4[j] = make_uint4(v[8 * j] | (v[8 * j + 1] << 16), v[8 * j + 2] | (v[8 * j + 3] << 16),
+                                           v[8 * j + 4] | (v[8 * j + 5] << 16), v[8 * j + 6] | (v[8 * j + 7] << 16));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) d4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col + j < p.n) dst[j] = OutT(v[j]);
+            }
+        }
+        if (do_mirror && row < p.n) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col + j < p.n) out[(col + j) * p.ld + row] = OutT(v[j]);
+        }
+    }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t taddr, int64_t row, int64_t n0,
+                                                  int row_in_tile, int64_t tile_slot, bool do_mirror,
+                                                  int valid_cols = kAccCols, bool tri = false,
+                                                  const int32_t *colsum = nullptr) {
+    const int32_t cr = (p.dense == 3 && row < p.n) ? p.rowsum[row] : 0;
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32_issue(taddr, va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < valid_cols; c0 += 64) {
+        tmem_ld_wait();
+        const bool more = c0 + 32 < valid_cols;
+        if (more) tmem_ld_32x32_issue(taddr + uint32_t(c0 + 32), vb);
+        emit_chunk<OutT>(p, va, c0, row, n0, row_in_tile, tile_slot, do_mirror, valid_cols, tri, cr, colsum);
+        if (more) {
+            tmem_ld_wait();
+            if (c0 + 64 < valid_cols) tmem_ld_32x32_issue(taddr + uint32_t(c0 + 64), va);
+            emit_chunk<OutT>(p, vb, c0 + 32, row, n0, row_in_tile, tile_slot, do_mirror, valid_cols, tri, cr, colsum);
         }
     }
 }
@@ -687,6 +724,13 @@ __device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
 }
+__device__ __forceinline__ void umma_mxf4_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t sfa, uint32_t sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, uint32_t v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
@@ -847,7 +891,7 @@ struct Fp4TileCfgT {
     static constexpr int kBBytes = kBN * BK;                          // 30 KB / 15 KB
     static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB / 31 KB (multiples of 1024)
     static constexpr int kStages = BK == 128 ? 3 : 6;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;   // + align slack, barriers, column sums
 };
 struct Fp4TileCfg : Fp4TileCfgT<128> {
     static constexpr int kPrefetch = 0;                               // K blocks the optional L2 prefetch runs ahead (measured: no gain,
@@ -860,7 +904,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, 
 }
 
 template <typename OutT, int kStages = Fp4TileCfg::kStages, int BK = 128>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsWide, 1)
 dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const UmmaParams p) {
     using Cfg = Fp4TileCfgT<BK>;
@@ -988,22 +1032,313 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
             const int2 w = p.worklist[u];
             const int64_t n0 = int64_t(w.y & kUnitColMask) * Cfg::kBN;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            // the row sums of this unit's columns, staged while the K loop still runs
+            int32_t *colsum = reinterpret_cast<int32_t *>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256);
+            if (p.dense == 3) {
+                for (int c = int(threadIdx.x) - 128; c < 256; c += 256)
+                    colsum[c] = (c < Cfg::kBN && n0 + c < p.n) ? p.rowsum[n0 + c] : 0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            {
+                const int h = (warp - 4) >> 2;                 // warps 4-7 drain half 0, warps 8-11 half 1, concurrently
                 mbar_wait(tfull_bar(h), uint32_t(it) & 1u);
                 tc_fence_after();
                 const int row_in_tile = h * 128 + quarter * 32 + lane;
                 drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h) * kHalf1Col,
-                                        int64_t(w.x) * BTB_TILE + row_in_tile, n0, row_in_tile, 0, p.mirror != 0, Cfg::kBN, true);
+                                        int64_t(w.x) * BTB_TILE + row_in_tile, n0, row_in_tile, 0, p.mirror != 0, Cfg::kBN, true,
+                                        p.dense == 3 ? colsum : nullptr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_local(tempty_bar(h));
             }
+            if (p.dense == 3) asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with colsum
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP4 CTA-pair variant (cta_group::2): the single-CTA full-tile kernel is bound by how fast one SM
+// can pull operands (measured ~53 B/clk; it needs 66 B/clk to keep the tensor pipe busy).  Here a
+// pair of CTAs computes 512 rows x 240 columns: each CTA stages its own 256 A rows but only HALF of
+// the B block (120 rows) -- the pair's MMAs (M = 256: 128 rows from each CTA, N = 240: 120 B rows
+// from each CTA) read the other half from the partner's shared memory -- 47 KB instead of 62 KB per
+// SM per 960 tensor cycles (49 B/clk).  Protocol: every TMA load of both CTAs signals the LEADER's
+// full barrier (leader: arrive.expect_tx for both CTAs' bytes); the leader's MMA warp issues for
+// the pair and releases the stage in both CTAs with one multicast tcgen05.commit; each CTA drains
+// its own 2 x 128 accumulator rows and reports to the leader's tempty barriers.
+struct Fp4PairCfg {
+    static constexpr int kBN = 240;
+    static constexpr int kABytes = 256 * kBlockK;                     // 32 KB
+    static constexpr int kBBytes = (kBN / 2) * kBlockK;               // 15 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;             // 47 KB (multiple of 1024)
+    static constexpr int kStages = 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;   // + align slack, barriers, column sums
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// TMA load of this CTA's tile, completion bytes reported to `remote_bar` (a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t remote_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(remote_bar), "r"(c0), "r"(c1) : "memory");
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreadsWide, 1)
+dist_umma_fp4_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const UmmaParams p) {
+    using Cfg = Fp4PairCfg;
+    constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t kHalf1Col = 256, kSfCol = 496;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int h) { return bar_base + 8u * (2 * kStages + h); };
+    auto tempty_bar = [&](int h) { return bar_base + 8u * (2 * kStages + 2 + h); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int64_t worker = blockIdx.x / 2, n_workers = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int h = 0; h < 2; ++h) { mbar_init(tfull_bar(h), 1); mbar_init(tempty_bar(h), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<2>(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp >= 4) tmem_st_32x32_x16(tmem_base + (uint32_t((warp & 3) * 32) << 16) + kSfCol, 0x7F7F7F7Fu);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers) {
+                const int2 w = p.worklist[u];
+                const int m0 = w.x * 512 + int(cta_rank) * 256;
+                const int n0 = (w.y & kUnitColMask) * Cfg::kBN + int(cta_rank) * (Cfg::kBN / 2);
+                if (p.lockstep && u != worker) {                 // see dist_umma_kernel; every CTA of every pair arrives
+                    const int64_t round = (u - worker) / n_workers;
+                    const int64_t full_rounds = p.units / n_workers;
+                    const int64_t last_count = p.units - full_rounds * n_workers;
+                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers * 2;
+                    if (round > full_rounds - 1) target += last_count * 2;
+                    target -= int64_t(p.lock_slack) * n_workers * 2;
+                    __threadfence();
+                    atomicAdd(p.lockstep, 1u);
+                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+                }
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                    const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
+                    tma_load_2d_pair(smem_a(stage), &map_a, lead_full, int(kb * kBlockK), m0);
+                    tma_load_2d_pair(smem_b(stage), &map_b, lead_full, int((kb + (kb >= p.neg_from ? p.b_shift : 0)) * kBlockK), n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader) {
+            constexpr uint32_t idesc0 = make_mxf4_idesc(256, Cfg::kBN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t it = 0;
+            for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+                const uint32_t drained = (uint32_t(it) & 1u) ^ 1u;
+                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                    const uint32_t idesc = idesc0 | ((kb >= p.neg_from && p.b_shift == 0) ? kNegateA : 0u);
+                    mbar_wait(full_bar(stage), phase);
+                    if (kb == 0) mbar_wait(tempty_bar(0), drained);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                        const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_mxf4_cg2(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
+                                          tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    __syncwarp();
+                    if (kb == 0) { mbar_wait(tempty_bar(1), drained); tc_fence_after(); }
+                    if (elect_one()) {
+                        const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + 128 * kBlockK);
+                        const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_mxf4_cg2(tmem_base + kHalf1Col, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc,
+                                          tmem_base + kSfCol, tmem_base + kSfCol + 4, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit<2>(empty_bar(stage));
+                        if (kb == p.k_blocks - 1) { umma_commit<2>(tfull_bar(0)); umma_commit<2>(tfull_bar(1)); }
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const int2 w = p.worklist[u];
+            const int64_t n0 = int64_t(w.y & kUnitColMask) * Cfg::kBN;
+            const int64_t m0 = int64_t(w.x) * 512 + int64_t(cta_rank) * 256;
+            int32_t *colsum = reinterpret_cast<int32_t *>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256);
+            if (p.dense == 3) {
+                for (int c = int(threadIdx.x) - 128; c < 256; c += 256)
+                    colsum[c] = (c < Cfg::kBN && n0 + c < p.n) ? p.rowsum[n0 + c] : 0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            {
+                const int h = (warp - 4) >> 2;
+                mbar_wait(tfull_bar(h), uint32_t(it) & 1u);
+                tc_fence_after();
+                const int row_in_tile = h * 128 + quarter * 32 + lane;
+                drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h) * kHalf1Col,
+                                        m0 + row_in_tile, n0, row_in_tile, 0, p.mirror != 0, Cfg::kBN, true,
+                                        p.dense == 3 ? colsum : nullptr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_bar(h), 0);
+            }
+            if (p.dense == 3) asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Probe (no data movement): how fast does one SM / one SM pair issue kind::mxf4 MMAs when the stage
+// release (tcgen05.commit) comes every `every` stages?  Shared memory is whatever it holds; a ring
+// of 4 barriers stands in for the empty barriers.  Reports cycles per stage (8 MMAs of 128x240x64
+// per CTA), averaged over `iters` stages, in *cycles_x100.
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1) umma_probe_kernel(int iters, int every, unsigned long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = smem_base, b_smem = smem_base + 256 * 128;
+    const uint32_t bar_base = smem_base + 64 * 1024;
+    auto bar = [&](int k) { return bar_base + 8u * k; };
+    const uint32_t tmem_slot = bar_base + 64;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+    if (warp == 1 && (threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 4; ++k) mbar_init(bar(k), 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (warp >= 4) tmem_st_32x32_x16(tmem_base + (uint32_t((warp & 3) * 32) << 16) + 496, 0x7F7F7F7Fu);
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    if (warp == 1 && cta_rank == 0) {
+        const uint32_t idesc = make_mxf4_idesc(CG == 2 ? 256 : 128, 240);
+        long long t0 = 0;
+        uint32_t phase[4] = {0, 0, 0, 0};
+        int commits = 0;
+        for (int it = 0; it < iters + 8; ++it) {
+            if (it == 8) t0 = clock64();
+            if (elect_one()) {
+                const uint64_t a_desc = make_kmajor_sw128_desc(a_smem), a2_desc = make_kmajor_sw128_desc(a_smem + 128 * 128);
+                const uint64_t b_desc = make_kmajor_sw128_desc(b_smem);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (CG == 1) umma_mxf4(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, tmem_base + 496, tmem_base + 500, 1u);
+                    else umma_mxf4_cg2(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, tmem_base + 496, tmem_base + 500, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if constexpr (CG == 1) umma_mxf4(tmem_base + 256, a2_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, tmem_base + 496, tmem_base + 500, 1u);
+                    else umma_mxf4_cg2(tmem_base + 256, a2_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, tmem_base + 496, tmem_base + 500, 1u);
+                }
+                if (it % every == every - 1) umma_commit<CG>(bar(commits & 3));
+            }
+            __syncwarp();
+            if (it % every == every - 1) {
+                ++commits;
+                if (commits >= 3) {                                  // stay at most 3 commits ahead
+                    const int k = (commits - 3) & 3;
+                    mbar_wait(bar(k), phase[k]);
+                    phase[k] ^= 1;
+                }
+            }
+        }
+        // drain
+        if (elect_one()) umma_commit<CG>(bar(commits & 3));
+        __syncwarp();
+        for (int c = commits >= 3 ? commits - 2 : 0; c <= commits; ++c) { const int k = c & 3; mbar_wait(bar(k), phase[k]); phase[k] ^= 1; }
+        const long long t1 = clock64();
+        if ((threadIdx.x & 31) == 0) out[blockIdx.x] = (unsigned long long)((t1 - t0) * 100 / iters);
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+int umma_probe(int cg, int every, int64_t *cycles_x100) {
+    const int iters = 4000;
+    unsigned long long *d = nullptr;
+    BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), 148 * 8));
+    BTB_CUDA(cudaMemset(d, 0, 148 * 8));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 64 * 1024 + 1024 + 256;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cg == 2) {
+        BTB_CUDA(cudaFuncSetAttribute(umma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.dynamicSmemBytes)));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, umma_probe_kernel<2>, iters, every, d));
+    } else {
+        BTB_CUDA(cudaFuncSetAttribute(umma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.dynamicSmemBytes)));
+        BTB_CUDA(cudaLaunchKernelEx(&cfg, umma_probe_kernel<1>, iters, every, d));
+    }
+    BTB_CUDA(cudaDeviceSynchronize());
+    unsigned long long h[148];
+    BTB_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    unsigned long long sum = 0, cnt = 0;
+    for (int i = 0; i < 148; ++i) if (h[i]) { sum += h[i]; ++cnt; }
+    *cycles_x100 = cnt ? int64_t(sum / cnt) : 0;
+    return BTB_OK;
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -1044,6 +1379,7 @@ int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 te
 int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
 int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
 int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
+int g_umma_fp4_pair = 1;       // "umma_fp4_pair": cta_group::2 version of the FP4 full-tile kernel (0: single-CTA kernel)
 int g_umma_tile_bk = 128;      // "umma_tile_bk": K bytes per stage of the FP4 full-tile kernel (128: 3 stages; 64: 6 stages -- measured equal)
 int g_umma_dbg_max_ctas = 0;   // experiment: cap the grid of the FP4 full-tile kernel (0 = one CTA per SM)
 int g_umma_dbg_stages = 0;     // experiment: 2 = run the FP4 full-tile kernel with two pipeline stages
@@ -1198,6 +1534,18 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
                 for (int64_t I = r0; I < r1; ++I)
                     if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h.push_back(make_int2(int(I), int(j)));
         }
+    }
+    if (kind == 2) {
+        // CTA-pair units (P, j): 512 rows x 240 columns, same band order (4 pair rows per band)
+        h.clear();
+        const int64_t NJ = (n + Fp4PairCfg::kBN - 1) / Fp4PairCfg::kBN;
+        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
+            const int64_t r1 = std::min(hi, r0 + kBand);
+            for (int64_t j = (r0 * BTB_TILE) / Fp4PairCfg::kBN; j < NJ; ++j)
+                for (int64_t P = r0 / 2; P < (r1 + 1) / 2; ++P)
+                    if ((P * 512) / Fp4PairCfg::kBN <= j) h.push_back(make_int2(int(P), int(j)));
+        }
+    } else if (kind == 1) {
         // L2 prefetch duty: the grid runs the list in rounds of one unit per SM; within a round the
         // first unit that touches an A panel (block row) / a B panel (column block) prefetches it
         int sms = 0;
@@ -1243,6 +1591,48 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
     BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int2 *d_units = nullptr;
     int64_t n_units = 0;
+    if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && dev < 16) {
+        // CTA pairs: 512-row units, B split between the two SMs of a pair
+        BTB_TRY(get_rows_list(n, row_lo, row_hi, 2, &d_units, &n_units));
+        if (n_units >= 2 * int64_t(sms / 2)) {
+            CUtensorMap ma, mb;
+            BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+            BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4PairCfg::kBN / 2));
+            UmmaParams p;
+            p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
+            p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
+            p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
+            p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;
+            p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+            if (neg_from >= 0) p.neg_from = neg_from;
+            const int64_t pairs = std::min<int64_t>(sms / 2, p.units);
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[2];
+            cfg.gridDim = dim3(unsigned(pairs * 2));
+            cfg.blockDim = dim3(kThreadsWide);
+            cfg.dynamicSmemBytes = Fp4PairCfg::kSmemBytes;
+            cfg.stream = stream;
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            static unsigned int *d_lock2[16] = {nullptr};
+            if (g_umma_lockstep && p.units > pairs) {
+                if (!d_lock2[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock2[dev]), 256));
+                BTB_CUDA(cudaMemsetAsync(d_lock2[dev], 0, 4, stream));
+                p.lockstep = d_lock2[dev]; p.lock_slack = g_umma_lockstep - 1;
+                attr[1].id = cudaLaunchAttributeCooperative;
+                attr[1].val.cooperative = 1;
+                cfg.numAttrs = 2;
+            }
+            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_pair_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4PairCfg::kSmemBytes));
+            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_pair_kernel<uint16_t>, ma, mb, p));
+            *launched = 1;
+            return BTB_OK;
+        }
+    }
     BTB_TRY(get_rows_list(n, row_lo, row_hi, 1, &d_units, &n_units));
     if (n_units < 2 * int64_t(sms) || dev >= 16) return BTB_OK;
     CUtensorMap ma, mb;
@@ -1263,7 +1653,7 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsWide);
     cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
     cfg.stream = stream;
     cfg.numAttrs = 0;

@@ -61,6 +61,8 @@ def row_share(n, rank, world):
         while i < T and acc + (T - i) <= want:
             acc += T - i
             i += 1
+        if i % 2 == 1 and i < T and T >= 4 * world:          # even starts: 512-row units of the CTA-pair kernel
+            i += 1
         return i
     return boundary(rank), boundary(rank + 1)
 

@@ -113,6 +113,19 @@ def test_kernel_variants_agree(capi, oracle):
                 _, got = gpu_matrix(capi, general, 1, 1)
                 assert (got == want_g).all(), (general_fp4, tile_mode)
         capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
+        # tuning knobs of the FP4 full-tile kernels: CTA pairs (cta_group::2), 64-byte K blocks with six
+        # stages, L2 prefetch, loose lockstep
+        for key, values, reset in ((b"umma_fp4_pair", (0, 1), None), (b"umma_tile_bk", (64, 128), 128),
+                                   (b"umma_prefetch", (8, 0), 0), (b"umma_lockstep", (3, 0, 1), 1)):
+            before = ctypes.c_int64(0)
+            lib.btb_query(key, ctypes.byref(before))
+            for v in values:
+                capi.check(lib.btb_set_option(key, v))
+                _, got = gpu_matrix(capi, big_dense, 1, 1)
+                assert (got == want_big_dense).all(), (key, v)
+                _, got = gpu_matrix(capi, big, 1, 1)
+                assert (got == want_big).all(), (key, v)
+            capi.check(lib.btb_set_option(key, reset if reset is not None else before.value))
         capi.check(lib.btb_set_option(b"umma_fp4_general", 0))   # the CTA-pair variants are int8 kernels
         capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
         for variant in (0, 1, 2, 3):
