@@ -43,6 +43,8 @@ extern int g_umma_dbg_negate;
 extern int g_umma_dbg_max_ctas;
 extern int g_umma_tile_bk;
 extern int g_umma_fp4_pair;
+extern int g_umma_coop;
+extern int g_umma_major_zero;
 extern int g_umma_dbg_stages;
 extern int g_umma_prefetch;
 void set_ingest_predict(int v);
@@ -130,6 +132,8 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "host_stream_rows")) { g_host_stream_rows = value < 8 ? 8 : value; return BTB_OK; }
     if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_coop")) { g_umma_coop = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "umma_major_zero")) { g_umma_major_zero = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_pair")) { g_umma_fp4_pair = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_bk")) { g_umma_tile_bk = value == 64 ? 64 : 128; return BTB_OK; }
     if (key && !strcmp(key, "umma_dbg_max_ctas")) { g_umma_dbg_max_ctas = value; return BTB_OK; }
@@ -157,6 +161,7 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
     if (!strcmp(key, "umma_tile_bk")) { *value = g_umma_tile_bk; return BTB_OK; }
     if (!strcmp(key, "umma_fp4_pair")) { *value = g_umma_fp4_pair; return BTB_OK; }
+    if (!strcmp(key, "umma_major_zero")) { *value = g_umma_major_zero; return BTB_OK; }
     if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }
     if (!strcmp(key, "host_stream")) { *value = g_host_stream; return BTB_OK; }
     if (!strcmp(key, "host_stream_last")) { *value = g_host_stream_last; return BTB_OK; }

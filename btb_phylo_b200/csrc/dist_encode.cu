@@ -25,6 +25,8 @@
 
 namespace btb {
 
+int g_umma_major_zero = 1;     // "umma_major_zero": per site, the most frequent symbol takes the all-zero vertex of the dense code
+
 // ------------------------------------------------------------------ alphabet scan (-a mode)
 __global__ void presence_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len,
                                 int64_t row_stride, uint32_t *__restrict__ present /*[8]*/) {
@@ -251,18 +253,70 @@ encode_simplex_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, 
     }
 }
 
+// ---- per-site symbol statistics for the dense codes -----------------------------------------------
+// d(i,j) only counts sites where the two rows differ, so every site may use its own bijection of
+// the four symbols onto the tetrahedron vertices.  Mapping each site's MOST FREQUENT symbol to the
+// all-zero vertex makes the operand as sparse as the data allows (a SNP alignment is mostly major
+// alleles): the tensor cores multiply mostly zeros, which is what keeps the kernel under the power
+// cap (the data-dependence of tensor power is measured: dense +-1 operands cost 25 % of the clock).
+// counts: thread = 4 adjacent sites over a strip of rows, four 16-bit counters packed per site.
+constexpr int kMajorStripRows = 2048, kMajorRowStep = 8;
+__global__ void __launch_bounds__(256)
+site_counts_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
+                   const uint8_t *__restrict__ table_g, uint32_t *__restrict__ counts /*[len][4]*/) {
+    __shared__ uint8_t table[256];
+    table[threadIdx.x] = table_g[threadIdx.x];
+    __syncthreads();
+    const int64_t site = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
+    if (site >= len) return;
+    const int64_t r0 = int64_t(blockIdx.y) * kMajorStripRows, r1 = r0 + kMajorStripRows < n ? r0 + kMajorStripRows : n;
+    const bool vec = (reinterpret_cast<uintptr_t>(seqs) % 4 == 0) && (row_stride % 4 == 0) && site + 3 < len;
+    uint64_t c[4] = {0, 0, 0, 0};
+    for (int64_t r = r0; r < r1; r += kMajorRowStep) {      // a sample of the rows is enough: any choice is exact, only sparsity is at stake
+        const uint8_t *p = seqs + r * row_stride + site;
+        uint32_t w;
+        if (vec) w = *reinterpret_cast<const uint32_t *>(p);
+        else {
+            w = 0;
+            for (int b = 0; b < 4; ++b) w |= uint32_t(site + b < len ? p[b] : 'A') << (8 * b);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] += 1ull << (16 * (table[(w >> (8 * b)) & 0xff] & 3));
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (site + b < len) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t v = uint32_t(c[b] >> (16 * k)) & 0xffffu;
+                if (v) atomicAdd(&counts[(site + b) * 4 + k], v);
+            }
+        }
+}
+__global__ void __launch_bounds__(256)
+site_major_kernel(const uint32_t *__restrict__ counts, int64_t len, uint8_t *__restrict__ major) {
+    const int64_t site = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (site >= len) return;
+    const uint4 c = *reinterpret_cast<const uint4 *>(counts + site * 4);
+    uint32_t best = c.x;
+    uint8_t m = 0;
+    if (c.y > best) { best = c.y; m = 1; }
+    if (c.z > best) { best = c.z; m = 2; }
+    if (c.w > best) { best = c.w; m = 3; }
+    major[site] = m;
+}
+
 // dense tetrahedron code as packed e2m1 nibbles (1.0 = 0x2): one thread per 16 sites -> 48 nibbles = 24 bytes
 __global__ void __launch_bounds__(256)
 encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
                   const uint8_t *__restrict__ table_g, int64_t kbytes, uint8_t *__restrict__ A, int aligned,
-                  int32_t *__restrict__ rowsum) {
-    __shared__ uint32_t vertex[256];                        // symbol -> its 3 nibbles (x | y << 4 | z << 8)
-    {
-        const uint32_t code = table_g[threadIdx.x];
-        vertex[threadIdx.x] = code == 1 ? 0x022u : code == 2 ? 0x202u : code == 3 ? 0x220u : 0u;
-    }
+                  int32_t *__restrict__ rowsum, const uint8_t *__restrict__ major /* per site, or nullptr */) {
+    // one thread per 32 sites: two 16-byte loads -> 96 nibbles = three 16-byte stores
+    __shared__ uint8_t code_of[256];                        // byte -> symbol code 0..3 (anything else: 0)
+    code_of[threadIdx.x] = table_g[threadIdx.x] & 3;
     __syncthreads();
-    const int64_t groups = (kbytes + 23) / 24;
+    constexpr uint64_t kVertex = 0x0220020200220000ull;     // vertex t -> its 3 nibbles (x | y << 4 | z << 8), 16 bits each
+    const int64_t groups = (kbytes + 47) / 48;
     const bool vec_in = aligned && (row_stride % 16 == 0) && (reinterpret_cast<uintptr_t>(seqs) % 16 == 0);
     for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
         const uint8_t *p = seqs + row * row_stride;
@@ -271,24 +325,37 @@ encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int6
         int nonzero = 0;
         for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
              g += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t site = g * 16;
-            uint32_t raw[4] = {0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu, 0x2e2e2e2eu};
-            if (vec_in && site + 15 < len) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(p + site);
-                raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w;
+            const int64_t site = g * 32;
+            uint32_t raw[8], maj[8];                        // maj: the site's zero-coded symbol (padded to 32 sites by the host)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { raw[q] = 0x2e2e2e2eu; maj[q] = 0; }
+            if (major && site < len) {
+                const uint4 m0 = *reinterpret_cast<const uint4 *>(major + site);
+                const uint4 m1 = *reinterpret_cast<const uint4 *>(major + site + 16);
+                maj[0] = m0.x; maj[1] = m0.y; maj[2] = m0.z; maj[3] = m0.w;
+                maj[4] = m1.x; maj[5] = m1.y; maj[6] = m1.z; maj[7] = m1.w;
+            }
+            if (vec_in && site + 31 < len) {
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(p + site);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(p + site + 16);
+                raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w;
+                raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
             } else {
-                for (int b = 0; b < 16; ++b)
+                for (int b = 0; b < 32; ++b)
                     if (site + b < len) raw[b >> 2] = (raw[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (uint32_t(p[site + b]) << (8 * (b & 3)));
             }
-            uint32_t out[6];
+            uint32_t out[12];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                   // 8 sites -> 96 bits
+            for (int h = 0; h < 4; ++h) {                   // 8 sites -> 96 bits
                 uint64_t lo = 0, hi = 0;                    // bits 0..63, 64..95
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     const uint32_t byte = (raw[2 * h + (b >> 2)] >> (8 * (b & 3))) & 0xff;
-                    const uint64_t t = vertex[byte];
-                    nonzero += t != 0;
+                    const uint32_t mj = (maj[2 * h + (b >> 2)] >> (8 * (b & 3))) & 3;
+                    const bool live = site + 8 * h + b < len;
+                    const uint32_t vtx = live ? (code_of[byte] ^ mj) : 0u;        // XOR: a bijection that sends the major symbol to 0
+                    const uint64_t t = (kVertex >> (16 * vtx)) & 0xfffu;
+                    nonzero += vtx != 0;
                     const int sh = 12 * b;
                     if (sh < 64) lo |= t << sh;
                     if (sh + 12 > 64) hi |= sh >= 64 ? t << (sh - 64) : t >> (64 - sh);
@@ -297,9 +364,16 @@ encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int6
                 out[3 * h + 1] = uint32_t(lo >> 32);
                 out[3 * h + 2] = uint32_t(hi);
             }
-            const int64_t wi = g * 6;
-            for (int k = 0; k < 6; ++k)
-                if (wi + k < total) dst[wi + k] = out[k];
+            const int64_t wi = g * 12;
+            if (wi + 12 <= total) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst + wi);       // 48-byte groups: 16-byte aligned
+                d4[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                d4[1] = make_uint4(out[4], out[5], out[6], out[7]);
+                d4[2] = make_uint4(out[8], out[9], out[10], out[11]);
+            } else {
+                for (int k = 0; k < 12; ++k)
+                    if (wi + k < total) dst[wi + k] = out[k];
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nonzero += __shfl_xor_sync(0xffffffffu, nonzero, o);
@@ -375,8 +449,8 @@ int dist_encode_fp4_dense_rows(const uint8_t *d_seqs, int64_t rows, int64_t len,
                                cudaStream_t stream) {
     if (rows <= 0) return BTB_OK;
     const bool aligned = (reinterpret_cast<uintptr_t>(d_seqs) % 4 == 0) && (row_stride % 4 == 0);
-    dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(rows, 65535));
-    encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, kb, A_rows, aligned ? 1 : 0, rowsum_rows);
+    dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(rows, 65535));
+    encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, kb, A_rows, aligned ? 1 : 0, rowsum_rows, nullptr);
     BTB_CUDA(cudaGetLastError());
     return BTB_OK;
 }
@@ -474,10 +548,24 @@ extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int
             dim3 grid((unsigned)std::min<int64_t>((pb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             encode_fp4_planes_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, sigma, pb, kb, A, aligned ? 1 : 0);
         } else if (umma_fp4_dense(sigma, len)) {
-            dim3 grid((unsigned)std::min<int64_t>((kb / 24 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
+            dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
             BTB_CUDA(cudaMemsetAsync(rowsum, 0, size_t(n) * 4, stream));
-            encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0, rowsum);
+            uint8_t *d_major = nullptr;
+            uint32_t *d_counts = nullptr;
+            if (g_umma_major_zero && n >= 64) {            // per-site majority symbol -> zero vertex (sparser operand)
+                const int64_t padded = (len + 31) / 32 * 32;
+                BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_counts), size_t(len) * 16, stream));
+                BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_major), size_t(padded), stream));
+                BTB_CUDA(cudaMemsetAsync(d_counts, 0, size_t(len) * 16, stream));
+                BTB_CUDA(cudaMemsetAsync(d_major, 0, size_t(padded), stream));
+                dim3 cgrid((unsigned)((len + 1023) / 1024), (unsigned)((n + kMajorStripRows - 1) / kMajorStripRows));
+                site_counts_kernel<<<cgrid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, d_counts);
+                site_major_kernel<<<(unsigned)((len + 255) / 256), 256, 0, stream>>>(d_counts, len, d_major);
+            }
+            encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_table, kb, A, aligned ? 1 : 0, rowsum, d_major);
+            if (d_counts) BTB_CUDA(cudaFreeAsync(d_counts, stream));
+            if (d_major) BTB_CUDA(cudaFreeAsync(d_major, stream));
         } else if (sigma_dense(sigma) && g_umma_dense_simplex) {
             dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(n, 65535));
             int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);

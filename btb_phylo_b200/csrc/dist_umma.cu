@@ -1379,6 +1379,9 @@ int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 te
 int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
 int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
 int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
+int g_umma_coop = 1;           // "umma_coop": 0 launches the CTA-pair kernel without the cooperative attribute -- only for
+                               // profilers (ncu cannot replay a cooperative cluster launch); the grid is one CTA per SM, so
+                               // all CTAs are co-resident whenever the GPU is otherwise idle
 int g_umma_fp4_pair = 1;       // "umma_fp4_pair": cta_group::2 version of the FP4 full-tile kernel (0: single-CTA kernel)
 int g_umma_tile_bk = 128;      // "umma_tile_bk": K bytes per stage of the FP4 full-tile kernel (128: 3 stages; 64: 6 stages -- measured equal)
 int g_umma_dbg_max_ctas = 0;   // experiment: cap the grid of the FP4 full-tile kernel (0 = one CTA per SM)
@@ -1625,7 +1628,7 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
                 p.lockstep = d_lock2[dev]; p.lock_slack = g_umma_lockstep - 1;
                 attr[1].id = cudaLaunchAttributeCooperative;
                 attr[1].val.cooperative = 1;
-                cfg.numAttrs = 2;
+                cfg.numAttrs = g_umma_coop ? 2 : 1;
             }
             BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_pair_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4PairCfg::kSmemBytes));
             BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_pair_kernel<uint16_t>, ma, mb, p));
