@@ -1,8 +1,11 @@
 // C-ABI of libbtbphylo.so: error plumbing, distance stage (levels 1-3).  See include/btb_phylo.h.
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <functional>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -57,6 +60,10 @@ int umma_probe(int cg, int every, int64_t *cycles_x100);
 int dist_presence_async(const uint8_t *, int64_t, int64_t, int64_t, uint32_t *, cudaStream_t);
 int dist_encode_fp4_dense_rows(const uint8_t *, int64_t, int64_t, int64_t, const uint8_t *, int64_t, uint8_t *, int32_t *,
                                cudaStream_t);
+int g_csv_mmap = 0;             // "csv_mmap": write snps.csv through a file mapping, rows formatted in place by all host threads.
+                               // Off: measured 3.5-3.9 s for the 12.2 GB C4 file against 2.7-3.1 s for write() -- shared-mapping
+                               // write faults cost more than the buffered write path, and formatting (0.4 s) hides behind either.
+int g_dense_pageable = 1;      // "dense_pageable": alignments above 256 MB are read into pageable memory
 int g_host_stream_last = -1;    // "host_stream_last": 1 if the last level-2 call completed on the streamed path
 int g_host_stream_rows = 64;    // "host_stream_rows": block rows per streamed band (narrow strips copy slowly)
 int g_host_stream = 0;         // "host_stream": level 2 uploads, computes and downloads band by band (see streamed_matrix).
@@ -128,6 +135,8 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
+    if (key && !strcmp(key, "csv_mmap")) { g_csv_mmap = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "dense_pageable")) { g_dense_pageable = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "host_stream")) { g_host_stream = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "host_stream_rows")) { g_host_stream_rows = value < 8 ? 8 : value; return BTB_OK; }
     if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
@@ -476,11 +485,61 @@ struct DenseFasta {
     std::vector<std::string> names;
     int64_t n = 0, len = 0, stride = 0;
     uint8_t *rows = nullptr;          // pinned
-    ~DenseFasta() { if (rows) cudaFreeHost(rows); }
+    bool pinned = true;               // large alignments use pageable memory: pinning 1.5 GB costs more than the staged upload
+    ~DenseFasta() { release(); }
+    void release() { if (rows) { if (pinned) cudaFreeHost(rows); else free(rows); } rows = nullptr; }
+    int alloc(size_t bytes) {
+        pinned = bytes <= (size_t(256) << 20) || !g_dense_pageable;
+        if (pinned) { BTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&rows), bytes)); }
+        else if (!(rows = static_cast<uint8_t *>(aligned_alloc(4096, (bytes + 4095) & ~size_t(4095))))) return fail(BTB_ENOMEM, "out of host memory");
+        return BTB_OK;
+    }
 };
 
 // File -> dense pinned rows.  Error texts follow snp-dists 0.8.2.
 int read_dense(const char *path, int threads, DenseFasta &df) {
+    // Fast path for what snp-sites writes (one unwrapped line per record, equal lengths): frame by
+    // prediction (host_io.h) and pread every record straight into the pinned rows.  The host checks
+    // that no line break hides inside a record; anything unexpected takes the exact path below.
+    if (get_ingest_predict()) {
+        std::vector<SourceFile> files;
+        const char *one[1] = {path};
+        std::vector<FastaRecord> recs;
+        bool fast = false;
+        if (open_sources(one, 1, files) == BTB_OK && frame_predicted(files, recs, &fast) == BTB_OK && fast &&
+            recs[0].line_w == 0 && recs[0].eol == 1 && recs[0].seq_len > 0 && int64_t(recs.size()) <= BTB_MAX_SEQ) {
+            df.n = int64_t(recs.size());
+            df.len = recs[0].seq_len;
+            df.stride = std::max<int64_t>(16, (df.len + 15) / 16 * 16);
+            BTB_TRY(df.alloc(size_t(df.n * df.stride)));
+            std::atomic<bool> ok{true};
+            auto work = [&](int64_t lo, int64_t hi) {
+                for (int64_t i = lo; i < hi && ok; ++i) {
+                    uint8_t *dst = df.rows + i * df.stride;
+                    if (read_exact(files[0], recs[size_t(i)].seq_off, size_t(df.len), dst) != BTB_OK ||
+                        memchr(dst, '\n', size_t(df.len)) || dst[df.len - 1] == '\r') { ok = false; return; }
+                    memset(dst + df.len, '.', size_t(df.stride - df.len));
+                }
+            };
+            const int T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), df.n / 16)));
+            if (T == 1) work(0, df.n);
+            else {
+                std::vector<std::thread> pool;
+                const int64_t span = (df.n + T - 1) / T;
+                for (int t = 0; t < T; ++t) {
+                    const int64_t lo = t * span, hi = std::min(df.n, lo + span);
+                    if (lo < hi) pool.emplace_back(work, lo, hi);
+                }
+                for (auto &th : pool) th.join();
+            }
+            if (ok) {
+                df.names.resize(recs.size());
+                for (size_t i = 0; i < recs.size(); ++i) df.names[i] = std::move(recs[i].name);
+                return BTB_OK;
+            }
+            df.release();
+        }
+    }
     FileBytes fb;
     BTB_TRY(load_file(path, fb));
     std::vector<FastaRecord> recs;
@@ -492,7 +551,7 @@ int read_dense(const char *path, int threads, DenseFasta &df) {
     df.n = int64_t(recs.size());
     df.len = walk_record(fb, recs[0], nullptr);
     df.stride = std::max<int64_t>(16, (df.len + 15) / 16 * 16);
-    BTB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&df.rows), size_t(df.n * df.stride)));
+    BTB_TRY(df.alloc(size_t(df.n * df.stride)));
     df.names.resize(recs.size());
     std::vector<int64_t> lens(recs.size(), 0);
     auto work = [&](int64_t lo, int64_t hi) {
@@ -558,6 +617,22 @@ void format_rows_spaced(const void *mat, int elem_bytes, int64_t ld, int64_t n, 
     }
     for (auto &th : pool) th.join();
 }
+// copies the formatted rows from their slots to their final, contiguous places dst + pos[r]
+void gather_rows(char *dst, const char *work, const std::vector<size_t> &off, const std::vector<size_t> &used,
+                 const std::vector<size_t> &pos, int64_t rows, int host_threads) {
+    auto job = [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; ++r) memcpy(dst + pos[size_t(r)], work + off[size_t(r)], used[size_t(r)]);
+    };
+    const int threads = std::max(1, std::min<int>(host_threads, 64));
+    if (threads == 1 || rows < 2 * threads) { job(0, rows); return; }
+    std::vector<std::thread> pool;
+    const int64_t span = (rows + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        int64_t lo = t * span, hi = std::min(rows, lo + span);
+        if (lo < hi) pool.emplace_back(job, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+}
 }  // namespace
 
 extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, int64_t n, int64_t row0,
@@ -568,21 +643,14 @@ extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, 
     const int64_t rows = row1 - row0;
     std::vector<size_t> off(size_t(rows) + 1, 0);
     for (int64_t r = 0; r < rows; ++r) off[size_t(r) + 1] = off[size_t(r)] + csv_slot_bytes(names[row0 + r], n, elem_bytes);
-    std::vector<size_t> used(size_t(rows), 0);
-    // format into generously spaced slots, then compact
-    std::vector<char> tmp;
-    const bool direct = off[size_t(rows)] <= cap;
-    char *work = buf;
-    if (!direct) { tmp.resize(off[size_t(rows)]); work = tmp.data(); }
-    format_rows_spaced(mat, elem_bytes, ld, n, rows, names + row0, sep, host_threads, work, off, used);
-    size_t total = 0;
-    for (int64_t r = 0; r < rows; ++r) total += used[size_t(r)];
-    if (total > cap) return fail(BTB_EINVAL, "btb_format_csv_rows: buffer too small (%zu needed)", total);
+    std::vector<size_t> used(size_t(rows), 0), pos(size_t(rows), 0);
+    // format into generously spaced slots (all threads), then gather the rows into place (all threads)
+    std::vector<char> tmp(off[size_t(rows)]);
+    format_rows_spaced(mat, elem_bytes, ld, n, rows, names + row0, sep, host_threads, tmp.data(), off, used);
     size_t w = 0;
-    for (int64_t r = 0; r < rows; ++r) {
-        memmove(buf + w, work + off[size_t(r)], used[size_t(r)]);
-        w += used[size_t(r)];
-    }
+    for (int64_t r = 0; r < rows; ++r) { pos[size_t(r)] = w; w += used[size_t(r)]; }
+    if (w > cap) return fail(BTB_EINVAL, "btb_format_csv_rows: buffer too small (%zu needed)", w);
+    gather_rows(buf, tmp.data(), off, used, pos, rows, host_threads);
     if (written) *written = w;
     return BTB_OK;
 }
@@ -794,8 +862,11 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     const bool to_stdout = !strcmp(out_path, "-") || !strcmp(out_path, "/dev/stdout");
     std::string tmp_path = to_stdout ? std::string("/dev/stdout") : std::string(out_path) + ".tmp";
     std::thread *writer_ptr = nullptr;
+    char *map = nullptr;               // snps.csv written through a mapping (see below)
+    size_t map_bytes = 0, map_off = 0;
     auto cleanup = [&]() {
         if (writer_ptr && writer_ptr->joinable()) writer_ptr->join();
+        if (map) { munmap(map, map_bytes); map = nullptr; }
         cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
         if (h_stage[0]) cudaFreeHost(h_stage[0]);
         if (h_stage[1]) cudaFreeHost(h_stage[1]);
@@ -837,7 +908,7 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
 
     timer.mark("H2D + encode + distance kernel");
     // ---- serialise: D2H row blocks (double-buffered) -> threads format -> ordered writes
-    fo = fopen(tmp_path.c_str(), "wb");
+    fo = fopen(tmp_path.c_str(), to_stdout ? "wb" : "w+b");      // read-write: the file is written through a shared mapping
     if (!fo) { rc = fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); cleanup(); return rc; }
     setvbuf(fo, nullptr, _IOFBF, 1 << 22);
     std::vector<const char *> name_ptr(static_cast<size_t>(n));
@@ -849,14 +920,48 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         fwrite(head.data(), 1, head.size(), fo);
     }
     fflush(fo);                                          // the matrix rows go straight to the descriptor
+    // Buffered write()s to one file serialise on its inode (and run at ~3 GB/s): a 12 GB snps.csv is
+    // instead written THROUGH A MAPPING -- the file is extended to an upper bound of the text size,
+    // every formatted block is copied into place by all host threads at once (page-cache pages are
+    // populated in parallel), and the file is cut to its real length at the end.
+    if (g_csv_mmap && !to_stdout && !molten && n >= 1024) {
+        size_t bound = size_t(ftell(fo));
+        for (auto &s : df.names) bound += s.size() + 1;
+        bound += size_t(n) * size_t(n) * size_t(eb == 2 ? 6 : 11);
+        map_off = size_t(ftell(fo));
+        if (ftruncate(fileno(fo), off_t(bound)) == 0) {
+            void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, fileno(fo), 0);
+            if (m != MAP_FAILED) { map = static_cast<char *>(m); map_bytes = bound; }
+        }
+        if (!map && ftruncate(fileno(fo), off_t(map_off)) != 0) { rc = fail(BTB_EIO, "cannot size '%s'", tmp_path.c_str()); cleanup(); return rc; }
+    }
     const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / std::max<int64_t>(1, ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[0]), size_t(block_rows * ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[1]), size_t(block_rows * ld * eb)));
     size_t max_name = 0;
     for (auto &s : df.names) max_name = std::max(max_name, s.size());
+    // per block: (1) all host threads count the exact text length of their rows, (2) a prefix sum gives
+    // every row its final place -- in the file mapping, or in a contiguous buffer that one write()
+    // pushes out -- and (3) all threads format their rows directly there: the text is written once.
     std::vector<char> text2[2];
-    text2[0].resize(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 16));
-    text2[1].resize(text2[0].size());
+    if (!molten && !map) {
+        text2[0].resize(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 2));
+        text2[1].resize(text2[0].size());
+    }
+    std::vector<size_t> row_len, row_pos;
+    double t_wait = 0, t_count = 0, t_format = 0, t_join = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    auto for_rows = [&](int64_t rows, const std::function<void(int64_t, int64_t)> &fn) {
+        const int T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), rows)));
+        if (T == 1) { fn(0, rows); return; }
+        std::vector<std::thread> pool;
+        const int64_t span = (rows + T - 1) / T;
+        for (int k = 0; k < T; ++k) {
+            const int64_t lo = k * span, hi = std::min(rows, lo + span);
+            if (lo < hi) pool.emplace_back(fn, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    };
     std::thread writer;
     writer_ptr = &writer;
     std::atomic<bool> write_failed{false};
@@ -875,29 +980,62 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     const int64_t blocks = (n + block_rows - 1) / block_rows;
     L1_CUDA(issue(0));
     for (int64_t b = 0; b < blocks; ++b) {
-        L1_CUDA(cudaEventSynchronize(ev[b & 1]));
+        { const double tw = now(); L1_CUDA(cudaEventSynchronize(ev[b & 1])); t_wait += now() - tw; }
         if (b + 1 < blocks) L1_CUDA(issue(b + 1));
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
         if (!molten) {
-            // format block b with `threads` workers while the writer thread is still pushing block b-1
-            // into the file (one large sequential write per block: buffered writes to one inode
-            // serialise in the kernel, so parallel pwrite does not pay)
-            size_t w = 0;
+            // format block b with `threads` workers while the writer thread still gathers block b-1 into place
             const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
-            std::vector<char> &tb = text2[b & 1];
-            L1_TRY(btb_format_csv_rows(src_rows, eb, ld, n, 0, r1 - r0, name_ptr.data() + r0, sep, threads, tb.data(), tb.size(), &w));
-            if (writer.joinable()) writer.join();
+            const int64_t rows = r1 - r0;
+            double tt = now();
+            row_len.assign(size_t(rows), 0);
+            row_pos.assign(size_t(rows), 0);
+            for_rows(rows, [&](int64_t lo, int64_t hi) {
+                for (int64_t r = lo; r < hi; ++r)
+                    row_len[size_t(r)] = strlen(name_ptr[size_t(r0 + r)]) + row_text_len(src_rows + size_t(r) * size_t(ld) * size_t(eb), eb, n) + 1;
+            });
+            size_t w = 0;
+            for (int64_t r = 0; r < rows; ++r) { row_pos[size_t(r)] = w; w += row_len[size_t(r)]; }
+            t_count += now() - tt; tt = now();
+            if (writer.joinable()) writer.join();        // the write() of block b-1 is done: its buffer parity is not ours
             if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
-            const char *wp = tb.data();
-            writer = std::thread([&write_failed, fd, wp, w]() {
-                const char *p = wp;
-                size_t left = w;
-                while (left) {
-                    ssize_t k = write(fd, p, left);
-                    if (k <= 0) { write_failed = true; return; }
-                    p += k; left -= size_t(k);
+            t_join += now() - tt; tt = now();
+            char *dst = nullptr;
+            if (map) {
+                if (map_off + w > map_bytes) { rc = fail(BTB_EIO, "snps.csv text exceeds its bound"); cleanup(); return rc; }
+                dst = map + map_off;
+                map_off += w;
+            } else {
+                if (w > text2[b & 1].size()) { rc = fail(BTB_EIO, "snps.csv text exceeds its bound"); cleanup(); return rc; }
+                dst = text2[b & 1].data();
+            }
+            std::atomic<bool> bad_len{false};
+            for_rows(rows, [&](int64_t lo, int64_t hi) {
+                for (int64_t r = lo; r < hi; ++r) {
+                    char *q = dst + row_pos[size_t(r)];
+                    const char *nm = name_ptr[size_t(r0 + r)];
+                    const size_t nl = strlen(nm);
+                    memcpy(q, nm, nl);
+                    q += nl;
+                    q += format_row(src_rows + size_t(r) * size_t(ld) * size_t(eb), eb, n, sep, q);
+                    *q++ = '\n';
+                    if (size_t(q - (dst + row_pos[size_t(r)])) != row_len[size_t(r)]) bad_len = true;
                 }
             });
+            if (bad_len) { rc = fail(BTB_EIO, "internal error: a formatted row does not have its predicted length"); cleanup(); return rc; }
+            t_format += now() - tt;
+            if (!map) {
+                const char *wp = dst;
+                writer = std::thread([&write_failed, fd, wp, w]() {
+                    const char *p = wp;
+                    size_t left = w;
+                    while (left) {
+                        ssize_t k = write(fd, p, left);
+                        if (k <= 0) { write_failed = true; return; }
+                        p += k; left -= size_t(k);
+                    }
+                });
+            }
         } else {
             for (int64_t r = r0; r < r1; ++r)
                 for (int64_t i = 0; i < n; ++i) {
@@ -912,7 +1050,14 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
+    if (map) {
+        munmap(map, map_bytes);
+        map = nullptr;
+        if (ftruncate(fileno(fo), off_t(map_off)) != 0) { rc = fail(BTB_EIO, "cannot size '%s'", tmp_path.c_str()); cleanup(); return rc; }
+    }
     timer.mark("D2H + format + write snps.csv");
+    if (timer.on) fprintf(stderr, "[btb timing]     (wait for D2H %.3f s, count row lengths %.3f s, wait for write() %.3f s, format in place %.3f s)\n",
+                          t_wait, t_count, t_join, t_format);
     if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
     fo = nullptr;
     // unlink first: replacing an existing file by rename makes ext4 flush the new file's data synchronously

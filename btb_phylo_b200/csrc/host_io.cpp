@@ -379,7 +379,7 @@ const DigitLut kLut;
 inline char *put_u32(char *p, uint32_t v) {
     if (v < 10000) {
         const char *s = kLut.d[v];
-        const int skip = v < 10 ? 3 : v < 100 ? 2 : v < 1000 ? 1 : 0;
+        const int skip = int(v < 10) + int(v < 100) + int(v < 1000);     // branch-free: digit counts are data dependent
         memcpy(p, s + skip, 4);                      // writes up to 4, advances by the real width
         return p + (4 - skip);
     }
@@ -397,15 +397,48 @@ inline char *put_u32(char *p, uint32_t v) {
 }
 }  // namespace
 
-size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst) {
-    char *p = dst;
+// bytes format_row will produce: one separator per cell plus the decimal digits
+size_t row_text_len(const void *row, int elem_bytes, int64_t n) {
+    size_t digits = 0;
     if (elem_bytes == 2) {
         const uint16_t *r = static_cast<const uint16_t *>(row);
-        for (int64_t i = 0; i < n; ++i) { *p++ = sep; p = put_u32(p, r[i]); }
+        for (int64_t i = 0; i < n; ++i) {
+            const uint32_t v = r[i];
+            digits += 1u + (v >= 10) + (v >= 100) + (v >= 1000) + (v >= 10000);
+        }
     } else {
         const uint32_t *r = static_cast<const uint32_t *>(row);
-        for (int64_t i = 0; i < n; ++i) { *p++ = sep; p = put_u32(p, r[i]); }
+        for (int64_t i = 0; i < n; ++i) {
+            const uint32_t v = r[i];
+            digits += 1u + (v >= 10) + (v >= 100) + (v >= 1000) + (v >= 10000) + (v >= 100000) + (v >= 1000000) +
+                      (v >= 10000000) + (v >= 100000000) + (v >= 1000000000);
+        }
     }
+    return size_t(n) + digits;
+}
+
+namespace {
+// exact-width variant for the last cells of a row: never writes past the value's own digits
+inline char *put_u32_exact(char *p, uint32_t v) {
+    char tmp[16];
+    char *e = put_u32(tmp, v);
+    memcpy(p, tmp, size_t(e - tmp));
+    return p + (e - tmp);
+}
+template <typename T>
+inline char *format_cells(const T *r, int64_t n, char sep, char *p) {
+    // put_u32 may write up to 3 bytes beyond the digits it keeps (overwritten by the next cell): the
+    // last two cells use the exact variant so a row never touches bytes behind its own end
+    const int64_t bulk = n > 2 ? n - 2 : 0;
+    for (int64_t i = 0; i < bulk; ++i) { *p++ = sep; p = put_u32(p, r[i]); }
+    for (int64_t i = bulk; i < n; ++i) { *p++ = sep; p = put_u32_exact(p, r[i]); }
+    return p;
+}
+}  // namespace
+
+size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst) {
+    char *p = elem_bytes == 2 ? format_cells(static_cast<const uint16_t *>(row), n, sep, dst)
+                              : format_cells(static_cast<const uint32_t *>(row), n, sep, dst);
     return size_t(p - dst);
 }
 

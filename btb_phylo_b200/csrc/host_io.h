@@ -87,5 +87,7 @@ int relabel_csv(const FileBytes &fb, char sep, const std::vector<std::string> &l
 
 // Fast decimal formatting of one matrix row segment; returns bytes written.
 size_t format_row(const void *row, int elem_bytes, int64_t n, char sep, char *dst);
+// Exactly the number of bytes format_row writes for this row (no formatting done).
+size_t row_text_len(const void *row, int elem_bytes, int64_t n);
 
 }  // namespace btb
