@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -47,6 +48,8 @@ struct Stream {
     ~Stream() { if (s) cudaStreamDestroy(s); }
     int create() { BTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return BTB_OK; }
 };
+
+double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void parallel_for(int64_t n, int threads, const std::function<void(int64_t, int64_t)> &fn) {
     threads = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), n)));
@@ -156,6 +159,7 @@ struct ExtractCtx {
     size_t chunk_cap = 0;
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_lw, h_el;
+    double t_wait = 0, t_fill = 0, t_enqueue = 0;      // BTB_TIMING: where run_chunk spends its time
 
     ~ExtractCtx() {
         for (int k = 0; k < 2; ++k)
@@ -192,7 +196,10 @@ struct ExtractCtx {
 
     // stage records [i0, i1) (global indices) into buffer b; `force_walk` re-stages with the exact walk
     int run_chunk(const ByteSource &src, const std::vector<FastaRecord> &recs, int64_t G, int b, int64_t i0, int64_t i1, bool force_walk) {
+        const double tw0 = wall_s();
         if (used[b]) BTB_CUDA(cudaEventSynchronize(done[b]));
+        const double tw1 = wall_s();
+        t_wait += tw1 - tw0;
         uint8_t *dst = h_text[b].as<uint8_t>();
         size_t pos = 0;
         std::vector<size_t> at(static_cast<size_t>(i1 - i0));
@@ -239,6 +246,8 @@ struct ExtractCtx {
             });
             if (bad != BTB_OK) return fail(bad, "%s", bad_text.c_str());
         }
+        const double tw2 = wall_s();
+        t_fill += tw2 - tw1;
         const int64_t l0 = i0 - s0, cnt = i1 - i0;
         BTB_CUDA(cudaMemcpyAsync(d_text[b].p, dst, total + 16, cudaMemcpyHostToDevice, st.s));
         BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + l0, h_off.data() + l0, size_t(cnt) * 8, cudaMemcpyHostToDevice, st.s));
@@ -248,6 +257,7 @@ struct ExtractCtx {
                                 d_el.as<int32_t>() + l0, cnt, l0, nloc, G, planes.as<uint32_t>(), flags.as<int32_t>() + l0, st.s));
         BTB_CUDA(cudaEventRecord(done[b], st.s));
         used[b] = true;
+        t_enqueue += wall_s() - tw2;
         return BTB_OK;
     }
 
@@ -285,6 +295,9 @@ struct ExtractCtx {
             b ^= 1;
         }
         BTB_CUDA(cudaStreamSynchronize(st.s));
+        if (getenv("BTB_TIMING"))
+            fprintf(stderr, "[btb timing]     (device %d staging: wait for a free buffer %.3f s, fill pinned chunks %.3f s, enqueue H2D + k1 %.3f s)\n",
+                    dev, t_wait, t_fill, t_enqueue);
         return BTB_OK;
     }
 };

@@ -247,6 +247,20 @@ def test_uint32_output_and_long_rows(capi, oracle):
         assert (got == oracle.snp_dists_rows(seqs, threads=8)).all()
 
 
+def test_uint32_output_through_the_full_tile_kernel(capi, oracle):
+    """Rows of 66,000 sites need uint32 cells; 6,400 sequences engage the single-CTA full-tile kernel
+    (the CTA-pair kernel writes uint16 only).  Checked against the POPC engine everywhere and against
+    the oracle on a few rows."""
+    n, L = 6400, 66000
+    seqs = synth.snp_alignment(n, L, seed=23)
+    plan, a = gpu_matrix(capi, seqs, 1, 1)
+    assert plan.out_dtype == torch.uint32 and plan.sigma == capi.SIGMA_DENSE4
+    _, b = gpu_matrix(capi, seqs, 0, 0)
+    assert (a == b).all() and (a == a.T).all() and (np.diag(a) == 0).all()
+    for r in (0, 3333, n - 1):
+        assert (a[r] == oracle.snp_dists_rows(seqs, threads=8, row0=r, row1=r + 1)[0]).all()
+
+
 def test_level2_host_call(capi, oracle):
     from btb_phylo_b200 import device
     seqs = synth.snp_alignment(777, 831, seed=5, heavy_n=0.2, lower=0.01)
