@@ -294,6 +294,11 @@ def gpu_arm(args):
                 "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
                 "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-element-per-site "
                         "tetrahedron code, so the tensor pipe executes 3/4 of that: achieved_executed is the hardware rate",
+                "why_frac_exceeds_1": "two independent reasons: (1) the kernel executes only executed_over_algorithmic of the ops `achieved` counts; "
+                                      "(2) `peak` scales the MEASURED sustained bf16 GEMM rate (dense random data, power-capped near 1.3 GHz) to the "
+                                      "operand type, while this kernel's sparse 0/1 operands run at 1.85-1.97 GHz under the same 1 kW cap. The honest "
+                                      "utilisation figures are frac_of_nominal_executed and ncu's tensor-pipe-active share "
+                                      "(profiles/r01_dist_umma_fp4_pair_ncu_summary.txt: 89.8 %).",
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(n, L, world),
                 "peak_source": peak_src, "ops": "int8 multiply-add = 2 ops; 2*sigma*L*N(N-1)/2 with sigma=4 (padding, diagonal tiles = overhead)",
                 "kernel_ms": kernel_ms, "peak_nominal_dense": nominal, "frac_of_nominal": achieved / nominal,
