@@ -319,3 +319,28 @@ def test_consensus_file_lists_equal_the_concatenated_multi_fasta(ph, capi, oracl
     with pytest.raises(Exception) as e:
         ph.snp_sites(str(sf), [paths[0], str(tmp_path / "missing.fas")])
     assert "Could not open filename" in str(e.value)
+
+
+def test_path_shims_serve_the_reference_command_lines(tmp_path):
+    """with tools/ first on PATH the exact command lines the reference builds
+    (btbphylo/phylogeny.py:133 and :149, run through a shell like utils.run does) produce the golden
+    files, and failures surface as a non-zero exit status."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PATH=os.path.join(root, "tools") + os.pathsep + os.path.dirname(sys.executable) + os.pathsep + os.environ["PATH"])
+    mf, sf, sc = tmp_path / "multi_fasta.fas", tmp_path / "snps.fas", tmp_path / "snps.csv"
+    mf.write_bytes(golden("c1_multi_fasta.fas"))
+    r = subprocess.run("snp-sites %s -c -o %s" % (mf, sf), shell=True, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert sf.read_bytes() == golden("c1_snps.fas")
+    r = subprocess.run("snp-dists -c -j 4 %s > %s" % (sf, sc), shell=True, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert sc.read_bytes() == golden("c1_snps.csv")
+    assert b"This is snp-dists 0.8.2" in r.stderr and b"Read 4 sequences of length 831" in r.stderr
+    mf.write_bytes(b">a\nACGT\n>b\nACGT\n")                     # no SNPs: snp-sites exits 1
+    r = subprocess.run("snp-sites %s -c -o %s" % (mf, tmp_path / "none.fas"), shell=True, env=env, capture_output=True)
+    assert r.returncode == 1 and b"No SNPs" in r.stderr and not (tmp_path / "none.fas").exists()
+    mf.write_bytes(b">a\nACGT\n>b\nACG\n")                      # unequal lengths: snp-dists exits 1
+    r = subprocess.run("snp-dists -c -j 1 %s > %s" % (mf, sc), shell=True, env=env, capture_output=True)
+    assert r.returncode == 1 and b"has length 3 but expected 4" in r.stderr
