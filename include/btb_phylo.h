@@ -43,11 +43,11 @@ extern "C" {
 /* distance engines: both are exact integer kernels for sm_100a */
 #define BTB_ENGINE_AUTO (-1)
 #define BTB_ENGINE_POPC   0   /* warp-tiled XOR/AND/POPC over bit-planes */
-#define BTB_ENGINE_UMMA   1   /* tcgen05 kind::i8 GEMM on one-hot int8 tiles, int32 accumulators in TMEM */
+#define BTB_ENGINE_UMMA   1   /* tcgen05 GEMM: kind::mxf4 on 0/1 nibble codes (kind::i8 for very long rows), accumulators in TMEM */
 
 /* `sigma` (number of symbol planes) takes this value when the alignment is "dense": at most four
  * distinct symbols and no byte that is ignored anywhere (always true for what snp-sites -c writes).
- * The engines then use their compact encodings: UMMA a single 3-byte-per-site operand whose
+ * The engines then use their compact encodings: UMMA a single operand of 3 elements per site whose
  * symbols are the 0/1 vertices of a regular tetrahedron (d = c_i + c_j - dot), POPC two code planes
  * without a validity plane. */
 #define BTB_SIGMA_DENSE4 (-4)
@@ -58,11 +58,24 @@ extern "C" {
 int         btb_last_error(char *buf, size_t cap);       /* copies the message, returns its length */
 const char *btb_version(void);
 int         btb_device_count(int *count);                 /* number of usable sm_100 devices */
-/* tuning knobs for tests/benchmarks: "umma_cta_group" = 1 | 2 (single CTA 128x256 UMMA | CTA pair 256x256);
- * "umma_dense_simplex" = 0 | 1 | 2 (dense alignments: one-hot | 3-byte +-1 simplex | 3-byte 0/1 tetrahedron, default 2);
- * "umma_lockstep" = 0 | 1 (grid-wide re-alignment of the TMA producers at tile boundaries);
- * "umma_cg2_variant" = 0..3 (CTA-pair kernel: bit 0 two K atoms per stage, bit 1 relayed stage release).
- * The environment variable BTB_OPTIONS="key=value,..." sets them for the Python binding. */
+/* Tuning knobs for tests, benchmarks and profilers (defaults in brackets).  Results never depend on them.
+ *   distance kernels (tcgen05):
+ *     "umma_fp4" [1]           kind::mxf4 kernels on packed e2m1 nibbles (0: the kind::i8 kernels)
+ *     "umma_fp4_general" [1]   validity + one-hot nibble planes for alphabets with ignored bytes / -a (0: int8 A x B)
+ *     "umma_fp4_pair" [1]      cta_group::2 CTA-pair kernel on 512 x 240 units (0: single-CTA 256 x 240 units)
+ *     "umma_major_zero" [1]    per site, the most frequent symbol takes the all-zero vertex of the dense code
+ *     "umma_tile_mode" [1]     full-tile kernels when a launch has >= 2 units per SM (0: half-tile units only)
+ *     "umma_dense_simplex" [2] dense int8 code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron
+ *     "umma_lockstep" [1]      0 off, k >= 1: TMA producers of all CTAs start a unit at most k-1 rounds apart
+ *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (for ncu)
+ *     "umma_prefetch" [0], "umma_tile_bk" [128], "umma_cta_group" [1], "umma_cg2_variant" [0]: measured alternatives
+ *       (L2 prefetch distance, 64-byte K blocks with six stages, int8 CTA pairs) kept for the record, see DESIGN.md
+ *   extraction: "pack_wpt" [4] plane words per thread of k1; "ingest_predict" [1] predicted FASTA framing
+ *   level 1/2:  "csv_mmap" [0] write snps.csv through a file mapping; "dense_pageable" [1] large snps.fas into
+ *               pageable host memory; "host_stream" [0] + "host_stream_rows" [64] streamed level-2 call
+ * btb_query also answers "ingest_last_predicted", "host_stream_last", "umma_max_active_clusters_cg1|2" and
+ * "probe_cg<1|2>_e<k>" (MMA issue probe, cycles x 100 per stage).
+ * The environment variable BTB_OPTIONS="key=value,..." sets options for the Python binding. */
 int         btb_set_option(const char *key, int value);
 /* introspection: "umma_cta_group", "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
 int         btb_query(const char *key, int64_t *value);
