@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,9 +84,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_lo=None, t_hi=None):
+        """Summary of the samples taken in [t_lo, t_hi] (the timed region).  A region shorter than the
+        sampling period may hold none: then the samples since start() (warm-up + timed steps, the same
+        work) are used and the summary says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,7 +100,11 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = "timed region"
+        rows = [r for t, r in self.rows if (t_lo is None or t >= t_lo) and (t_hi is None or t <= t_hi)]
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than the sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except (ValueError, IndexError):
@@ -106,7 +113,7 @@ class ClockSampler:
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -157,6 +164,31 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers
+    of the end-to-end leg are allocated next to its PCIe root (first-touch policy).  Returns a short
+    description for the JSON line; does nothing when the topology cannot be read or the container's
+    cpuset has no CPU on that node."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "gpu %s: no NUMA node reported" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "gpu %s on node %d: none of this process's %d cpus is on that node" % (bdf, node, len(os.sched_getaffinity(0)))
+        os.sched_setaffinity(0, allowed)
+        return "gpu %s on node %d: bound to %d of its cpus" % (bdf, node, len(allowed))
+    except Exception as e:                                           # noqa: BLE001 -- best effort, never fatal
+        return "unavailable (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     import numpy as np
@@ -170,6 +202,8 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _capi.lib()
@@ -194,13 +228,17 @@ def gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    step()                                                          # (lists, lazy allocations) before the sampler has anything to see
+    sync_all()
+    time.sleep(0.15)                                                # nvidia-smi needs ~0.1 s to deliver its first sample
     for _ in range(args.warmup):
         step()
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     kern_ms = []
+    t_timed0 = time.perf_counter()
     ev[0].record()
     for s in range(args.steps):
         plan.encode()
@@ -208,7 +246,7 @@ def gpu_arm(args):
         plan.compute_rows(out, row_lo, row_hi)
         ev[2 * s + 2].record()
     sync_all()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_timed0, time.perf_counter())
     total_ms = ev[0].elapsed_time(ev[2 * args.steps])
     kern_ms = [ev[2 * s + 1].elapsed_time(ev[2 * s + 2]) for s in range(args.steps)]
     t = torch.tensor([total_ms, statistics.mean(kern_ms)], dtype=torch.float64, device=device)
@@ -248,7 +286,8 @@ def gpu_arm(args):
     d2h = n * n * elem if world == 1 else ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * elem
     e2e = {"value": unique_pairs(n) / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(n * L),
            "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_s, "steps": e2e_steps,
-           "call": "btb_dist_matrix_host (C-ABI level 2; per-rank bytes)"}
+           "call": "btb_dist_matrix_host (C-ABI level 2; per-rank bytes)", "host_numa": numa,
+           "pcie_GBps": (n * L + d2h) / e2e_s / 1e9}
 
     if rank != 0:
         if world > 1:
@@ -306,6 +345,7 @@ def gpu_arm(args):
                 "cublas_int8_8192_measured": int8_lib}
 
     # ---- CPU baseline on this box's host cores (bounded sample), also the parity spot-check -----
+    os.sched_setaffinity(0, all_cpus)                                # the CPU arm gets every core again
     threads = os.cpu_count() or 1
     h_np = h_seqs.numpy()[:, :L]
     rows, dt, cpu_rows = cpu_rows_per_second(h_np, threads, 12.0)
