@@ -490,9 +490,17 @@ extern "C" int btb_snp_sites_files(const char *const *in_fastas, int64_t n_files
     timer.mark("map + index records");
     if (recs.empty()) return no_snps();
     // Records the GPU cannot address with (line width, terminator length) go through the exact walk.
+    // A record's layout (and with it its length) is only inferred from its first line and its byte count:
+    // the first record, which sets the expected length, is always walked, and so is every record whose
+    // inferred length disagrees with it -- a blank line inside a record must not read as "unequal length".
     auto needs_walk = [](const FastaRecord &r) { return !r.regular || (r.line_w > 0 && r.line_w < 32); };
+    {
+        const int64_t exact0 = walk_record(fb, recs[0], nullptr);
+        if (exact0 != recs[0].seq_len) recs[0].regular = false;
+        recs[0].seq_len = exact0;
+    }
     for (auto &r : recs)
-        if (needs_walk(r)) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
+        if (needs_walk(r) || r.seq_len != recs[0].seq_len) { r.seq_len = walk_record(fb, r, nullptr); r.regular = false; }
     ByteSource src;
     src.fb = &fb;
     return extract_pipeline(src, recs, shown, out_fasta, pure_mode, n_gpus, threads, timer, n_samples, genome_len, n_snps);

@@ -1,0 +1,84 @@
+"""GPU (-m gpu): randomised parity of the two file-level entry points against the CPU oracle on small
+FASTA-ish inputs with the framing oddities the shared parser defines: mixed line widths (below and above
+the GPU's 32-base minimum), LF / CRLF, blank lines, header comments, lower case, N / - / IUPAC, a missing
+final newline, lines that start with '>' or '@' inside a sequence, unequal lengths.  Success / failure
+must agree, and on success the bytes."""
+import random
+
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def random_fasta(rng, equal=True, markers=False):
+    n = rng.randint(1, 7)
+    G = rng.randint(1, 260)
+    alphabet = "ACGT" * 6 + "acgt" + "N-" + ("RYKM?" if rng.random() < 0.3 else "")
+    ref = [rng.choice("ACGT") for _ in range(G)]
+    parts = []
+    for i in range(n):
+        g = G if equal or rng.random() < 0.7 else max(0, G + rng.randint(-3, 3))
+        seq = [ref[k] if k < G and rng.random() < 0.85 else rng.choice(alphabet) for k in range(g)]
+        seq = "".join(seq)
+        eol = "\r\n" if rng.random() < 0.25 else "\n"
+        w = rng.choice([0, 0, rng.randint(1, 31), rng.randint(32, 90), 60, 70])
+        head = ">s%d" % i + (" some comment %d" % i if rng.random() < 0.3 else "") + ("\tx" if rng.random() < 0.1 else "")
+        lines = [seq] if not w else [seq[k:k + w] for k in range(0, len(seq), w)] or [""]
+        body = []
+        for li, line in enumerate(lines):
+            if markers and li > 0 and rng.random() < 0.15:
+                line = rng.choice(">@") + line[1:] if line else line
+            body.append(line)
+            if rng.random() < 0.05:
+                body.append("")                              # a blank line inside the record
+        text = head + eol + eol.join(body) + eol
+        parts.append(text)
+    data = "".join(parts)
+    if rng.random() < 0.2:
+        data = data.rstrip("\r\n")                           # no final newline
+    if rng.random() < 0.1:
+        data = "junk line\n" + data
+    return data.encode()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_snp_sites_fuzz(capi, oracle, tmp_path, seed):
+    from btb_phylo_b200 import phylogeny as ph
+    rng = random.Random(1000 + seed)
+    mf, sf, of = tmp_path / "m.fa", tmp_path / "s.fas", tmp_path / "o.fas"
+    for case in range(40):
+        data = random_fasta(rng, equal=rng.random() < 0.85, markers=rng.random() < 0.3)
+        mf.write_bytes(data)
+        for f in (sf, of):
+            if f.exists():
+                f.unlink()
+        r = oracle.run_snp_sites(str(mf), str(of))
+        try:
+            ph.snp_sites(str(sf), str(mf), threads=2)
+            ok = True
+        except Exception:
+            ok = False
+        assert ok == (r.returncode == 0), (seed, case, data, r.stderr)
+        if ok:
+            assert sf.read_bytes() == of.read_bytes(), (seed, case, data)
+        else:
+            assert not sf.exists(), (seed, case)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_snp_dists_fuzz(capi, oracle, tmp_path, seed):
+    rng = random.Random(2000 + seed)
+    lib = capi.lib()
+    mf, sc, oc = tmp_path / "m.fa", tmp_path / "s.csv", tmp_path / "o.csv"
+    for case in range(30):
+        data = random_fasta(rng, equal=rng.random() < 0.9, markers=rng.random() < 0.2)
+        mf.write_bytes(data)
+        flags = [f for f in ("-a", "-k") if rng.random() < 0.4]
+        sep_flag = rng.random() < 0.5
+        r = oracle.run_snp_dists(str(mf), str(oc), threads=2, flags=tuple((["-c"] if sep_flag else []) + flags))
+        for engine in (-1, 0, 1):
+            rc = lib.btb_snp_dists(str(mf).encode(), str(sc).encode(), int("-a" in flags), int("-k" in flags), 0,
+                                   b"," if sep_flag else b"\t", 1, 1, 1, 2, engine, None, None)
+            assert (rc == 0) == (r.returncode == 0), (seed, case, engine, data, capi.last_error(), r.stderr)
+            if rc == 0:
+                assert sc.read_bytes() == oc.read_bytes(), (seed, case, engine, flags, data)
