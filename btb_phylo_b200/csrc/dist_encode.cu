@@ -589,7 +589,7 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
         occurs[int('.')] = false;
         int code_of[256];
         for (int b = 0; b < 256; ++b) code_of[b] = occurs[b] ? s++ : -1;
-        if (s > 254) return fail(BTB_EINVAL, "alphabet too large");
+        if (s > 255) return fail(BTB_EINVAL, "alphabet too large");      // codes 0..254, 0xff = ignored: every byte value but '.' fits
         for (int b = 0; b < 256; ++b) {
             int u = up(b);
             if (u != '.' && code_of[u] >= 0) table[b] = uint8_t(code_of[u]);

@@ -82,3 +82,68 @@ def test_snp_dists_fuzz(capi, oracle, tmp_path, seed):
             assert (rc == 0) == (r.returncode == 0), (seed, case, engine, data, capi.last_error(), r.stderr)
             if rc == 0:
                 assert sc.read_bytes() == oc.read_bytes(), (seed, case, engine, flags, data)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_consensus_lists_cut_anywhere_equal_the_concatenation(capi, oracle, tmp_path, seed):
+    """A multi-FASTA cut into files at arbitrary byte positions (even inside a line or a header) and
+    passed as a list gives what the concatenated file gives."""
+    from btb_phylo_b200 import phylogeny as ph
+    rng = random.Random(3000 + seed)
+    mf, sf, of = tmp_path / "m.fa", tmp_path / "s.fas", tmp_path / "o.fas"
+    for case in range(25):
+        data = random_fasta(rng, equal=rng.random() < 0.9, markers=rng.random() < 0.2)
+        cuts = sorted(rng.sample(range(len(data) + 1), k=min(len(data) + 1, rng.randint(1, 5)))) if rng.random() < 0.6 else \
+            [i for i in range(len(data)) if data[i:i + 1] == b">" and i > 0]          # ... or exactly at the records
+        pieces, last = [], 0
+        for c in cuts + [len(data)]:
+            pieces.append(data[last:c])
+            last = c
+        paths = []
+        for k, piece in enumerate(pieces):
+            f = tmp_path / ("p%d_%d.fa" % (case, k))
+            f.write_bytes(piece)
+            paths.append(str(f))
+        mf.write_bytes(data)
+        for f in (sf, of):
+            if f.exists():
+                f.unlink()
+        r = oracle.run_snp_sites(str(mf), str(of))
+        try:
+            ph.snp_sites(str(sf), paths, threads=2)
+            ok = True
+        except Exception:
+            ok = False
+        assert ok == (r.returncode == 0), (seed, case, data, cuts)
+        if ok:
+            assert sf.read_bytes() == of.read_bytes(), (seed, case, data, cuts)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_distance_engines_fuzz_on_arbitrary_bytes(capi, oracle, seed):
+    """Level 2 on raw byte matrices: any byte value may occur (control bytes, '.', high bytes), sizes
+    straddle the tile and K-block boundaries, all engines, all modes."""
+    import numpy as np
+    from btb_phylo_b200 import device
+    rng = np.random.default_rng(4000 + seed)
+    for case in range(12):
+        n = int(rng.choice([1, 2, 3, 31, 127, 128, 129, 255, 256, 257, 300, 511, 513, 700]))
+        L = int(rng.choice([1, 2, 15, 16, 17, 31, 63, 64, 65, 255, 256, 257, 300, 1000]))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:                                         # dense DNA
+            pool = np.frombuffer(b"ACGT", dtype=np.uint8)
+        elif kind == 1:                                       # DNA with gaps, IUPAC, lower case, dots
+            pool = np.frombuffer(b"ACGTACGTACGTacgtNN--.RYKMSWnx?", dtype=np.uint8)
+        elif kind == 2:                                       # a few arbitrary byte values
+            pool = rng.integers(0, 256, size=int(rng.integers(2, 9))).astype(np.uint8)
+        else:                                                 # anything
+            pool = np.arange(256, dtype=np.uint8)
+        seqs = pool[rng.integers(0, len(pool), size=(n, L))]
+        base = seqs[rng.integers(0, n)]                       # clade-like: most rows close to one of them
+        keep = rng.random((n, L)) < 0.8
+        seqs = np.where(keep, base[None, :], seqs).astype(np.uint8)
+        for allchars, keepcase in ((False, False), (True, False), (False, True), (True, True)):
+            want = oracle.snp_dists_rows(seqs, allchars=allchars, keepcase=keepcase, threads=4)
+            for engine in (capi.ENGINE_AUTO, capi.ENGINE_POPC, capi.ENGINE_UMMA):
+                got = device.distance_matrix_host(seqs, allchars=allchars, keepcase=keepcase, engine=engine)
+                assert (got == want).all(), (seed, case, n, L, kind, allchars, keepcase, engine)
