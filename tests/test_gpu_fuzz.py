@@ -147,3 +147,65 @@ def test_distance_engines_fuzz_on_arbitrary_bytes(capi, oracle, seed):
             for engine in (capi.ENGINE_AUTO, capi.ENGINE_POPC, capi.ENGINE_UMMA):
                 got = device.distance_matrix_host(seqs, allchars=allchars, keepcase=keepcase, engine=engine)
                 assert (got == want).all(), (seed, case, n, L, kind, allchars, keepcase, engine)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_snp_sites_fuzz_at_kernel_scale(capi, oracle, tmp_path, seed):
+    """Genomes long enough for several CTAs per sample and many plane words, laid out like consensus
+    files (one wrap width per file, so the predicted framing is tried first), with anomalies injected
+    into a few records: a blank line, a line one base short followed by one a base long, a CR in the
+    middle of a line, a tab, a line starting with '>', lower case, N runs, a record without SNPs."""
+    import numpy as np
+    from btb_phylo_b200 import phylogeny as ph
+    rng = random.Random(5000 + seed)
+    nrng = np.random.default_rng(5000 + seed)
+    mf, sf, of = tmp_path / "m.fa", tmp_path / "s.fas", tmp_path / "o.fas"
+    for case in range(10):
+        n = rng.randint(3, 14)
+        G = rng.choice([32768, 32769, 40000, 65536, 100003, 131071])
+        w = rng.choice([60, 60, 70, 80, 33, 32, 0, 200])
+        eol = b"\r\n" if rng.random() < 0.2 else b"\n"
+        ref = nrng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), G)
+        rows = []
+        for i in range(n):
+            r = ref.copy()
+            k = rng.randint(0, 400)
+            r[nrng.integers(0, G, k)] = nrng.choice(np.frombuffer(b"ACGTacgtN-", dtype=np.uint8), k)
+            if rng.random() < 0.3:
+                a = rng.randint(0, G - 500)
+                r[a:a + rng.randint(1, 500)] = ord("N")
+            rows.append(r.tobytes())
+        recs = []
+        for i, row in enumerate(rows):
+            lines = [row] if not w else [row[k:k + w] for k in range(0, G, w)]
+            anomaly = rng.random()
+            if w and len(lines) > 4 and anomaly < 0.30:
+                j = rng.randint(1, len(lines) - 3)
+                kind = rng.randint(0, 4)
+                if kind == 0:
+                    lines.insert(j, b"")
+                elif kind == 1:
+                    lines[j], lines[j + 1] = lines[j][:-1], lines[j][-1:] + lines[j + 1]
+                elif kind == 2:
+                    lines[j] = lines[j][:5] + b"\r" + lines[j][6:]
+                elif kind == 3:
+                    lines[j] = lines[j][:9] + b"\t" + lines[j][10:]
+                else:
+                    lines[j] = b">" + lines[j][1:]
+            recs.append(b">smp%d" % i + (b" len=%d" % G if i % 3 == 0 else b"") + eol + eol.join(lines) + eol)
+        data = b"".join(recs)
+        if rng.random() < 0.25:
+            data = data[: -len(eol)]
+        mf.write_bytes(data)
+        for f in (sf, of):
+            if f.exists():
+                f.unlink()
+        r = oracle.run_snp_sites(str(mf), str(of))
+        try:
+            ph.snp_sites(str(sf), str(mf), threads=4)
+            ok = True
+        except Exception:
+            ok = False
+        assert ok == (r.returncode == 0), (seed, case, n, G, w, eol, r.stderr[-300:])
+        if ok:
+            assert sf.read_bytes() == of.read_bytes(), (seed, case, n, G, w, eol)
