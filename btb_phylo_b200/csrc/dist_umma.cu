@@ -1594,7 +1594,7 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
     BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int2 *d_units = nullptr;
     int64_t n_units = 0;
-    if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && dev < 16) {
+    if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && (row_hi % 2 == 0 || row_hi == tiles_per_dim(n)) && dev < 16) {
         // CTA pairs: 512-row units, B split between the two SMs of a pair
         BTB_TRY(get_rows_list(n, row_lo, row_hi, 2, &d_units, &n_units));
         if (n_units >= 2 * int64_t(sms / 2)) {
@@ -1812,6 +1812,13 @@ int distance_rows_umma(const void *d_operands, int64_t n, int64_t len, int sigma
     const int64_t kb = umma_k_bytes(len, sigma);
     const uint8_t *A = static_cast<const uint8_t *>(d_operands);
     if (umma_use_fp4(sigma, len) && g_umma_tile_mode == 1) {
+        // the CTA-pair kernel works on pairs of block rows: an odd end (other than the matrix end) is
+        // split off, so that no row outside the requested range is ever written
+        if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && row_hi % 2 == 1 && row_hi < tiles_per_dim(n) &&
+            row_hi - 1 > row_lo) {
+            BTB_TRY(distance_rows_umma(d_operands, n, len, sigma, row_lo, row_hi - 1, d_out, out_elem_bytes, out_ld, mirror, stream));
+            return distance_rows_umma(d_operands, n, len, sigma, row_hi - 1, row_hi, d_out, out_elem_bytes, out_ld, mirror, stream);
+        }
         int launched = 0;
         const int64_t neg_from = umma_fp4_general(sigma, len) ? umma_fp4_plane_bytes(len) / kBlockK : -1;
         BTB_TRY(launch_fp4_rows(A, n, kb, neg_from, row_lo, row_hi, d_out, out_elem_bytes, out_ld, mirror, stream, &launched));

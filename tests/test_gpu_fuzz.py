@@ -209,3 +209,51 @@ def test_snp_sites_fuzz_at_kernel_scale(capi, oracle, tmp_path, seed):
         assert ok == (r.returncode == 0), (seed, case, n, G, w, eol, r.stderr[-300:])
         if ok:
             assert sf.read_bytes() == of.read_bytes(), (seed, case, n, G, w, eol)
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_block_row_ranges_fuzz(capi, oracle, dense):
+    """btb_distance_rows on random block-row ranges of a 7,000-sequence alignment: even and odd first
+    rows, ranges small enough for the half-tile kernel and large enough for the CTA-pair and the
+    single-CTA full-tile kernels, with and without mirroring.  Cells of the range equal the oracle,
+    every other cell of the matrix keeps its sentinel."""
+    import numpy as np
+    import torch
+    from btb_phylo_b200 import device, synth
+    from tests.test_gpu_distance import to_device
+    n, L = 7000, 300
+    seqs = synth.snp_alignment(n, L, seed=61, heavy_n=0.0 if dense else 0.08)
+    want = torch.from_numpy(oracle.snp_dists_rows(seqs, threads=8).astype(np.int32)).cuda()
+    plan = device.DistancePlan(to_device(seqs), length=L, engine=capi.ENGINE_UMMA)
+    assert (plan.sigma == capi.SIGMA_DENSE4) == dense
+    plan.encode()
+    T = device.block_rows(n)
+    rng = random.Random(62)
+    ranges = [(0, T), (1, T), (0, 1), (T - 1, T), (2, 3), (3, 4)]
+    while len(ranges) < 22:
+        lo = rng.randint(0, T - 1)
+        ranges.append((lo, rng.randint(lo, T)))
+    rows_idx = torch.arange(n, device="cuda")
+    upper = rows_idx[None, :] >= rows_idx[:, None]
+    for lo, hi in ranges:
+        for mirror in (True, False):
+            out = torch.full((n, (n + 7) // 8 * 8), 0xEEEE, dtype=torch.uint16, device="cuda")
+            plan.compute_rows(out, lo, hi, mirror=mirror)
+            torch.cuda.synchronize()
+            got = out[:, :n].to(torch.int32)
+            r0, r1 = min(n, lo * 256), min(n, hi * 256)
+            in_rows = (rows_idx >= r0) & (rows_idx < r1)
+            must = in_rows[:, None] & upper                                  # (r, c >= r), r in the range
+            assert bool((got[must] == want[must]).all()), (dense, lo, hi, mirror)
+            if mirror:
+                must_t = must.T
+                assert bool((got[must_t] == want[must_t]).all()), (dense, lo, hi, mirror)
+            # lower halves of diagonal tiles / mirrored cells may or may not be written; everything else must not be
+            same_block = (rows_idx[:, None] // 256) == (rows_idx[None, :] // 256)
+            may = must | must.T | (in_rows[:, None] & same_block) | (in_rows[None, :] & same_block)
+            if not mirror:
+                may = must | (in_rows[:, None] & same_block)
+            untouched = ~may
+            assert bool((got[untouched] == 0xEEEE).all()), (dense, lo, hi, mirror)
+            stray = may & ~must & ~(must.T if mirror else torch.zeros_like(must))
+            assert bool(((got[stray] == want[stray]) | (got[stray] == 0xEEEE)).all()), (dense, lo, hi, mirror)
