@@ -344,3 +344,27 @@ def test_path_shims_serve_the_reference_command_lines(tmp_path):
     mf.write_bytes(b">a\nACGT\n>b\nACG\n")                      # unequal lengths: snp-dists exits 1
     r = subprocess.run("snp-dists -c -j 1 %s > %s" % (mf, sc), shell=True, env=env, capture_output=True)
     assert r.returncode == 1 and b"has length 3 but expected 4" in r.stderr
+
+
+def test_long_rows_uint32_cells_through_the_file_writer(ph, capi, oracle, tmp_path):
+    """66,000-site rows need uint32 cells and print 5-digit distances: the level-1 writer (exact row
+    lengths, in-place formatting) against the oracle's snp-dists; also through the file mapping."""
+    n, L = 1030, 66000
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = acgt[rng.integers(0, 4, size=(n, L))]                      # unrelated rows: distances around 3 L / 4
+    seqs[::3] = seqs[0]                                               # ... and some identical / close ones
+    seqs[1::3, : L // 2] = seqs[1, : L // 2]
+    names = synth.sample_names(n)
+    sf, sc, oc = tmp_path / "snps.fas", tmp_path / "snps.csv", tmp_path / "o.csv"
+    synth.write_fasta(str(sf), names, seqs, wrap=0)
+    assert oracle.run_snp_dists(str(sf), str(oc), threads=8).returncode == 0
+    want = oc.read_bytes()
+    ph.build_snp_matrix(str(sc), str(sf), threads=4)
+    assert sc.read_bytes() == want
+    try:
+        capi.check(capi.lib().btb_set_option(b"csv_mmap", 1))
+        ph.build_snp_matrix(str(sc), str(sf), threads=3)
+        assert sc.read_bytes() == want
+    finally:
+        capi.check(capi.lib().btb_set_option(b"csv_mmap", 0))
