@@ -117,3 +117,48 @@ def test_fasta_and_csv_names(capi, ph):
     names = _names_from(capi.lib().btb_fasta_names, os.path.join(GOLDEN, "kat3_snps.fas").encode(), 2)
     assert names == ["A_consensus", "B_consensus", "C_consensus", "D_consensus"]
     assert _names_from(capi.lib().btb_csv_row_names, os.path.join(GOLDEN, "kat3_snps.csv").encode(), b",") == names
+
+
+def test_relabel_fuzz_against_pandas(ph, oracle, tmp_path):
+    """Random row names from a hostile alphabet (digits only, NA-like words, quotes, dots, signs, mixed
+    case, submission numbers): whenever the reference's pandas round trip succeeds, the streaming
+    relabel writes the same bytes; whenever it fails, so does ours (and the file is left alone)."""
+    import numpy as np
+    rng = random.Random(77)
+    words = ["NA", "nan", "NULL", "None", "n/a", "1e5", "12", "-3", "+7", "0.5", ".5", "inf", "True", "false", "TRUE",
+             "AF-12-34567-89", "af-21-1234-21_consensus", "x_consensus", "12-3456-78", "99-12345-99x", "a.b", "a'b", 'a"b',
+             "#c", "d#", "e;f", "g|h", "i:j", "k/l", "m=n", "o p", " q", "r ", "1_000", "0x1F", "1,5"]
+    agree = fail = 0
+    for case in range(160):
+        n = rng.randint(1, 6)
+        names = []
+        for _ in range(n):
+            if rng.random() < 0.6:
+                names.append(rng.choice(words))
+            else:
+                names.append("".join(rng.choice("ABab019-_.x") for _ in range(rng.randint(1, 9))))
+        if any("," in x for x in names) and rng.random() < 0.8:
+            continue                                          # commas break the matrix shape for both; keep a few
+        d = np.array([[abs(i - j) * 3 for j in range(n)] for i in range(n)], dtype=np.uint32)
+        text = oracle.format_matrix(names, d)
+        a, b = tmp_path / "a.csv", tmp_path / "b.csv"
+        a.write_bytes(text)
+        b.write_bytes(text)
+        try:
+            pandas_round_trip(str(b))
+            ref_ok = True
+        except Exception:
+            ref_ok = False
+        try:
+            ph.post_process_snps_csv(str(a))
+            ours_ok = True
+        except Exception:
+            ours_ok = False
+        assert ours_ok == ref_ok, (case, names, ref_ok, ours_ok)
+        if ref_ok:
+            assert a.read_bytes() == b.read_bytes(), (case, names)
+            agree += 1
+        else:
+            assert a.read_bytes() == text, (case, names)
+            fail += 1
+    assert agree > 40 and fail > 10
