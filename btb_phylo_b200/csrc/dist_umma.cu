@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -1392,6 +1393,22 @@ int g_umma_lockstep = 1;       // 0: off; k >= 1: producers of all CTAs start ea
 int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
 int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
+// Arrival counters of the lockstep barrier.  Every launch takes the next of 64 slots (128 bytes apart) and
+// clears it on its own stream: a launch on another stream can then never reset a counter a running
+// kernel is still waiting on (the launches need the whole GPU, so 64 launches later a slot is long free).
+static int lock_slot(int dev, unsigned int **slot) {
+    static unsigned int *pool[16] = {nullptr};
+    static std::atomic<unsigned> next[16];
+    static std::mutex m;
+    if (dev < 0 || dev >= 16) return fail(BTB_EINVAL, "device ordinal too large");
+    {
+        std::lock_guard<std::mutex> lock(m);
+        if (!pool[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&pool[dev]), 64 * 128));
+    }
+    *slot = pool[dev] + (next[dev].fetch_add(1) % 64u) * 32u;
+    return BTB_OK;
+}
+
 template <int CG, typename OutT, int ATOMS = 1, bool RELAY = false>
 static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
     using Cfg = UmmaCfg<CG, ATOMS, RELAY>;
@@ -1414,12 +1431,12 @@ static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaP
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     UmmaParams q = p;
-    static unsigned int *d_lock[16] = {nullptr};
     cudaLaunchAttribute attrs2[2];
     if (g_umma_lockstep && p.units > ctas / (CG == 2 ? 2 : 1) && dev < 16) {
-        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
-        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        q.lockstep = d_lock[dev]; q.lock_slack = g_umma_lockstep - 1;
+        unsigned int *slot = nullptr;
+        BTB_TRY(lock_slot(dev, &slot));
+        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
+        q.lockstep = slot; q.lock_slack = g_umma_lockstep - 1;
         attrs2[0] = attr[0];
         attrs2[1].id = cudaLaunchAttributeCooperative;
         attrs2[1].val.cooperative = 1;
@@ -1465,11 +1482,11 @@ static int launch_umma_tile(const CUtensorMap &ma, const CUtensorMap &mb, const 
     cfg.stream = stream;
     cfg.numAttrs = 0;
     UmmaParams q = p;
-    static unsigned int *d_lock[16] = {nullptr};
     if (g_umma_lockstep && p.units > ctas && dev < 16) {
-        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
-        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        q.lockstep = d_lock[dev]; q.lock_slack = g_umma_lockstep - 1;
+        unsigned int *slot = nullptr;
+        BTB_TRY(lock_slot(dev, &slot));
+        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
+        q.lockstep = slot; q.lock_slack = g_umma_lockstep - 1;
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
@@ -1621,11 +1638,11 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            static unsigned int *d_lock2[16] = {nullptr};
             if (g_umma_lockstep && p.units > pairs) {
-                if (!d_lock2[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock2[dev]), 256));
-                BTB_CUDA(cudaMemsetAsync(d_lock2[dev], 0, 4, stream));
-                p.lockstep = d_lock2[dev]; p.lock_slack = g_umma_lockstep - 1;
+                unsigned int *slot = nullptr;
+                BTB_TRY(lock_slot(dev, &slot));
+                BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
+                p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
                 attr[1].id = cudaLaunchAttributeCooperative;
                 attr[1].val.cooperative = 1;
                 cfg.numAttrs = g_umma_coop ? 2 : 1;
@@ -1660,11 +1677,11 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
     cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
     cfg.stream = stream;
     cfg.numAttrs = 0;
-    static unsigned int *d_lock[16] = {nullptr};
     if (g_umma_lockstep && p.units > ctas) {
-        if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
-        BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-        p.lockstep = d_lock[dev]; p.lock_slack = g_umma_lockstep - 1;
+        unsigned int *slot = nullptr;
+        BTB_TRY(lock_slot(dev, &slot));
+        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
+        p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
@@ -1736,11 +1753,11 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         cfg.dynamicSmemBytes = UmmaCfg<1>::kSmemBytes;
         cfg.stream = stream;
         cfg.numAttrs = 0;
-        static unsigned int *d_lock[16] = {nullptr};
-        if (g_umma_lockstep && p.units > ctas && dev < 16) {
-            if (!d_lock[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_lock[dev]), 256));
-            BTB_CUDA(cudaMemsetAsync(d_lock[dev], 0, 4, stream));
-            p.lockstep = d_lock[dev]; p.lock_slack = g_umma_lockstep - 1;
+            if (g_umma_lockstep && p.units > ctas && dev < 16) {
+                unsigned int *slot = nullptr;
+                BTB_TRY(lock_slot(dev, &slot));
+                BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
+                p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
             attr[0].id = cudaLaunchAttributeCooperative;
             attr[0].val.cooperative = 1;
             cfg.attrs = attr;
