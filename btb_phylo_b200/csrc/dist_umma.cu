@@ -1533,7 +1533,7 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
     std::lock_guard<std::mutex> lock(g_lists_mutex);
     for (auto &e : g_lists[dev])
         if (e.n == n && e.lo == lo && e.hi == hi && e.kind == kind) { *d_out = e.d; *count = e.count; return BTB_OK; }
-    if (g_lists[dev].size() > 96) {
+    if (g_lists[dev].size() > 512) {                     // (never reached by one alignment: a list per band and kind)
         BTB_CUDA(cudaDeviceSynchronize());
         for (auto &e : g_lists[dev]) cudaFree(e.d);
         g_lists[dev].clear();
