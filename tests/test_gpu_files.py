@@ -78,6 +78,11 @@ def test_edge_snp_sites_and_gzip(ph, tmp_path):
     gz.write_bytes(gzip.compress(golden("c1_multi_fasta.fas")))
     assert ph.snp_sites(str(sf), str(gz)) == {"number_of_snps": 831}
     assert sf.read_bytes() == golden("c1_snps.fas")
+    # snp-dists reads gzip too (kseq over gzread)
+    gz2, sc = tmp_path / "c1_snps.fas.gz", tmp_path / "snps.csv"
+    gz2.write_bytes(gzip.compress(golden("c1_snps.fas")))
+    ph.build_snp_matrix(str(sc), str(gz2), threads=2)
+    assert sc.read_bytes() == golden("c1_snps.csv")
 
 
 def test_errors_raise_like_the_reference(ph, tmp_path):
