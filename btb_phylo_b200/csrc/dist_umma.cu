@@ -1,21 +1,22 @@
-// k4, UMMA engine: the SNP distance matrix as an exact int8 GEMM on the 5th-gen tensor cores.
+// k4, UMMA engine: the SNP distance matrix as an exact GEMM on the 5th-gen tensor cores.
 //
 // Replaces the O(N^2 L) byte-compare loop of snp-dists 0.8.2, reached in
-// the reference through btbphylo/phylogeny.py:149.  With the operands of dist_encode.cu,
-//     d(i,j) = sum_k A[i][k] * B[j][k]          (A one-hot, B masked complement, values 0/1)
-// or, for dense alignments (one +-1 simplex operand X),  d(i,j) = (3 len - sum_k X[i][k] X[j][k]) / 4,
-// which tcgen05.mma kind::i8 evaluates exactly with int32 accumulators in tensor memory.
+// the reference through btbphylo/phylogeny.py:149.  With the operands of dist_encode.cu (0/1 codes),
+//     dense alignments:   d(i,j) = c_i + c_j - sum_k X[i][k] X[j][k]      (tetrahedron code, c = row sums)
+//     general alphabets:  d(i,j) = sum_k V[i][k] V[j][k] - sum_s sum_k X_s[i][k] X_s[j][k]
+// evaluated exactly by tcgen05.mma kind::mxf4 on e2m1 nibbles (fp32 accumulators hold the integers)
+// or, for very long rows / umma_fp4 = 0, by kind::i8 with int32 accumulators
+//     d(i,j) = sum_k A[i][k] * B[j][k]          (A one-hot, B masked complement).
 //
-// Kernel shape (sm_100a only):
-//   * persistent; one unit of work = one BTB_TILE x BTB_TILE tile of the upper triangle
-//     (CG = 2: a CTA pair, UMMA 256 x 256 x 32, each CTA holds 128 accumulator rows) or one
-//     128-row half of it (CG = 1: UMMA 128 x 256 x 32);
-//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, 128 K-bytes per stage),
-//     warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator,
-//     warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> direct + mirrored global stores);
-//   * smem ring of kStages stages with full/empty mbarriers; two TMEM accumulator stages so the
-//     epilogue of tile t overlaps the K loop of tile t+1.
-// Bound: tensor pipe.  ops = 2 * sigma4 * L * 256 * 256 per tile.
+// Kernels in this file (sm_100a only; all persistent, warp 0 = TMA producer, warp 1 = MMA issuer with
+// one elected lane, warp 2 = TMEM allocator, warps 4.. = epilogue; full/empty mbarrier rings):
+//   dist_umma_fp4_pair_kernel   default: CTA pairs (cta_group::2), 512 x 240 units, B split across the pair
+//   dist_umma_fp4_tile_kernel   one CTA per 256 x 240 unit (two halves share every staged B block)
+//   dist_umma_fp4_kernel        128-row half tiles (small launches, explicit tile lists)
+//   dist_umma_tile_kernel       int8, 256 x 256 tiles as two halves
+//   dist_umma_kernel            int8 half tiles and the older int8 CTA-pair variant
+//   umma_probe_kernel           MMA / commit issue-rate probe (no data movement)
+// Bound: tensor pipe (at the board's power cap).  DESIGN.md section 4 has the measurements.
 #include <cuda.h>
 
 #include <algorithm>
