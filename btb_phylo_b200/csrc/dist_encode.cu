@@ -8,15 +8,21 @@
 //                 Bit order inside a row is a fixed permutation of the sites (a lane reads 4
 //                 consecutive bytes, a ballot gathers byte b of all lanes), identical for every
 //                 row -- a distance is a sum over sites, so any common order is exact.
-//   UMMA engine : K-major int8, sigma4 = roundup(sigma, 4) bytes per site:
+//   UMMA engine, kind::mxf4 (default): packed e2m1 nibbles (1.0 = 0x2), ONE operand for both sides.
+//                 dense (BTB_SIGMA_DENSE4: <= 4 symbols, nothing ignored -- every snp-sites -c output):
+//                   3 nibbles per site, the 0/1 vertices of a regular tetrahedron (0,0,0) (1,1,0)
+//                   (1,0,1) (0,1,1) + an int32 row sum c_i:  d = c_i + c_j - dot.  Per site the most
+//                   frequent symbol takes the zero vertex (site_counts / site_major kernels).
+//                 general: sigma + 1 nibble planes per row (validity V, one-hot X_s), each padded
+//                   to whole 128-byte K blocks:  d = V.V - sum_s X_s.X_s  (negate-A descriptor bit).
+//   UMMA engine, kind::i8 (umma_fp4 = 0 or rows beyond the fp32-exact range): K-major int8,
+//                 sigma4 = roundup(sigma, 4) bytes per site:
 //                 A[i][site*sigma4 + b] = [valid and code == b]            (one-hot)
 //                 B[i][site*sigma4 + b] = [valid and code != b, b < sigma] (masked complement)
-//                 so that  sum_b A_i * B_j = [valid_i][valid_j][code_i != code_j]  = snp-dists' test.
-//   dense (BTB_SIGMA_DENSE4: <= 4 symbols, nothing ignored -- every snp-sites -c output):
-//                 UMMA: one operand, 3 bytes per site, the +-1 vertices of a regular simplex
-//                 (1,1,1) (1,-1,-1) (-1,1,-1) (-1,-1,1): dot = 3 on a match, -1 on a mismatch, so
-//                 d = (3 len - dot) / 4 with 25 % fewer MMAs and half the operand bytes;
-//                 POPC: the validity plane is dropped.
+//                 so that  sum_b A_i * B_j = [valid_i][valid_j][code_i != code_j]  = snp-dists' test;
+//                 dense: one operand, 3 bytes per site (tetrahedron code as above, or the +-1 simplex
+//                 (1,1,1) (1,-1,-1) (-1,1,-1) (-1,-1,1) with d = (3 len - dot) / 4, or one-hot).
+//   POPC, dense : the validity plane is dropped.
 //
 // HBM-bound streaming kernels: algorithmic bytes = n*len read + operand bytes written.
 #include <algorithm>
