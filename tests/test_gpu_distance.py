@@ -1,6 +1,7 @@
 """GPU (-m gpu): the distance stage (k4) through the C-ABI against the CPU oracle, bit-exact.
-Both engines (POPC bit-planes, tcgen05 kind::i8 GEMM with CTA pairs and single CTAs), default and
--a / -k modes, ragged sizes, tile-packed output, rank shares, uint16 / uint32 output."""
+Both engines (POPC bit-planes; tcgen05: kind::mxf4 on 0/1 nibble codes with CTA pairs, single CTAs and
+half-tile units, and the kind::i8 kernels), default and -a / -k modes, ragged sizes, tile-packed
+output, rank shares by tiles and by block rows, uint16 / uint32 output, the level-2 host call."""
 import ctypes
 
 import numpy as np
