@@ -1649,6 +1649,17 @@ static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_
                 cfg.numAttrs = g_umma_coop ? 2 : 1;
             }
             BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_pair_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4PairCfg::kSmemBytes));
+            // the lockstep barrier needs every pair resident: never launch more pairs than the device can hold
+            static int max_pairs[16] = {0};
+            if (!max_pairs[dev]) {
+                int m = 0;
+                cudaLaunchConfig_t probe = cfg;
+                probe.gridDim = dim3(unsigned(sms / 2 * 2));
+                probe.numAttrs = 1;                       // cluster dimension only
+                BTB_CUDA(cudaOccupancyMaxActiveClusters(&m, dist_umma_fp4_pair_kernel<uint16_t>, &probe));
+                max_pairs[dev] = std::max(1, m);
+            }
+            if (pairs > max_pairs[dev]) cfg.gridDim = dim3(unsigned(max_pairs[dev] * 2));
             BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_pair_kernel<uint16_t>, ma, mb, p));
             *launched = 1;
             return BTB_OK;
