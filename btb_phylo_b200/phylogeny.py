@@ -49,12 +49,13 @@ def _raise_like_run(cmd, err):
           *****""" % (cmd, 1, err))
 
 
-def snp_sites(snp_sites_outpath, multi_fasta_path, threads=1):
+def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None):
     """Run the snp-sites stage on consensus files (reference: phylogeny.py:128-141).
 
     Writes `snp_sites_outpath` (one unwrapped record per sample) and returns
-    {"number_of_snps": L}.  `threads` (host staging threads) is optional; the reference
-    signature has two positional arguments and those keep working.
+    {"number_of_snps": L}.  `threads` (host threads that read the file into the upload buffers) is
+    optional -- the reference signature has two positional arguments and those keep working; the
+    default is every core (BTBPHYLO_THREADS overrides), since the stage is bound by reading the file.
 
     `multi_fasta_path` may also be a list / tuple of per-sample consensus FASTA paths: they are
     taken as if concatenated in that order -- the file build_multi_fasta (phylogeny.py:48-88) would
@@ -63,6 +64,8 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=1):
     n = ctypes.c_int64(0)
     g = ctypes.c_int64(0)
     l = ctypes.c_int64(0)
+    if threads is None:
+        threads = int(os.environ.get("BTBPHYLO_THREADS", 0)) or min(32, os.cpu_count() or 1)
     if isinstance(multi_fasta_path, (list, tuple)):
         paths = [os.fsencode(x) for x in multi_fasta_path]
         shown = "<%d consensus files>" % len(paths)
