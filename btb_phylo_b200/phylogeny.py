@@ -27,12 +27,16 @@ class PhylogenyError(Exception):
     `except Exception` in callers (btb_phylo.py) behaves identically."""
 
 
-def _gpus():
-    """GPU count: BTBPHYLO_GPUS, else every visible sm_100 device."""
+def _gpus(input_bytes=None):
+    """GPU count: BTBPHYLO_GPUS, else the visible sm_100 devices -- but no more than one per 4 GB of
+    input text when the size is known (a second CUDA context costs more than it saves on small files)."""
     env = os.environ.get("BTBPHYLO_GPUS")
     if env:
         return max(1, int(env))
-    return max(1, _capi.device_count())
+    n = max(1, _capi.device_count())
+    if input_bytes is not None:
+        n = max(1, min(n, input_bytes // (4 << 30)))
+    return n
 
 
 def _engine():
@@ -66,16 +70,23 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None):
     l = ctypes.c_int64(0)
     if threads is None:
         threads = int(os.environ.get("BTBPHYLO_THREADS", 0)) or min(32, os.cpu_count() or 1)
+    def size_of(path):
+        try:
+            return os.path.getsize(path)
+        except OSError:
+            return 0                                       # the library reports the unreadable file
     if isinstance(multi_fasta_path, (list, tuple)):
         paths = [os.fsencode(x) for x in multi_fasta_path]
         shown = "<%d consensus files>" % len(paths)
         arr = (ctypes.c_char_p * max(1, len(paths)))(*paths)
         rc = _capi.lib().btb_snp_sites_files(arr, len(paths), shown.encode(), os.fsencode(snp_sites_outpath), 1,
-                                             _gpus(), int(threads), ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
+                                             _gpus(sum(size_of(x) for x in paths)), int(threads),
+                                             ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
     else:
         shown = multi_fasta_path
         rc = _capi.lib().btb_snp_sites(os.fsencode(multi_fasta_path), os.fsencode(snp_sites_outpath), 1,
-                                       _gpus(), int(threads), ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
+                                       _gpus(size_of(multi_fasta_path)), int(threads),
+                                       ctypes.byref(n), ctypes.byref(g), ctypes.byref(l))
     if rc != _capi.OK:
         _raise_like_run("snp-sites %s -c -o %s" % (shown, snp_sites_outpath), _capi.last_error())
     # read the number of snps for metadata exactly as the reference does (phylogeny.py:136-140)
