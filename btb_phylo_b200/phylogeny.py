@@ -122,14 +122,22 @@ def build_snp_matrix(snp_dists_outpath, snp_sites_outpath, threads=1, post_proce
     (phylogeny.py:172-187, called at btb_phylo.py:598) leaves behind -- without the pandas parse and
     re-serialisation of the O(N^2) matrix."""
     t = max(1, int(threads))
+    # one GPU computes the 50,000-sample matrix in 30 ms: the stage is bound by reading snps.fas and writing
+    # snps.csv, and every further GPU costs a CUDA context and an upload.  More GPUs only when asked for
+    # (BTBPHYLO_GPUS) or when the alignment is large enough (> 8 GB) for its operands to crowd one device.
+    try:
+        fas_bytes = os.path.getsize(snp_sites_outpath)
+    except OSError:
+        fas_bytes = 0
+    gpus = _gpus(fas_bytes // 2)
     if post_process:
         labels = _labels_for(_names_from(_capi.lib().btb_fasta_names, os.fsencode(snp_sites_outpath), t))
         blob = "\n".join(labels).encode("utf-8")
         rc = _capi.lib().btb_snp_dists_labelled(os.fsencode(snp_sites_outpath), os.fsencode(snp_dists_outpath),
-                                                0, 0, 0, b",", 1, 0, _gpus(), t, _engine(), blob, len(labels), None, None)
+                                                0, 0, 0, b",", 1, 0, gpus, t, _engine(), blob, len(labels), None, None)
     else:
         rc = _capi.lib().btb_snp_dists(os.fsencode(snp_sites_outpath), os.fsencode(snp_dists_outpath),
-                                       0, 0, 0, b",", 1, 0, _gpus(), t, _engine(), None, None)
+                                       0, 0, 0, b",", 1, 0, gpus, t, _engine(), None, None)
     if rc != _capi.OK:
         _raise_like_run("snp-dists -c -j %s %s > %s" % (threads, snp_sites_outpath, snp_dists_outpath),
                         _capi.last_error())
