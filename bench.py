@@ -284,10 +284,27 @@ def gpu_arm(args):
     e2e_s = float(t[0])
     r0, r1 = min(n, row_lo * 256), min(n, row_hi * 256)
     d2h = n * n * elem if world == 1 else ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * elem
+    # what the box's PCIe link gives a plain pinned copy (context for e2e, which is bound by the 5 GB download)
+    def _copy_rate(dst, src):
+        best = 0.0
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0c = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, src.numel() * src.element_size() / (time.perf_counter() - t0c) / 1e9)
+        return best
+    try:
+        probe_dev = torch.empty(min(h_seqs.numel(), 1 << 30), dtype=torch.uint8, device=device)
+        probe_host = h_seqs.view(-1)[: probe_dev.numel()]
+        pcie = {"h2d_GBps": _copy_rate(probe_dev, probe_host), "d2h_GBps": _copy_rate(probe_host.clone().pin_memory(), probe_dev)}
+        del probe_dev
+    except Exception as exc:                                         # noqa: BLE001 -- context only, never fatal
+        pcie = {"unavailable": type(exc).__name__}
     e2e = {"value": unique_pairs(n) / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(n * L),
            "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_s, "steps": e2e_steps,
            "call": "btb_dist_matrix_host (C-ABI level 2; per-rank bytes)", "host_numa": numa,
-           "pcie_GBps": (n * L + d2h) / e2e_s / 1e9}
+           "pcie_GBps": (n * L + d2h) / e2e_s / 1e9, "pcie_plain_copy": pcie}
 
     if rank != 0:
         if world > 1:
