@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libbtbphylo.so")
 ENGINE_AUTO, ENGINE_POPC, ENGINE_UMMA = -1, 0, 1
 TILE = 256
 SIGMA_DENSE4 = -4
-OK, EINVAL, EIO, EFORMAT, ENOSNPS, ECUDA, ENODEVICE, ENOMEM = range(8)
+OK, EINVAL, EIO, EFORMAT, ENOSNPS, ECUDA, ENODEVICE, ENOMEM, ECOMM = range(9)
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -32,6 +32,10 @@ SIGNATURES = {
     "btb_dist_matrix_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_vp, c_int, c_i64]),
     "btb_release_workspace": (c_int, []),
+    "btb_comm_create": (c_int, [ctypes.c_char_p, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "btb_comm_destroy": (c_int, [c_vp]),
+    "btb_dist_matrix_host_comm": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_int, c_i64]),
+    "btb_comm_last_timings": (c_int, [c_vp, ctypes.POINTER(ctypes.c_double), c_int]),
     "btb_extract_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, p_i64, c_vp, c_i64]),
     "btb_plane_words": (c_i64, [c_i64]),
     "btb_pack_planes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),

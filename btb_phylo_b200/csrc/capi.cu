@@ -60,6 +60,12 @@ int umma_probe(int cg, int every, int64_t *cycles_x100);
 int dist_presence_async(const uint8_t *, int64_t, int64_t, int64_t, uint32_t *, cudaStream_t);
 int dist_encode_fp4_dense_rows(const uint8_t *, int64_t, int64_t, int64_t, const uint8_t *, int64_t, uint8_t *, int32_t *,
                                cudaStream_t);
+extern int g_comm_band_rows;
+extern int g_comm_last_path;
+struct CommShared;
+CommShared *comm_shared_new(int world);
+void comm_shared_free(CommShared *sh);
+int comm_create_local(CommShared *sh, int rank, int world, int device, btb_comm **out);
 int g_csv_mmap = 0;             // "csv_mmap": write snps.csv through a file mapping, rows formatted in place by all host threads.
                                // Off: measured 3.5-3.9 s for the 12.2 GB C4 file against 2.7-3.1 s for write() -- shared-mapping
                                // write faults cost more than the buffered write path, and formatting (0.4 s) hides behind either.
@@ -118,15 +124,37 @@ extern "C" int btb_last_error(char *buf, size_t cap) {
 
 extern "C" const char *btb_version(void) { return "btb-phylo-b200 0.1 (snp-sites 2.5.1 -c / snp-dists 0.8.2 semantics, sm_100a)"; }
 
-extern "C" int btb_device_count(int *count) {
+namespace btb {
+// CUDA ordinals of the usable (sm_100) devices, ascending: worker k of a multi-GPU call runs on ordinal [k]
+std::vector<int> usable_devices() {
+    std::vector<int> out;
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
-    int ok = 0;
     for (int d = 0; d < c; ++d) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) out.push_back(d);
     }
-    if (count) *count = ok;
+    return out;
+}
+// the ordinals the n workers of a multi-GPU call run on: the first n usable devices; with the test knob
+// "multi_gpu_oversubscribe" a box with fewer devices runs several workers per device
+int g_oversubscribe = 0;
+std::vector<int> worker_devices(int n_gpus) {
+    std::vector<int> d = usable_devices();
+    const size_t have = d.size();
+    if (g_oversubscribe && have > 0)
+        for (size_t k = have; k < size_t(std::max(1, n_gpus)) && k < 16; ++k) d.push_back(d[k % have]);
+    if (d.size() > size_t(std::max(1, n_gpus))) d.resize(size_t(std::max(1, n_gpus)));
+    return d;
+}
+int first_usable_device() {
+    const std::vector<int> d = usable_devices();
+    return d.empty() ? 0 : d[0];          // 0: require_device(0) then reports why nothing is usable
+}
+}  // namespace btb
+
+extern "C" int btb_device_count(int *count) {
+    if (count) *count = int(usable_devices().size());
     return BTB_OK;
 }
 
@@ -138,6 +166,8 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "csv_mmap")) { g_csv_mmap = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "dense_pageable")) { g_dense_pageable = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "host_stream")) { g_host_stream = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "multi_gpu_oversubscribe")) { g_oversubscribe = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "comm_band_rows")) { g_comm_band_rows = value < 2 ? 2 : value; return BTB_OK; }
     if (key && !strcmp(key, "host_stream_rows")) { g_host_stream_rows = value < 8 ? 8 : value; return BTB_OK; }
     if (key && !strcmp(key, "ingest_predict")) { set_ingest_predict(value); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_general")) { g_umma_fp4_general = value ? 1 : 0; return BTB_OK; }
@@ -173,6 +203,8 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     if (!strcmp(key, "umma_major_zero")) { *value = g_umma_major_zero; return BTB_OK; }
     if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }
     if (!strcmp(key, "host_stream")) { *value = g_host_stream; return BTB_OK; }
+    if (!strcmp(key, "comm_last_path")) { *value = g_comm_last_path; return BTB_OK; }
+    if (!strcmp(key, "comm_band_rows")) { *value = g_comm_band_rows; return BTB_OK; }
     if (!strcmp(key, "host_stream_last")) { *value = g_host_stream_last; return BTB_OK; }
     if (!strcmp(key, "ingest_last_predicted")) { *value = get_ingest_last(); return BTB_OK; }
     return fail(BTB_EINVAL, "btb_query: unknown key '%s'", key);
@@ -657,65 +689,35 @@ extern "C" int btb_format_csv_rows(const void *mat, int elem_bytes, int64_t ld, 
 
 namespace {
 
-// Multi-GPU distance stage: operands replicated, bands of block rows dealt
-// to the devices in snake order (band sizes shrink with the row index), every device copies the
-// matrix rows it completed plus the mirrored column strip into the host matrix H.  No collective:
-// one host thread per device.  H is n x ld elements, pinned.
-int multi_gpu_matrix(const DenseFasta &df, int n_dev, int allchars, int keepcase, int engine, int eb, int64_t ld,
-                     char *H) {
-    const int64_t n = df.n, len = df.len, T = tiles_per_dim(n);
-    std::vector<std::vector<int64_t>> bands(static_cast<size_t>(n_dev));
-    int64_t k = 0;
-    for (int64_t r0 = 0; r0 < T; r0 += kBand, ++k) {
-        const int64_t lap = k / n_dev, pos = k % n_dev;
-        bands[size_t((lap & 1) ? n_dev - 1 - pos : pos)].push_back(r0);
-    }
+// Multi-GPU distance stage inside one process: one host thread per device, the
+// devices form an in-process btb_comm group -- each uploads and encodes 1/P of the samples, the operand
+// shards travel GPU to GPU (peer copies), every device computes its block rows and copies them into the
+// host matrix H (n x ld elements) band by band.  No collective library.  See dist_comm.cu.
+int multi_gpu_matrix(const DenseFasta &df, const std::vector<int> &devs, int allchars, int keepcase, int engine, int eb,
+                     int64_t ld, char *H) {
+    const int n_dev = int(devs.size());
+    CommShared *sh = comm_shared_new(n_dev);
+    if (!sh) return fail(BTB_ENOMEM, "out of host memory");
     std::vector<int> rcs(static_cast<size_t>(n_dev), BTB_OK);
     std::vector<std::string> errs(static_cast<size_t>(n_dev));
-    auto worker = [&](int dev) {
-        auto body = [&]() -> int {
-            BTB_TRY(require_device(dev));
-            cudaStream_t st;
-            BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
-            auto done = [&](int rc) { cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out); cudaStreamDestroy(st); return rc; };
-            if (cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)) != cudaSuccess) return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
-            if (cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st) != cudaSuccess) return done(fail(BTB_ECUDA, "H2D failed"));
-            uint8_t table[256];
-            int sigma = 4;
-            int rc = btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st);
-            if (rc) return done(rc);
-            if (cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)) != cudaSuccess) return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
-            const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
-            if (cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))) != cudaSuccess)
-                return done(fail(BTB_ENOMEM, "device %d: out of memory", dev));
-            rc = btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st);
-            if (rc) return done(rc);
-            for (int64_t r0 : bands[size_t(dev)]) {
-                const int64_t w = std::min<int64_t>(kBand, T - r0), first = band_first_tile(T, r0);
-                rc = btb_distance_tiles(eng, d_ops, n, len, sigma, first, first + band_tiles(T, r0, w), d_out, eb, ld, 0, 1, st);
-                if (rc) return done(rc);
-                const int64_t row0 = r0 * BTB_TILE, row1 = std::min<int64_t>(n, (r0 + w) * BTB_TILE);
-                // rows of the band from its first column to the end ...
-                if (cudaMemcpy2DAsync(H + size_t(row0 * ld + row0) * eb, size_t(ld) * eb, d_out + size_t(row0 * ld + row0) * eb,
-                                      size_t(ld) * eb, size_t(n - row0) * eb, size_t(row1 - row0), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-                    return done(fail(BTB_ECUDA, "D2H failed"));
-                // ... and the mirrored strip below it
-                if (row1 < n && cudaMemcpy2DAsync(H + size_t(row1 * ld + row0) * eb, size_t(ld) * eb, d_out + size_t(row1 * ld + row0) * eb,
-                                                  size_t(ld) * eb, size_t(row1 - row0) * eb, size_t(n - row1), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-                    return done(fail(BTB_ECUDA, "D2H failed"));
-            }
-            if (cudaStreamSynchronize(st) != cudaSuccess) return done(fail(BTB_ECUDA, "device %d: kernel or copy failed: %s", dev, cudaGetErrorString(cudaGetLastError())));
-            return done(BTB_OK);
-        };
-        rcs[size_t(dev)] = body();
-        if (rcs[size_t(dev)]) errs[size_t(dev)] = last_error();
+    std::vector<btb_comm *> comms(static_cast<size_t>(n_dev), nullptr);
+    auto worker = [&](int k) {
+        int rc = comm_create_local(sh, k, n_dev, devs[size_t(k)], &comms[size_t(k)]);
+        if (rc == BTB_OK)
+            rc = btb_dist_matrix_host_comm(comms[size_t(k)], df.rows, df.n, df.len, df.stride, allchars, keepcase, engine, H, eb, ld);
+        rcs[size_t(k)] = rc;
+        if (rc) errs[size_t(k)] = last_error();
     };
     std::vector<std::thread> pool;
-    for (int d = 0; d < n_dev; ++d) pool.emplace_back(worker, d);
+    for (int k = 0; k < n_dev; ++k) pool.emplace_back(worker, k);
     for (auto &t : pool) t.join();
-    for (int d = 0; d < n_dev; ++d)
-        if (rcs[size_t(d)]) return fail(rcs[size_t(d)], "%s", errs[size_t(d)].c_str());
+    pool.clear();
+    // teardown waits for the peers, so it is collective as well
+    for (int k = 0; k < n_dev; ++k) pool.emplace_back([&, k] { btb_comm_destroy(comms[size_t(k)]); });
+    for (auto &t : pool) t.join();
+    comm_shared_free(sh);
+    for (int k = 0; k < n_dev; ++k)
+        if (rcs[size_t(k)]) return fail(rcs[size_t(k)], "%s", errs[size_t(k)].c_str());
     return BTB_OK;
 }
 
@@ -834,7 +836,7 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         fprintf(stderr, "Will use %d threads.\n", threads);
     }
     StageTimer timer("btb_snp_dists");
-    BTB_TRY(require_device(0));
+    BTB_TRY(require_device(first_usable_device()));
     timer.mark("device init");
     DenseFasta df;
     int rc = read_dense(in_fasta, threads, df);
@@ -884,13 +886,14 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         }                                                                                                 \
     } while (0)
 #define L1_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
-    int usable = 0;
-    btb_device_count(&usable);
-    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(std::min(n_gpus, usable), tiles_per_dim(n) / kBand)));
+    std::vector<int> devs = worker_devices(n_gpus);
+    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(devs.size()), tiles_per_dim(n) / kBand)));
+    devs.resize(size_t(n_dev));
     if (n_dev > 1) {
         L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_full), size_t(n * ld * eb)));
-        rc = multi_gpu_matrix(df, n_dev, allchars, keepcase, engine, eb, ld, h_full);
+        rc = multi_gpu_matrix(df, devs, allchars, keepcase, engine, eb, ld, h_full);
         if (rc != BTB_OK) { cleanup(); return rc; }
+        L1_TRY(require_device(devs[0]));
     }
     uint8_t table[256];
     int sigma = 4;

@@ -124,6 +124,9 @@ inline int64_t umma_k_bytes(int64_t len, int sigma) {   // row length, multiple 
     return (k + 127) / 128 * 128;
 }
 
+// per-site symbol counts of several ranks (sharded encode, dist_comm.cu); the pointers may be peer memory
+struct CountPtrs { const uint32_t *p[16]; int n; };
+
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -312,6 +312,24 @@ site_major_kernel(const uint32_t *__restrict__ counts, int64_t len, uint8_t *__r
     major[site] = m;
 }
 
+// the same from the counts of several ranks (sharded upload, dist_comm.cu): the pointers may be peer memory
+__global__ void __launch_bounds__(256)
+site_major_sum_kernel(const CountPtrs cp, int64_t len, uint8_t *__restrict__ major) {
+    const int64_t site = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (site >= len) return;
+    uint4 c = make_uint4(0, 0, 0, 0);
+    for (int q = 0; q < cp.n; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(cp.p[q] + site * 4);
+        c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
+    uint32_t best = c.x;
+    uint8_t m = 0;
+    if (c.y > best) { best = c.y; m = 1; }
+    if (c.z > best) { best = c.z; m = 2; }
+    if (c.w > best) { best = c.w; m = 3; }
+    major[site] = m;
+}
+
 // dense tetrahedron code as packed e2m1 nibbles (1.0 = 0x2): one thread per 16 sites -> 48 nibbles = 24 bytes
 __global__ void __launch_bounds__(256)
 encode_fp4_kernel(const uint8_t *__restrict__ seqs, int64_t n, int64_t len, int64_t row_stride,
@@ -554,32 +572,57 @@ int dist_encode_fp4_dense_rows(const uint8_t *d_seqs, int64_t rows, int64_t len,
     return BTB_OK;
 }
 
-}  // namespace btb
+// ---- pieces for the sharded multi-rank path (dist_comm.cu): a rank encodes only its own rows -------
+// per-site symbol counts of `rows` sequences into d_counts[len][4] (cleared here)
+int dist_site_counts(const uint8_t *d_seqs, int64_t rows, int64_t len, int64_t row_stride, const uint8_t *d_table,
+                     uint32_t *d_counts, cudaStream_t stream) {
+    BTB_CUDA(cudaMemsetAsync(d_counts, 0, size_t(len) * 16, stream));
+    if (rows <= 0 || len <= 0) return BTB_OK;
+    dim3 cgrid((unsigned)((len + 1023) / 1024), (unsigned)((rows + kMajorStripRows - 1) / kMajorStripRows));
+    site_counts_kernel<<<cgrid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, d_counts);
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
+}
 
-using namespace btb;
+int dist_site_major_sum(const CountPtrs &cp, int64_t len, uint8_t *d_major, cudaStream_t stream) {
+    if (len <= 0) return BTB_OK;
+    site_major_sum_kernel<<<(unsigned)((len + 255) / 256), 256, 0, stream>>>(cp, len, d_major);
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
+}
 
-// =============================================================================== C-ABI
-extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
-                                 int allchars, int keepcase, uint8_t table[256], int *sigma,
-                                 void *stream_) {
-    if (!table || !sigma) return fail(BTB_EINVAL, "btb_dist_alphabet: NULL output");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// FP4 operand rows (dense tetrahedron nibbles + row sums, or the general validity / one-hot planes) of
+// `rows` sequences; A_rows / rowsum_rows point at the first of these rows inside the full operand;
+// rowsum_rows must be zero.  d_major: the per-site zero-coded symbol (padded to 32 sites) or nullptr.
+int dist_encode_fp4_rows(const uint8_t *d_seqs, int64_t rows, int64_t len, int64_t row_stride, const uint8_t table[256],
+                         const uint8_t *d_table, int sigma, uint8_t *A_rows, int32_t *rowsum_rows, const uint8_t *d_major,
+                         cudaStream_t stream) {
+    if (rows <= 0) return BTB_OK;
+    const int64_t kb = umma_k_bytes(len, sigma);
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_seqs) % 4 == 0) && (row_stride % 4 == 0);
+    if (umma_fp4_general(sigma, len)) {
+        const int64_t pb = umma_fp4_plane_bytes(len);
+        dim3 grid((unsigned)std::min<int64_t>((pb / 16 + 255) / 256, 1024), (unsigned)std::min<int64_t>(rows, 65535));
+        encode_fp4_planes_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, sigma, pb, kb, A_rows, aligned ? 1 : 0);
+    } else if (umma_fp4_dense(sigma, len)) {
+        dim3 grid((unsigned)std::min<int64_t>((kb / 48 + 256) / 256, 1024), (unsigned)std::min<int64_t>(rows, 65535));
+        if (is_default_acgt_table(table))
+            encode_fp4_acgt_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, kb, A_rows, rowsum_rows, d_major);
+        else
+            encode_fp4_kernel<<<grid, 256, 0, stream>>>(d_seqs, rows, len, row_stride, d_table, kb, A_rows, aligned ? 1 : 0, rowsum_rows, d_major);
+    } else {
+        return fail(BTB_EINVAL, "dist_encode_fp4_rows: not an FP4 operand layout");
+    }
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
+}
+
+// Symbol table and sigma from the byte values that occur (`present`, 256 bits; scanned = false: unknown).
+// snp-dists load rules: upper-case unless -k; default mode counts ACGT only; -a counts
+// everything but '.'.
+int dist_alphabet_from_presence(const uint32_t present[8], bool scanned, int allchars, int keepcase, uint8_t table[256], int *sigma) {
     for (int b = 0; b < 256; ++b) table[b] = 0xff;
     auto up = [&](int b) { return (!keepcase && b >= 'a' && b <= 'z') ? b - 32 : b; };
-    uint32_t *d_present = nullptr;
-    uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool scan = d_seqs && n * len > 0;
-    if (allchars && !d_seqs && n * len > 0) return fail(BTB_EINVAL, "btb_dist_alphabet: allchars needs the alignment");
-    if (scan) {
-        BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_present), sizeof(present), stream));
-        BTB_CUDA(cudaMemsetAsync(d_present, 0, sizeof(present), stream));
-        dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 2048));
-        presence_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_present);
-        BTB_CUDA(cudaGetLastError());
-        BTB_CUDA(cudaMemcpyAsync(present, d_present, sizeof(present), cudaMemcpyDeviceToHost, stream));
-        BTB_CUDA(cudaStreamSynchronize(stream));
-        BTB_CUDA(cudaFreeAsync(d_present, stream));
-    }
     int s = 0;
     if (!allchars) {
         const char *acgt = "ACGT";
@@ -603,11 +646,38 @@ extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, 
         if (s == 0) s = 1;
     }
     // dense: nothing that occurs is ignored, and at most four symbols
-    bool dense = scan && s <= 4;
+    bool dense = scanned && s <= 4;
     for (int b = 0; b < 256 && dense; ++b)
         if ((present[b >> 5] >> (b & 31) & 1) && table[b] == 0xff) dense = false;
     *sigma = dense ? BTB_SIGMA_DENSE4 : s;
     return BTB_OK;
+}
+
+}  // namespace btb
+
+using namespace btb;
+
+// =============================================================================== C-ABI
+extern "C" int btb_dist_alphabet(const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                                 int allchars, int keepcase, uint8_t table[256], int *sigma,
+                                 void *stream_) {
+    if (!table || !sigma) return fail(BTB_EINVAL, "btb_dist_alphabet: NULL output");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint32_t *d_present = nullptr;
+    uint32_t present[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool scan = d_seqs && n * len > 0;
+    if (allchars && !d_seqs && n * len > 0) return fail(BTB_EINVAL, "btb_dist_alphabet: allchars needs the alignment");
+    if (scan) {
+        BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_present), sizeof(present), stream));
+        BTB_CUDA(cudaMemsetAsync(d_present, 0, sizeof(present), stream));
+        dim3 grid((unsigned)std::min<int64_t>((len + 255) / 256, 64), (unsigned)std::min<int64_t>(n, 2048));
+        presence_kernel<<<grid, 256, 0, stream>>>(d_seqs, n, len, row_stride, d_present);
+        BTB_CUDA(cudaGetLastError());
+        BTB_CUDA(cudaMemcpyAsync(present, d_present, sizeof(present), cudaMemcpyDeviceToHost, stream));
+        BTB_CUDA(cudaStreamSynchronize(stream));
+        BTB_CUDA(cudaFreeAsync(d_present, stream));
+    }
+    return dist_alphabet_from_presence(present, scan, allchars, keepcase, table, sigma);
 }
 
 extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma) {

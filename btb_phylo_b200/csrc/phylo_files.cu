@@ -20,6 +20,9 @@
 
 namespace btb {
 int require_device(int device);
+std::vector<int> usable_devices();
+std::vector<int> worker_devices(int n_gpus);
+int first_usable_device();
 }
 using namespace btb;
 
@@ -148,7 +151,7 @@ constexpr int kRetryExact = 1000;      // internal: the predicted framing did no
 // One device's share of the extraction stage: samples [s0, s1) of the file, their planes and the
 // staging pipeline (host threads copy record bytes into pinned chunks, H2D, k1).
 struct ExtractCtx {
-    int dev = 0, threads = 1, rc = BTB_OK;
+    int slot = 0, dev = 0, threads = 1, rc = BTB_OK;      // slot: worker index; dev: its CUDA ordinal
     std::string err;
     int64_t s0 = 0, s1 = 0, nloc = 0, L = 0;
     Stream st;
@@ -334,9 +337,8 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
     if (G == 0) return no_snps();
 
     // ---- devices: samples are dealt to the GPUs as contiguous record ranges of equal bytes ---------
-    int usable = 0;
-    btb_device_count(&usable);
-    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(std::min(n_gpus, usable), n)));
+    const std::vector<int> devs = worker_devices(n_gpus);
+    const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(devs.size()), n)));
     const int64_t words = btb_plane_words(G);
     std::vector<ExtractCtx> ctx(static_cast<size_t>(n_dev));
     {
@@ -355,7 +357,7 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
         ctx[size_t(d)].s1 = n;
         for (int k = d + 1; k < n_dev; ++k) ctx[size_t(k)].s0 = ctx[size_t(k)].s1 = n;
     }
-    for (int d = 0; d < n_dev; ++d) { ctx[size_t(d)].dev = d; ctx[size_t(d)].threads = std::max(1, threads / n_dev); }
+    for (int d = 0; d < n_dev; ++d) { ctx[size_t(d)].slot = d; ctx[size_t(d)].dev = devs.empty() ? 0 : devs[size_t(d)]; ctx[size_t(d)].threads = std::max(1, threads / n_dev); }
     auto for_each_device = [&](const std::function<int(ExtractCtx &)> &fn) -> int {
         if (n_dev == 1) { int rc = fn(ctx[0]); return rc; }
         std::vector<std::thread> pool;
@@ -379,7 +381,7 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
         BTB_TRY(c.pack_all(src, recs, G, &bad));
         if (bad >= 0) { std::lock_guard<std::mutex> lock(bad_mutex); if (bad_record < 0 || bad < bad_record) bad_record = int(bad); return BTB_OK; }
         BTB_TRY(btb_column_mask(c.planes.as<uint32_t>(), c.nloc, c.nloc, G, c.state.as<uint32_t>(), 0, c.st.s));
-        BTB_CUDA(cudaMemcpyAsync(h_state[size_t(c.dev)].data(), c.state.p, size_t(5 * words * 4), cudaMemcpyDeviceToHost, c.st.s));
+        BTB_CUDA(cudaMemcpyAsync(h_state[size_t(c.slot)].data(), c.state.p, size_t(5 * words * 4), cudaMemcpyDeviceToHost, c.st.s));
         BTB_CUDA(cudaStreamSynchronize(c.st.s));
         return BTB_OK;
     }));
@@ -455,7 +457,7 @@ extern "C" int btb_snp_sites_files(const char *const *in_fastas, int64_t n_files
     const char *shown = alignment_name ? alignment_name : in_fastas[0];
     const int threads = std::max(1, host_threads);
     StageTimer timer("btb_snp_sites");
-    BTB_TRY(require_device(0));
+    BTB_TRY(require_device(first_usable_device()));
     timer.mark("device init");
     std::vector<FastaRecord> recs;
     if (g_ingest_predict) {

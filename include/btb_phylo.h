@@ -37,6 +37,7 @@ extern "C" {
 #define BTB_ECUDA       5   /* a CUDA runtime/driver call failed */
 #define BTB_ENODEVICE   6   /* no sm_100 device visible */
 #define BTB_ENOMEM      7
+#define BTB_ECOMM       8   /* multi-rank exchange: a peer failed, timed out, or has no peer-to-peer path */
 
 #define BTB_MAX_SEQ     100000      /* snp-dists 0.8.2 MAX_SEQ */
 
@@ -126,6 +127,30 @@ int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t ro
 
 /* btb_dist_matrix_host keeps its device buffers between calls; this frees them. */
 int btb_release_workspace(void);
+
+/* ---- the same for the ranks of a one-node job, one process per GPU ----
+ * btb_dist_matrix_host(rank, world) makes every rank upload and encode the whole alignment.  With a
+ * btb_comm the ranks share that work: rank r uploads and encodes samples [n r / P, n (r+1) / P) only, the
+ * encoded operand shards are exchanged GPU to GPU (CUDA IPC peer copies over NVLink, issued by the rank
+ * that needs the rows; no NCCL, no host staging), and each rank computes its btb_dist_row_share block rows
+ * and copies them into `out` band by band while later bands are computed.  `out` is normally ONE n x n
+ * matrix shared by all ranks (a shared-memory segment every rank has mapped and page-locked): the ranks
+ * write disjoint cells, and after the last rank returns it holds the whole matrix, both triangles.
+ *
+ * btb_comm_create: collective over the `world` ranks of the job.  `name` is a POSIX shared-memory name
+ * unique to the job (rank 0 creates "/name", the others attach; it is unlinked again once all have).
+ * A comm on which any call failed is dead (every later call returns BTB_ECOMM): destroy it.
+ * Alphabets / engines without an exchange path (POPC bit-planes, int8 operands of very long rows) fall
+ * back to the replicated upload; btb_query("comm_last_path") tells which path the last call took. */
+typedef struct btb_comm btb_comm;
+int btb_comm_create(const char *name, int rank, int world, int device, btb_comm **comm);
+int btb_comm_destroy(btb_comm *comm);
+int btb_dist_matrix_host_comm(btb_comm *comm, const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                              int allchars, int keepcase, int engine,
+                              void *out, int out_elem_bytes, int64_t out_ld);
+/* wall-clock seconds of the phases of the last call on this rank: upload + presence scan, barrier A, buffers +
+ * site counts, barrier B, encode, wait for peers + NVLink copies, distance kernels + D2H (7 values) */
+int btb_comm_last_timings(const btb_comm *comm, double *seconds, int cap);
 
 /* Variable columns of an n x G alignment held as dense rows: keep[k] = 1 where snp-sites keeps
  * column k; returns their count in *n_snps.  snps_out (may be NULL) receives n rows of *n_snps

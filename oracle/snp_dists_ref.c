@@ -22,7 +22,9 @@
  *
  * Build:  make -C oracle   (gcc -O3 -std=c99 -fopenmp, the upstream Makefile's flags; links zlib)
  * Library entry points (ctypes; tests and bench.py's cpu_baseline only):
- *   oracle_snp_dists_rows()  -- rows [row0,row1) of the matrix for in-memory sequences.
+ *   oracle_snp_dists_rows()  -- rows [row0,row1) of the matrix for in-memory sequences;
+ *   oracle_snp_dists_prepare() / _rows_prepared() / _release() -- the same split into snp-dists' load step
+ *   (once) and its loop nest (what bench.py's CPU arm times).
  */
 #include <ctype.h>
 #include <stdint.h>
@@ -51,14 +53,24 @@ static void ref_prepare(char *s, size_t L, int allchars, int keepcase) {
             if (s[i] != 'A' && s[i] != 'C' && s[i] != 'G' && s[i] != 'T') s[i] = REF_IGNORE;
 }
 
-/* In-memory form: seqs = n rows of L raw bytes.  Writes rows [row0,row1) x n as uint32 into out
- * (row-major, (row1-row0) x n).  Mirrors the upstream loop nest: outer row j serial, inner i parallel. */
-int oracle_snp_dists_rows(const char *seqs, long n, long L, int allchars, int keepcase,
-                          int threads, long row0, long row1, uint32_t *out) {
+/* In-memory forms.  snp-dists loads and prepares every sequence ONCE (main() below does the same), then
+ * computes the square row by row: oracle_snp_dists_prepare() is that load step, and
+ * oracle_snp_dists_rows_prepared() the loop nest -- outer row j serial, inner i the OpenMP parallel-for --
+ * writing rows [row0,row1) x n as uint32 into out (row-major).  bench.py times the second only. */
+char *oracle_snp_dists_prepare(const char *seqs, long n, long L, int allchars, int keepcase) {
     char *p = (char *)malloc((size_t)n * (size_t)L + 1);
-    if (!p) return 2;
-    memcpy(p, seqs, (size_t)n * (size_t)L);
-    for (long i = 0; i < n; i++) ref_prepare(p + (size_t)i * L, (size_t)L, allchars, keepcase);
+    if (!p) return NULL;
+#pragma omp parallel for
+    for (long i = 0; i < n; i++) {
+        memcpy(p + (size_t)i * L, seqs + (size_t)i * L, (size_t)L);
+        ref_prepare(p + (size_t)i * L, (size_t)L, allchars, keepcase);
+    }
+    return p;
+}
+
+void oracle_snp_dists_release(char *prepared) { free(prepared); }
+
+int oracle_snp_dists_rows_prepared(const char *p, long n, long L, int threads, long row0, long row1, uint32_t *out) {
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
 #endif
@@ -68,8 +80,17 @@ int oracle_snp_dists_rows(const char *seqs, long n, long L, int allchars, int ke
         for (long i = 0; i < n; i++)
             d[i] = (uint32_t)ref_distance(p + (size_t)j * L, p + (size_t)i * L, (size_t)L);
     }
-    free(p);
     return 0;
+}
+
+/* prepare + rows + release in one call (tests) */
+int oracle_snp_dists_rows(const char *seqs, long n, long L, int allchars, int keepcase,
+                          int threads, long row0, long row1, uint32_t *out) {
+    char *p = oracle_snp_dists_prepare(seqs, n, L, allchars, keepcase);
+    if (!p) return 2;
+    int rc = oracle_snp_dists_rows_prepared(p, n, L, threads, row0, row1, out);
+    free(p);
+    return rc;
 }
 
 #ifndef ORACLE_NO_MAIN

@@ -152,37 +152,47 @@ def test_full_genome_width_property(ph, oracle, tmp_path):
     assert sf.read_bytes() == o_sf.read_bytes()
 
 
-def test_multi_gpu_file_path_same_bytes(capi, oracle, tmp_path):
-    """n_gpus = 2 (bands of block rows dealt to the devices, host assembly) writes the same snps.csv
-    as one GPU and as the oracle.  Needs two visible devices (gpurun --gpus 2)."""
-    if capi.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    n, L = 4500, 700
+@pytest.fixture
+def workers_share_devices(capi):
+    """Multi-GPU level-1 calls on a box with fewer GPUs than workers: several workers per device
+    (the sharding, exchange and assembly logic is the same; only the speed-up is missing)."""
+    capi.check(capi.lib().btb_set_option(b"multi_gpu_oversubscribe", 1))
+    yield
+    capi.check(capi.lib().btb_set_option(b"multi_gpu_oversubscribe", 0))
+
+
+@pytest.mark.parametrize("workers", [2, 3])
+def test_multi_gpu_file_path_same_bytes(capi, oracle, tmp_path, workers_share_devices, workers):
+    """n_gpus > 1 (one host thread per device, sharded upload, operand shards exchanged GPU to GPU,
+    block rows per device, one host matrix) writes the same snps.csv as one GPU and as the oracle."""
+    n, L = 6400, 700
     names = synth.sample_names(n)
     seqs = synth.snp_alignment(n, L, seed=6, heavy_n=0.05)
     sf = tmp_path / "snps.fas"
     synth.write_fasta(str(sf), names, seqs, wrap=0)
     outs = []
-    for gpus in (1, 2):
+    for gpus in (1, workers):
         out = tmp_path / ("snps_%d.csv" % gpus)
         capi.check(capi.lib().btb_snp_dists(str(sf).encode(), str(out).encode(), 0, 0, 0, b",", 1, 1, gpus, 8, -1, None, None))
         outs.append(out.read_bytes())
     assert outs[0] == outs[1]
     assert outs[0] == oracle.format_matrix(names, oracle.snp_dists_rows(seqs, threads=8))
+    v = ctypes.c_int64(-1)
+    capi.check(capi.lib().btb_query(b"comm_last_path", ctypes.byref(v)))
+    assert v.value == 1                      # the sharded path ran, not the replicated fallback
 
 
-def test_multi_gpu_snp_sites_same_bytes(capi, oracle, tmp_path):
-    """n_gpus = 2: samples are dealt to the devices, the per-device column states are OR-ed on the
+@pytest.mark.parametrize("workers", [2, 5])
+def test_multi_gpu_snp_sites_same_bytes(capi, oracle, tmp_path, workers_share_devices, workers):
+    """n_gpus > 1: samples are dealt to the devices, the per-device column states are OR-ed on the
     host, every device compacts its own samples.  Same snps.fas as one GPU and as the oracle."""
-    if capi.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
     n, G = 37, 250007
     names = synth.sample_names(n)
     aln = synth.genome_alignment(n, G, 3000, seed=41, n_frac=0.02, lower=0.01)
     mf = tmp_path / "multi_fasta.fas"
     mf.write_bytes(synth.fasta_bytes(names, aln, wrap=[60, 70, 0, 31], eol=b"\n"))
     outs = []
-    for gpus in (1, 2):
+    for gpus in (1, workers):
         out = tmp_path / ("snps_%d.fas" % gpus)
         L = ctypes.c_int64(0)
         capi.check(capi.lib().btb_snp_sites(str(mf).encode(), str(out).encode(), 1, gpus, 8, None, None, ctypes.byref(L)))
