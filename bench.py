@@ -6,10 +6,12 @@ sites, distance stage), one process per GPU.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of the hot path over the whole alignment: SNP alignment bytes resident in HBM
--> operand encode -> tcgen05 kind::i8 distance GEMM over this rank's share of upper-triangle tiles
+-> operand encode -> tcgen05 kind::mxf4 distance GEMM (exact 0/1 products) over this rank's block rows
 -> distances in HBM.  `value` = unique pairs N(N-1)/2 of the whole job / max-over-ranks device
-time.  `e2e` = the same through the C-ABI's host-buffer call (btb_dist_matrix_host): pinned host
-alignment in, H2D, encode, GEMM, D2H of the rank's distances, pinned host matrix out.
+time.  `e2e` = the same through the C-ABI's host-buffer call: page-locked host alignment in, H2D,
+encode, GEMM, D2H, page-locked host matrix out (N = 1: btb_dist_matrix_host; N > 1:
+btb_dist_matrix_host_comm -- sharded upload, operand shards GPU to GPU, ONE shared host matrix).
+`snps_csv` = wall clock of build_snp_matrix() file to file (BASELINE metric, second half).
 `--impl reference` times the CPU arm (the restated snp-dists 0.8.2 loop nest, all host threads)
 on a bounded sample of the same workload.  SURVEY.md section 8d defines work and peaks.
 """
@@ -207,6 +209,155 @@ def bind_to_gpu_numa_node(local):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def _shared_array(path, shape, dtype, create):
+    """A file under /dev/shm mapped by every rank: ONE alignment and ONE matrix for the whole job."""
+    import numpy as np
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if create:
+        with open(path, "wb") as f:
+            f.truncate(nbytes)
+    return np.memmap(path, dtype=dtype, mode="r+", shape=shape)
+
+
+def _page_lock(arr):
+    import torch
+    rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+    if int(rc) != 0:
+        raise RuntimeError("cudaHostRegister failed: %s" % rc)
+
+
+def _page_unlock(arr):
+    import torch
+    torch.cuda.cudart().cudaHostUnregister(arr.ctypes.data)
+
+
+def e2e_single(lib, _capi, torch, seqs, plan, n, L, local, steps):
+    """N = 1: btb_dist_matrix_host, pinned host alignment in, pinned host matrix out."""
+    h_seqs = torch.empty((n, seqs.shape[1]), dtype=torch.uint8, pin_memory=True)
+    h_seqs.copy_(seqs)
+    ld = (n + 7) // 8 * 8
+    h_out = torch.zeros((n, ld), dtype=plan.out_dtype, pin_memory=True)
+
+    def call():
+        _capi.check(lib.btb_dist_matrix_host(ctypes.c_void_p(h_seqs.data_ptr()), n, L, h_seqs.stride(0), 0, 0,
+                                             _capi.ENGINE_UMMA, local, 0, 1, ctypes.c_void_p(h_out.data_ptr()),
+                                             plan.elem, ld), "btb_dist_matrix_host")
+    call()                                                         # warm-up (allocations, page touching)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    info = {"call": "btb_dist_matrix_host (C-ABI level 2): pinned host alignment -> H2D -> encode -> distance kernels -> D2H band by band -> pinned host matrix",
+            "h2d_bytes_per_step": int(n * L), "d2h_bytes_per_step": int(n * n * plan.elem)}
+    return e2e_s, info, h_seqs.numpy()[:, :L], h_out.numpy()[:, :n], (h_seqs, h_out)
+
+
+def e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, local, steps):
+    """N > 1: btb_dist_matrix_host_comm.  ONE page-locked alignment and ONE page-locked matrix in shared
+    memory; rank r uploads and encodes samples [n r / N, n (r+1) / N), the operand shards are exchanged
+    GPU to GPU (CUDA IPC peer copies), every rank copies its block rows into the one matrix."""
+    import numpy as np
+    tag = [None]
+    if rank == 0:
+        tag[0] = "btbphylo_bench_%d_%s" % (os.getpid(), os.urandom(4).hex())
+    dist.broadcast_object_list(tag, src=0, group=host_pg)
+    tag = tag[0]
+    stride = seqs.shape[1]
+    p_seqs, p_mat = "/dev/shm/%s.seqs" % tag, "/dev/shm/%s.mat" % tag
+    out_np = np.uint16 if plan.elem == 2 else np.uint32
+    if rank == 0:
+        a = _shared_array(p_seqs, (n, stride), np.uint8, True)
+        a[:] = seqs.cpu().numpy()
+        _shared_array(p_mat, (n, n), out_np, True)
+        del a
+    dist.barrier(group=host_pg)
+    h_seqs = _shared_array(p_seqs, (n, stride), np.uint8, False)
+    h_out = _shared_array(p_mat, (n, n), out_np, False)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    h_out[lo:hi] = 0                                               # first touch of "my" rows next to my GPU
+    _page_lock(h_seqs)
+    _page_lock(h_out)
+    comm = ctypes.c_void_p()
+    _capi.check(lib.btb_comm_create(tag.encode(), rank, world, local, ctypes.byref(comm)), "btb_comm_create")
+
+    def call():
+        _capi.check(lib.btb_dist_matrix_host_comm(comm, ctypes.c_void_p(h_seqs.ctypes.data), n, L, stride, 0, 0, _capi.ENGINE_UMMA,
+                                                  ctypes.c_void_p(h_out.ctypes.data), plan.elem, n), "btb_dist_matrix_host_comm")
+    call()
+    torch.cuda.synchronize()
+    dist.barrier(group=host_pg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    phases = (ctypes.c_double * 8)()
+    lib.btb_comm_last_timings(comm, phases, 8)
+    path = ctypes.c_int64(-1)
+    lib.btb_query(b"comm_last_path", ctypes.byref(path))
+    dist.barrier(group=host_pg)                                                  # every rank's cells are in the matrix
+    _capi.check(lib.btb_comm_destroy(comm), "btb_comm_destroy")
+    names = ["upload_shard+presence", "barrier_A", "buffers+site_counts", "barrier_B", "encode_shard", "wait+nvlink_pull", "kernels+d2h"]
+    info = {"call": "btb_dist_matrix_host_comm (C-ABI level 2, one process per GPU): ONE page-locked alignment and ONE page-locked matrix in "
+                    "shared memory; sharded upload + encode, operand shards GPU to GPU over NVLink (CUDA IPC peer copies, no NCCL), "
+                    "block rows per rank, D2H band by band",
+            "h2d_bytes_per_step": int(n * L), "d2h_bytes_per_step": int(n * n * plan.elem),
+            "bytes_are": "summed over all ranks (each rank moves about 1/N of both)",
+            "path": "sharded" if path.value == 1 else "replicated-upload fallback",
+            "rank0_phase_ms": {k: round(phases[i] * 1e3, 3) for i, k in enumerate(names)}}
+
+    def cleanup():
+        _page_unlock(h_seqs)
+        _page_unlock(h_out)
+        dist.barrier(group=host_pg)
+        if rank == 0:
+            os.unlink(p_seqs)
+            os.unlink(p_mat)
+    return e2e_s, info, h_seqs[:, :L], h_out, cleanup
+
+
+def csv_wall(seqs_host, n_gpus, threads):
+    """BASELINE metric, second half: wall clock of build_snp_matrix() (the reference's entry point,
+    btbphylo/phylogeny.py:144-150), snps.fas file in -> snps.csv file out, on tmpfs and on the box's disk."""
+    from btb_phylo_b200 import phylogeny, synth
+    n, L = seqs_host.shape
+    res = {"entry_point": "btb_phylo_b200.phylogeny.build_snp_matrix(snps.csv, snps.fas, threads=%d), BTBPHYLO_GPUS=%d" % (threads, n_gpus),
+           "n_gpus": n_gpus, "host_threads": threads}
+    os.environ["BTBPHYLO_GPUS"] = str(n_gpus)
+    names = synth.sample_names(n)
+    for label, base in (("tmpfs", "/dev/shm"), ("disk", os.environ.get("BTB_BENCH_DISK_DIR", os.path.join(ROOT, "gpurun_out")))):
+        d = os.path.join(base, "btb_bench_csv_%d" % os.getpid())
+        try:
+            os.makedirs(d, exist_ok=True)
+            sf, sc = os.path.join(d, "snps.fas"), os.path.join(d, "snps.csv")
+            synth.write_fasta(sf, names, seqs_host, wrap=0)
+            walls = []
+            for _ in range(2):                                      # first call of a process pays CUDA context + library load
+                if os.path.exists(sc):
+                    os.unlink(sc)
+                t0 = time.perf_counter()
+                phylogeny.build_snp_matrix(sc, sf, threads=threads)
+                walls.append(time.perf_counter() - t0)
+            size = os.path.getsize(sc)
+            res[label] = {"csv_wall_s": min(walls), "first_call_s": walls[0], "snps_csv_bytes": size,
+                          "csv_GBps": size / min(walls) / 1e9, "cells_per_s": n * n / min(walls), "dir": base}
+        except Exception as exc:                                     # noqa: BLE001 -- e.g. no space: report, do not lose the run
+            res[label] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        finally:
+            for fn in ("snps.fas", "snps.csv"):
+                try:
+                    os.unlink(os.path.join(d, fn))
+                except OSError:
+                    pass
+            try:
+                os.rmdir(d)
+            except OSError:
+                pass
+    return res
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -221,8 +372,10 @@ def gpu_arm(args):
     device = torch.device("cuda", local)
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local)
+    host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        host_pg = dist.new_group(backend="gloo")                    # host-side barriers that keep the GPUs free
     lib = _capi.lib()
     n, L = N_SAMPLES, N_SITES
 
@@ -254,7 +407,6 @@ def gpu_arm(args):
         step()
     sync_all()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
-    kern_ms = []
     t_timed0 = time.perf_counter()
     ev[0].record()
     for s in range(args.steps):
@@ -272,36 +424,22 @@ def gpu_arm(args):
     total_ms, kernel_ms = float(t[0]), float(t[1])
     ms_per_step = total_ms / args.steps
     value = unique_pairs(n) / (ms_per_step * 1e-3)
-
-    # ---- end to end through the C-ABI host call: pinned host in, pinned host out ---------------
-    h_seqs = torch.empty((n, seqs.shape[1]), dtype=torch.uint8, pin_memory=True)
-    h_seqs.copy_(seqs)
-    elem = plan.elem
-    ld = (n + 7) // 8 * 8
-    h_out = torch.zeros((n, ld), dtype=plan.out_dtype, pin_memory=True)
     del out
     torch.cuda.empty_cache()
 
-    def e2e_step():
-        _capi.check(lib.btb_dist_matrix_host(ctypes.c_void_p(h_seqs.data_ptr()), n, L, h_seqs.stride(0), 0, 0,
-                                             _capi.ENGINE_UMMA, local, rank, world, ctypes.c_void_p(h_out.data_ptr()),
-                                             elem, ld), "btb_dist_matrix_host")
-
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()                                                     # warm-up (allocations, page touching)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # ---- end to end through the C-ABI host call: page-locked host alignment in, page-locked host matrix out ----
+    e2e_steps = max(1, min(args.steps, 5))
+    if world == 1:
+        e2e_s, e2e_info, h_seqs_np, h_out_np, keep = e2e_single(lib, _capi, torch, seqs, plan, n, L, local, e2e_steps)
+        cleanup = None
+    else:
+        e2e_s, e2e_info, h_seqs_np, h_out_np, cleanup = e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, local, e2e_steps)
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
-    r0, r1 = min(n, row_lo * 256), min(n, row_hi * 256)
-    d2h = n * n * elem if world == 1 else ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * elem
-    # what the box's PCIe link gives a plain pinned copy (context for e2e, which is bound by the 5 GB download)
+
+    # what the box's PCIe link gives a plain pinned copy (context for e2e)
     def _copy_rate(dst, src):
         best = 0.0
         for _ in range(2):
@@ -311,87 +449,98 @@ def gpu_arm(args):
             torch.cuda.synchronize()
             best = max(best, src.numel() * src.element_size() / (time.perf_counter() - t0c) / 1e9)
         return best
-    try:
-        probe_dev = torch.empty(min(h_seqs.numel(), 1 << 30), dtype=torch.uint8, device=device)
-        probe_host = h_seqs.view(-1)[: probe_dev.numel()]
-        pcie = {"h2d_GBps": _copy_rate(probe_dev, probe_host), "d2h_GBps": _copy_rate(probe_host.clone().pin_memory(), probe_dev)}
-        del probe_dev
-    except Exception as exc:                                         # noqa: BLE001 -- context only, never fatal
-        pcie = {"unavailable": type(exc).__name__}
-    e2e = {"value": unique_pairs(n) / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(n * L),
-           "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_s, "steps": e2e_steps,
-           "call": "btb_dist_matrix_host (C-ABI level 2; per-rank bytes)", "host_numa": numa,
-           "pcie_GBps": (n * L + d2h) / e2e_s / 1e9, "pcie_plain_copy": pcie}
+    pcie = None
+    if rank == 0:
+        try:
+            probe_host = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+            probe_dev = torch.empty(1 << 30, dtype=torch.uint8, device=device)
+            pcie = {"h2d_GBps": _copy_rate(probe_dev, probe_host), "d2h_GBps": _copy_rate(probe_host, probe_dev)}
+            del probe_dev, probe_host
+        except Exception as exc:                                     # noqa: BLE001 -- context only, never fatal
+            pcie = {"unavailable": type(exc).__name__}
+    e2e = {"value": unique_pairs(n) / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": e2e_info.pop("h2d_bytes_per_step"),
+           "d2h_bytes_per_step": e2e_info.pop("d2h_bytes_per_step"), "seconds_per_step": e2e_s, "steps": e2e_steps,
+           "host_numa": numa, "pcie_plain_copy_one_gpu": pcie}
+    e2e.update(e2e_info)
+    e2e["pcie_GBps_all_ranks"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / e2e_s / 1e9
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        if cleanup:
+            cleanup()
+        del plan, seqs
+        lib.btb_release_workspace()
+        torch.cuda.empty_cache()
+        dist.barrier(group=host_pg)                                 # rank 0: CPU baseline + snps.csv wall (uses every GPU itself)
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (the distance GEMM), measured live ---------------------
+    fp4 = bool(_query(lib, b"umma_fp4")) and plan.sigma == _capi.SIGMA_DENSE4 and _query(lib, b"umma_dense_simplex") == 2
+    pair = bool(_query(lib, b"umma_fp4_pair")) and fp4
+    dense_code = _query(lib, b"umma_dense_simplex")
+    planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
+    share = my_tiles / multirank.tile_count(n)                       # rank 0's launch
+    useful_ops = 2.0 * planes_executed * L * unique_pairs(n) * share
+    algorithmic_ops = 2.0 * SIGMA * L * unique_pairs(n) * share
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_mhz = clocks.get("sm_mhz") or 0.0
+    # tensor-pipe issue rate of the MMA shape the kernel uses, measured on this GPU with a kernel that
+    # issues the same instructions without data movement (btb_query probe_cg<cta_group>_e1: clk x 100 per
+    # pipeline stage of 8 MMAs 128 x 240 x 64 per SM): flop / clk / SM
+    probe = _query(lib, b"probe_cg2_e1" if pair else b"probe_cg1_e1") / 100.0 if fp4 else 0.0
+    stage_flop = 8 * 2.0 * 128 * 240 * 64
+    flop_per_clk_sm = stage_flop / probe if probe > 0 else (32768.0 if fp4 else 16384.0)
+    peak = flop_per_clk_sm * sms * sm_mhz * 1e6 / 1e12 if sm_mhz else None
+    achieved = useful_ops / (kernel_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-    bf16_src = "bf16_tflops_sustained of MEASURED_PEAKS.json" if bf16 else "1.59 PFLOP/s fallback of B200_PROFILING.md"
-    bf16 = bf16 or 1590.0
-    fp4 = bool(_query(lib, b"umma_fp4")) and plan.sigma == _capi.SIGMA_DENSE4 and _query(lib, b"umma_dense_simplex") == 2
-    # the tensor pipe's rate for the operand type the kernel multiplies: int8 = 2 x bf16, e2m1 (kind::mxf4) = 4 x bf16
-    peak = (4.0 if fp4 else 2.0) * bf16
-    peak_src = "%d x %s (%s runs at %dx the bf16 rate on sm_100; SURVEY.md 8d uses the int8 figure = %.1f)" % (
-        4 if fp4 else 2, bf16_src, "kind::mxf4 e2m1" if fp4 else "kind::i8", 4 if fp4 else 2, 2.0 * bf16)
-    ops_per_launch = 2.0 * SIGMA * L * unique_pairs(n) * my_tiles / multirank.tile_count(n)   # this rank's launch
-    achieved = ops_per_launch / (kernel_ms * 1e-3) / 1e12
-    int8_lib = None
-    try:                                                            # context only: cuBLAS int8 GEMM on this GPU
-        a8 = torch.randint(-2, 2, (8192, 8192), dtype=torch.int8, device=device)
-        b8 = torch.randint(-2, 2, (8192, 8192), dtype=torch.int8, device=device)
-        best = 1e9
-        for _ in range(6):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); torch._int_mm(a8, b8); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        int8_lib = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
-    except Exception:
-        pass
-    dense_code = _query(lib, b"umma_dense_simplex")
-    planes_executed = 3 if (plan.sigma == _capi.SIGMA_DENSE4 and dense_code in (1, 2)) else 4
-    nominal = 9000.0 if fp4 else 4500.0
-    pair = bool(_query(lib, b"umma_fp4_pair")) and fp4
-    roofline = {"bound": "tensor", "kernel": ("dist_umma_fp4_pair_kernel (tcgen05.mma cta_group::2 kind::mxf4, exact 0/1 products)" if pair else
-                                              "dist_umma_fp4_tile_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)") if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
-                "achieved": achieved, "peak": peak, "peak_int8_basis": 2.0 * bf16, "frac_int8_basis": achieved / (2.0 * bf16),
-                "executed_over_algorithmic": planes_executed / 4.0, "achieved_executed": achieved * planes_executed / 4.0,
-                "note": "algorithmic work counts sigma = 4 planes per site (SURVEY.md 8d); dense alignments run a 3-element-per-site "
-                        "tetrahedron code, so the tensor pipe executes 3/4 of that: achieved_executed is the hardware rate",
-                "why_frac_exceeds_1": "two independent reasons: (1) the kernel executes only executed_over_algorithmic of the ops `achieved` counts; "
-                                      "(2) `peak` scales the MEASURED sustained bf16 GEMM rate (dense random data, power-capped near 1.3 GHz) to the "
-                                      "operand type, while this kernel's sparse 0/1 operands run at 1.85-1.97 GHz under the same 1 kW cap. The honest "
-                                      "utilisation figures are frac_of_nominal_executed and ncu's tensor-pipe-active share "
-                                      "(profiles/r01_dist_umma_fp4_pair_ncu_summary.txt: 89.8 %).",
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(n, L, world),
-                "peak_source": peak_src, "ops": "int8 multiply-add = 2 ops; 2*sigma*L*N(N-1)/2 with sigma=4 (padding, diagonal tiles = overhead)",
-                "kernel_ms": kernel_ms, "peak_nominal_dense": nominal, "frac_of_nominal": achieved / nominal,
-                "frac_of_nominal_executed": achieved * planes_executed / 4.0 / nominal,
-                "cublas_int8_8192_measured": int8_lib}
+    bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+    roofline = {"bound": "tensor",
+                "kernel": ("dist_umma_fp4_pair_kernel (tcgen05.mma cta_group::2 kind::mxf4, exact 0/1 products)" if pair else
+                           "dist_umma_fp4_tile_kernel (tcgen05.mma kind::mxf4, exact 0/1 products)") if fp4 else "dist_umma_tile_kernel (tcgen05.mma kind::i8)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": _ncu_traffic(n, L, world), "kernel_ms": kernel_ms,
+                "achieved_is": "EXECUTED useful flop of this launch = 2 x %d elements per site x L x unique pairs of this rank's tiles / kernel time "
+                               "(CUDA events on the launching stream); padding of L to the K step, diagonal units and cells below the diagonal are not counted" % planes_executed,
+                "peak_is": "measured kind::mxf4 issue rate (%.0f flop/clk/SM from the data-free probe kernel: %.1f clk per 8-MMA stage) x %d SMs x the SM clock "
+                           "sampled by nvidia-smi inside the timed region (%.0f MHz)" % (flop_per_clk_sm, probe, sms, sm_mhz),
+                "algorithmic": {"ops_per_launch": algorithmic_ops, "tflops": algorithmic_ops / (kernel_ms * 1e-3) / 1e12,
+                                "note": "SURVEY.md 8d counts sigma = 4 planes per site; the dense tetrahedron code executes 3, so executed / algorithmic = %.2f" % (planes_executed / 4.0),
+                                "frac_int8_basis": algorithmic_ops / (kernel_ms * 1e-3) / 1e12 / (2.0 * bf16),
+                                "int8_basis_peak": 2.0 * bf16,
+                                "int8_basis_is": "cross-reference only: SURVEY.md 8d's provisional peak (2 x measured bf16) was written for a kind::i8 one-hot GEMM; "
+                                                 "this kernel multiplies e2m1 nibbles (kind::mxf4, 4 x the bf16 rate) and executes 3/4 of the ops, so this quotient exceeds 1 by construction"},
+                "peak_nominal_dense": 9000.0 if fp4 else 4500.0,
+                "frac_of_nominal": achieved / (9000.0 if fp4 else 4500.0)}
 
     # ---- CPU baseline on this box's host cores (bounded sample), also the parity spot-check -----
     os.sched_setaffinity(0, all_cpus)                                # the CPU arm gets every core again
     threads = os.cpu_count() or 1
-    arm = CpuArm(h_seqs.numpy()[:, :L], threads)
+    arm = CpuArm(np.ascontiguousarray(h_seqs_np), threads)
     rows = arm.rows_for(15.0)
     dt, cpu_rows = arm.time_rows(rows)
-    gpu_rows = h_out.numpy()[:rows, :n].astype(np.uint32)
-    owned = np.ones((rows, n), dtype=bool)                           # rank 0 owns block rows [0, row_hi): the
-    owned[r1:, r1:] = False                                          # first matrix rows are always among them
-    match = bool((gpu_rows[owned] == cpu_rows[owned]).all())
+    gpu_rows = np.asarray(h_out_np[:rows, :n]).astype(np.uint32)
+    match = bool((gpu_rows == cpu_rows).all())                      # whole matrix rows: every rank's cells are in the one matrix
     t_row = dt / rows
     cpu = {"value": unique_pairs(n) / (t_row * n), "unit": "pairs/s", "cores": threads, "kind": "port",
            "sample": "first " + arm.sample_text(rows, t_row), "t_row_s": t_row,
-           "rows_match_gpu": match, "cells_compared": int(owned.sum())}
+           "rows_match_gpu": match, "cells_compared": int(rows * n)}
+    seqs_host = np.ascontiguousarray(h_seqs_np)
+    del arm, cpu_rows, gpu_rows
+    if cleanup:
+        cleanup()
+    keep = None                                                       # noqa: F841 -- the pinned e2e buffers go before the file stage
+
+    # ---- BASELINE metric, second half: snps.csv wall time, file to file, through the reference's entry point ----
+    csv = None
+    if not os.environ.get("BTB_BENCH_NO_CSV"):
+        lib.btb_release_workspace()
+        del plan, seqs
+        torch.cuda.empty_cache()
+        csv = csv_wall(seqs_host, world, threads)
 
     # kernels of this library per timed step: operand encode (+ the two per-site majority kernels of the dense
     # FP4 code) and the distance kernel
@@ -400,15 +549,20 @@ def gpu_arm(args):
         "metric": "pairwise SNP distances/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "e2m1 x e2m1 -> fp32 (0/1 operands, exact integers)" if _query(lib, b"umma_fp4") else "int8 x int8 -> int32 (exact)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L, "engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", 2 if (_query(lib, b"umma_fp4") and _query(lib, b"umma_fp4_pair")) else _query(lib, b"umma_cta_group")), "options": os.environ.get("BTB_OPTIONS", ""),
-                   "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles, "block_rows_this_rank": [row_lo, row_hi], "sharding": "contiguous 256-row blocks with equal upper-triangle tile counts per rank, no collective",
-                   "l2_policy": "operands (12 GB one-hot) and output (5 GB) exceed the 126 MB L2; no flush needed",
-                   "timed_region": "operand encode + distance GEMM per step, CUDA events on the launching stream"},
+        "config": {"workload": WORKLOAD, "n_samples": n, "n_sites": L},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "snps_csv": csv,
+        "csv_wall_s": (csv or {}).get("tmpfs", {}).get("csv_wall_s"), "csv_wall_s_disk": (csv or {}).get("disk", {}).get("csv_wall_s"),
+        "details": {"engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", 2 if pair else _query(lib, b"umma_cta_group")),
+                    "options": os.environ.get("BTB_OPTIONS", ""), "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles,
+                    "block_rows_this_rank": [row_lo, row_hi],
+                    "sharding": "contiguous 256-row blocks with equal upper-triangle tile counts per rank, no collective on the compute path",
+                    "l2_policy": "operands (2.25 GB) and output (5 GB) exceed the 126 MB L2; no flush needed",
+                    "timed_region": "operand encode + distance kernels per step, CUDA events on the launching stream, max over ranks"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_pg)
         dist.destroy_process_group()
 
 

@@ -1,10 +1,13 @@
 // C-ABI of libbtbphylo.so: error plumbing, distance stage (levels 1-3).  See include/btb_phylo.h.
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <chrono>
+#include <condition_variable>
 #include <functional>
 #include <cstdarg>
 #include <cstring>
@@ -66,7 +69,10 @@ struct CommShared;
 CommShared *comm_shared_new(int world);
 void comm_shared_free(CommShared *sh);
 int comm_create_local(CommShared *sh, int rank, int world, int device, btb_comm **out);
-int g_csv_mmap = 0;             // "csv_mmap": write snps.csv through a file mapping, rows formatted in place by all host threads.
+int g_csv_prealloc = 1;          // "csv_prealloc": write() mode allocates the file's blocks before writing (see snp_dists_impl)
+int g_replace_unlink_first = 0;  // "replace_unlink_first": remove an existing output before the rename (see host_io.h)
+int g_csv_mmap = -1;            // "csv_mmap": -1 auto (mapped writes on tmpfs, write() elsewhere), 0 never, 1 always.
+            // "csv_mmap": write snps.csv through a file mapping, rows formatted in place by all host threads.
                                // Off: measured 3.5-3.9 s for the 12.2 GB C4 file against 2.7-3.1 s for write() -- shared-mapping
                                // write faults cost more than the buffered write path, and formatting (0.4 s) hides behind either.
 int g_dense_pageable = 1;      // "dense_pageable": alignments above 256 MB are read into pageable memory
@@ -163,7 +169,9 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : 1; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
-    if (key && !strcmp(key, "csv_mmap")) { g_csv_mmap = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "csv_mmap")) { g_csv_mmap = value < 0 ? -1 : (value ? 1 : 0); return BTB_OK; }
+    if (key && !strcmp(key, "csv_prealloc")) { g_csv_prealloc = value ? 1 : 0; return BTB_OK; }
+    if (key && !strcmp(key, "replace_unlink_first")) { g_replace_unlink_first = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "dense_pageable")) { g_dense_pageable = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "host_stream")) { g_host_stream = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "multi_gpu_oversubscribe")) { g_oversubscribe = value ? 1 : 0; return BTB_OK; }
@@ -692,9 +700,12 @@ namespace {
 // Multi-GPU distance stage inside one process: one host thread per device, the
 // devices form an in-process btb_comm group -- each uploads and encodes 1/P of the samples, the operand
 // shards travel GPU to GPU (peer copies), every device computes its block rows and copies them into the
-// host matrix H (n x ld elements) band by band.  No collective library.  See dist_comm.cu.
+// matrix H (n x ld elements) band by band.  H is host memory or -- level 1 -- the matrix buffer of the first
+// device, which every device can write over NVLink: the CSV writer then serialises it exactly as in the
+// one-GPU case and no n x n host matrix is ever allocated (page-locking 5 GB costs 2 s, a pageable
+// target slows the copies down 6-fold; both measured).  No collective library.  See dist_comm.cu.
 int multi_gpu_matrix(const DenseFasta &df, const std::vector<int> &devs, int allchars, int keepcase, int engine, int eb,
-                     int64_t ld, char *H) {
+                     int64_t ld, void *H) {
     const int n_dev = int(devs.size());
     CommShared *sh = comm_shared_new(n_dev);
     if (!sh) return fail(BTB_ENOMEM, "out of host memory");
@@ -790,22 +801,138 @@ extern "C" int btb_relabel_csv(const char *in_csv, const char *out_csv, char sep
     if (!in_csv || !out_csv || !labels) return fail(BTB_EINVAL, "btb_relabel_csv: NULL argument");
     std::vector<std::string> lab;
     BTB_TRY(split_labels(labels, n_labels, lab));
-    const std::string tmp = std::string(out_csv) + ".tmp";
+    std::string tmp;
     int rc;
     {
         FileBytes fb;                                    // unmapped before the rename below
         BTB_TRY(load_file(in_csv, fb));
-        FILE *fo = fopen(tmp.c_str(), "wb");
-        if (!fo) return fail(BTB_EIO, "cannot open '%s' for writing", tmp.c_str());
+        int fd = -1;
+        BTB_TRY(open_output_temp(out_csv, tmp, &fd));
+        FILE *fo = fdopen(fd, "wb");
+        if (!fo) { close(fd); discard_output(tmp); return fail(BTB_EIO, "cannot open '%s' for writing", tmp.c_str()); }
         setvbuf(fo, nullptr, _IOFBF, 1 << 22);
         rc = relabel_csv(fb, sep, lab, fo);
         if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp.c_str());
     }
-    if (rc != BTB_OK) { remove(tmp.c_str()); return rc; }
-    unlink(out_csv);
-    if (rename(tmp.c_str(), out_csv) != 0) { remove(tmp.c_str()); return fail(BTB_EIO, "cannot rename to '%s'", out_csv); }
+    if (rc != BTB_OK) { discard_output(tmp); return rc; }
+    return commit_output(tmp, out_csv, g_replace_unlink_first != 0);     // in == out (post_process_snps_csv): one atomic rename
+}
+
+
+namespace {
+
+bool write_all(int fd, const char *p, size_t left) {
+    while (left) {
+        const ssize_t k = write(fd, p, left);
+        if (k < 0 && errno == EINTR) continue;
+        if (k <= 0) return false;
+        p += k;
+        left -= size_t(k);
+    }
+    return true;
+}
+
+void parallel_rows(int64_t rows, int threads, const std::function<void(int64_t, int64_t)> &fn) {
+    const int T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), rows)));
+    if (T == 1) { fn(0, rows); return; }
+    std::vector<std::thread> pool;
+    const int64_t span = (rows + T - 1) / T;
+    for (int k = 0; k < T; ++k) {
+        const int64_t lo = k * span, hi = std::min(rows, lo + span);
+        if (lo < hi) pool.emplace_back(fn, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+}
+
+// write() mode of the CSV writer: the formatting threads fill block b into slot b % kSlots while the one
+// writer thread pushes earlier blocks out, in order (a file has one inode lock: more writers do not help).
+struct TextRing {
+    static constexpr int kSlots = 3;
+    std::vector<char> buf[kSlots];
+    size_t len[kSlots] = {0, 0, 0};
+    int64_t filled = 0, written = 0;          // blocks handed to / finished by the writer
+    bool failed = false, stop = false;
+    std::mutex m;
+    std::condition_variable cv;
+    void init(size_t slot_bytes) { for (auto &b : buf) b.resize(slot_bytes); }
+    char *acquire(int64_t b) {                // the slot of block b, once the writer is done with block b - kSlots
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [&] { return written > b - kSlots || failed || stop; });
+        return (failed || stop) ? nullptr : buf[b % kSlots].data();
+    }
+    void submit(int64_t b, size_t bytes) {
+        std::lock_guard<std::mutex> lock(m);
+        len[b % kSlots] = bytes;
+        filled = b + 1;
+        cv.notify_all();
+    }
+    void run(int fd, int64_t blocks) {
+        for (int64_t b = 0; b < blocks; ++b) {
+            {
+                std::unique_lock<std::mutex> lock(m);
+                cv.wait(lock, [&] { return filled > b || stop; });
+                if (filled <= b) return;
+            }
+            const bool ok = write_all(fd, buf[b % kSlots].data(), len[b % kSlots]);
+            std::lock_guard<std::mutex> lock(m);
+            if (!ok) failed = true;
+            written = b + 1;
+            cv.notify_all();
+            if (!ok) return;
+        }
+    }
+    bool finish(int64_t blocks) {
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [&] { return written >= blocks || failed || stop; });
+        return !failed;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lock(m);
+        stop = true;
+        cv.notify_all();
+    }
+};
+
+// k5 on the device: bytes of text the cells of one matrix row take (one separator + the decimal digits per
+// cell) -- one CTA per row, 16-byte loads.  HBM-bound: n * n * elem bytes read once.
+template <typename T>
+__global__ void __launch_bounds__(256) csv_row_len_kernel(const T *__restrict__ mat, int64_t ld, int64_t n, unsigned long long *__restrict__ out) {
+    constexpr int kPer = 16 / int(sizeof(T));
+    const T *row = mat + int64_t(blockIdx.x) * ld;
+    unsigned int s = 0;
+    for (int64_t c = int64_t(threadIdx.x) * kPer; c < n; c += 256 * kPer) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + c);          // ld is a multiple of 8 elements: 16-byte aligned, padded
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (c + k >= n) break;
+            uint32_t x;
+            if constexpr (sizeof(T) == 2) x = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu; else x = w[k];
+            s += 1u + (x > 9u) + (x > 99u) + (x > 999u) + (x > 9999u);
+            if constexpr (sizeof(T) == 4) s += (x > 99999u) + (x > 999999u) + (x > 9999999u) + (x > 99999999u) + (x > 999999999u);
+        }
+    }
+    __shared__ unsigned int part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 8; ++k) t += part[k];
+        out[blockIdx.x] = t + (unsigned long long)n;                          // + one separator per cell
+    }
+}
+
+int csv_row_lengths(const void *d_mat, int eb, int64_t ld, int64_t n, unsigned long long *d_len, cudaStream_t st) {
+    if (n <= 0) return BTB_OK;
+    if (eb == 2) csv_row_len_kernel<uint16_t><<<unsigned(n), 256, 0, st>>>(static_cast<const uint16_t *>(d_mat), ld, n, d_len);
+    else csv_row_len_kernel<uint32_t><<<unsigned(n), 256, 0, st>>>(static_cast<const uint32_t *>(d_mat), ld, n, d_len);
+    BTB_CUDA(cudaGetLastError());
     return BTB_OK;
 }
+
+}  // namespace
 
 static int snp_dists_impl(const char *in_fasta, const char *out_path, int allchars, int keepcase, int molten,
                           char sep, int corner, int quiet, int n_gpus, int host_threads, int engine,
@@ -854,27 +981,36 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     const int eb = len < 65536 ? 2 : 4;
     const int64_t ld = (n + 7) / 8 * 8;
 
-    cudaStream_t st, st2;
+    cudaStream_t st = nullptr, st2 = nullptr;
     BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     BTB_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
     uint8_t *d_seqs = nullptr, *d_ops = nullptr, *d_out = nullptr;
+    unsigned long long *d_rowlen = nullptr;
     char *h_stage[2] = {nullptr, nullptr};
-    char *h_full = nullptr;            // multi-GPU: the devices fill this pinned matrix, then it is formatted
-    FILE *fo = nullptr;
     const bool to_stdout = !strcmp(out_path, "-") || !strcmp(out_path, "/dev/stdout");
-    std::string tmp_path = to_stdout ? std::string("/dev/stdout") : std::string(out_path) + ".tmp";
-    std::thread *writer_ptr = nullptr;
-    char *map = nullptr;               // snps.csv written through a mapping (see below)
-    size_t map_bytes = 0, map_off = 0;
+    int fd = to_stdout ? STDOUT_FILENO : -1;
+    std::string tmp_path;
+    char *map = nullptr;               // snps.csv written through a mapping (tmpfs, see below)
+    size_t map_bytes = 0;
+    std::thread prealloc;              // fallocate of the mapped file, chunk by chunk, beside everything else
+    std::atomic<size_t> prealloc_limit{0}, prealloc_done{0};
+    std::atomic<bool> prealloc_over{false};    // the helper has stopped (finished, or fallocate is not supported here)
+    TextRing ring;                     // write() mode: formatted blocks on their way to the writer thread
+    std::thread writer;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     auto cleanup = [&]() {
-        if (writer_ptr && writer_ptr->joinable()) writer_ptr->join();
+        ring.abort();
+        if (writer.joinable()) writer.join();
+        prealloc_limit = 0;
+        if (prealloc.joinable()) prealloc.join();
         if (map) { munmap(map, map_bytes); map = nullptr; }
-        cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out);
+        cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out); cudaFree(d_rowlen);
         if (h_stage[0]) cudaFreeHost(h_stage[0]);
         if (h_stage[1]) cudaFreeHost(h_stage[1]);
-        if (h_full) cudaFreeHost(h_full);
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        if (ev[1]) cudaEventDestroy(ev[1]);
         cudaStreamDestroy(st); cudaStreamDestroy(st2);
-        if (fo) { fclose(fo); if (!to_stdout) remove(tmp_path.c_str()); }
+        if (fd >= 0 && !to_stdout) { close(fd); fd = -1; discard_output(tmp_path); }
     };
 #define L1_CUDA(call)                                                                                     \
     do {                                                                                                  \
@@ -886,190 +1022,204 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         }                                                                                                 \
     } while (0)
 #define L1_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
+#define L1_FAIL(...) do { rc = fail(__VA_ARGS__); cleanup(); return rc; } while (0)
+
+    // ---- the output file is opened (and, on tmpfs, sized, mapped and preallocated by a helper thread)
+    //      while the GPUs work
+    if (!to_stdout) L1_TRY(open_output_temp(out_path, tmp_path, &fd));
+    std::string head;
+    if (!molten) {
+        head = corner ? "snp-dists 0.8.2" : "";
+        for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
+        head.push_back('\n');
+        if (!write_all(fd, head.data(), head.size())) L1_FAIL(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
+    }
+    std::vector<size_t> name_len(static_cast<size_t>(n));
+    size_t names_total = 0;
+    for (int64_t i = 0; i < n; ++i) { name_len[size_t(i)] = df.names[size_t(i)].size(); names_total += name_len[size_t(i)]; }
+    // Buffered write()s to one file serialise on its inode whatever the number of writers (measured on
+    // the B200 boxes, tools/io_probe.cpp: 5.4 GB/s on the ext4 disk, 3.2 GB/s on tmpfs, for 1 or 16 writers;
+    // 16 threads writing 16 FILES reach 32-36 GB/s).  On tmpfs a shared mapping of the preallocated file
+    // takes 8.8 GB/s from 16 threads (page faults need no inode lock); on ext4 mapped writes are slower
+    // than write() (4.5-5.1 GB/s: page_mkwrite journals every page).  So: tmpfs -> the file is sized to an
+    // upper bound of the text, mapped, and preallocated chunk by chunk by a helper thread that starts NOW
+    // (beside the upload and the distance kernels) and stops at the exact text size once that is known;
+    // all host threads format their rows straight into the mapping, block by block, each block as soon as
+    // the helper has passed its end (threads that fault fresh pages in while fallocate runs slow both down:
+    // 1.66 s of formatting instead of 0.5 s, measured); the file is cut to its real length at the end.  Anything else -> formatted blocks go through a ring to one writer thread and write().
+    const bool want_map = !to_stdout && !molten && n >= 1024 && (g_csv_mmap == 1 || (g_csv_mmap < 0 && on_memory_fs(out_path)));
+    if (want_map) {
+        const size_t bound = head.size() + names_total + size_t(n) + size_t(n) * size_t(n) * size_t(eb == 2 ? 6 : 11);
+        if (ftruncate(fd, off_t(bound)) == 0) {
+            void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            if (m != MAP_FAILED) { map = static_cast<char *>(m); map_bytes = bound; }
+            else if (ftruncate(fd, off_t(head.size())) != 0) L1_FAIL(BTB_EIO, "cannot size '%s'", tmp_path.c_str());
+        }
+        if (map) {
+            prealloc_limit = bound;
+            const int pfd = fd;
+            const size_t from = head.size();
+            prealloc_done = from;
+            prealloc = std::thread([pfd, from, &prealloc_limit, &prealloc_done, &prealloc_over] {
+                constexpr size_t kChunk = size_t(128) << 20;
+                for (size_t done = from; done < prealloc_limit.load(std::memory_order_acquire);) {
+                    const size_t len = std::min(kChunk, prealloc_limit.load(std::memory_order_acquire) - done);
+                    if (fallocate(pfd, 0, off_t(done), off_t(len)) != 0) break;       // unsupported: the formatters fault the pages in
+                    done += len;
+                    prealloc_done.store(done, std::memory_order_release);
+                }
+                prealloc_over.store(true, std::memory_order_release);
+            });
+        }
+    }
+
+    // ---- distance stage -------------------------------------------------------------------------------------
     std::vector<int> devs = worker_devices(n_gpus);
     const int n_dev = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(devs.size()), tiles_per_dim(n) / kBand)));
     devs.resize(size_t(n_dev));
+    std::vector<unsigned long long> cells_len(static_cast<size_t>(n), 0);       // text bytes of row r's cells (separators + digits)
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)));
+    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_rowlen), size_t(n) * 8));
     if (n_dev > 1) {
-        L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_full), size_t(n * ld * eb)));
-        rc = multi_gpu_matrix(df, devs, allchars, keepcase, engine, eb, ld, h_full);
+        // every device computes its block rows and writes them into the first device's matrix (NVLink)
+        rc = multi_gpu_matrix(df, devs, allchars, keepcase, engine, eb, ld, d_out);
         if (rc != BTB_OK) { cleanup(); return rc; }
         L1_TRY(require_device(devs[0]));
+        timer.mark("sharded H2D + encode + exchange + distance kernels + assembly on device 0");
+    } else {
+        uint8_t table[256];
+        int sigma = 4;
+        L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)));
+        L1_CUDA(cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st));
+        L1_TRY(btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st));
+        const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
+        L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
+        L1_TRY(btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st));
+        L1_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, 0, tile_count(n), d_out, eb, ld, 0, 1, st));
     }
-    uint8_t table[256];
-    int sigma = 4;
-    if (n_dev == 1) {
-    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_seqs), size_t(n * df.stride)));
-    L1_CUDA(cudaMemcpyAsync(d_seqs, df.rows, size_t(n * df.stride), cudaMemcpyHostToDevice, st));
-    L1_TRY(btb_dist_alphabet(d_seqs, n, len, df.stride, allchars, keepcase, table, &sigma, st));
-    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), size_t(n * ld * eb)));
-    const int eng = pick_engine(engine, len, btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, sigma));
-    L1_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ops), size_t(std::max<int64_t>(16, btb_dist_operand_bytes(eng, n, len, sigma)))));
-    L1_TRY(btb_dist_encode(eng, d_seqs, n, len, df.stride, table, sigma, d_ops, st));
-    L1_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, 0, tile_count(n), d_out, eb, ld, 0, 1, st));
+    // k5, first half on the device: the exact text length of every row (one pass over the matrix at HBM
+    // speed) -- every row's place in the file is known before a single byte is formatted
+    L1_TRY(csv_row_lengths(d_out, eb, ld, n, d_rowlen, st));
+    L1_CUDA(cudaMemcpyAsync(cells_len.data(), d_rowlen, size_t(n) * 8, cudaMemcpyDeviceToHost, st));
     L1_CUDA(cudaStreamSynchronize(st));
+    if (n_dev == 1) timer.mark("H2D + encode + distance kernel + row text lengths");
+    cudaFree(d_seqs); d_seqs = nullptr;
+    cudaFree(d_ops); d_ops = nullptr;
+    std::vector<size_t> row_pos(static_cast<size_t>(n) + 1);                      // file offset of every row
+    row_pos[0] = head.size();
+    for (int64_t r = 0; r < n; ++r) row_pos[size_t(r) + 1] = row_pos[size_t(r)] + name_len[size_t(r)] + size_t(cells_len[size_t(r)]) + 1;
+    const size_t total = row_pos[size_t(n)];
+    if (map) {
+        if (total > map_bytes) L1_FAIL(BTB_EIO, "internal error: snps.csv text exceeds its bound");
+        prealloc_limit = total;                         // the helper stops at the real size
+    } else if (!to_stdout && !molten && g_csv_prealloc && total > (size_t(64) << 20)) {
+        // ext4 & co: blocks allocated up front (unwritten extents) -- no delayed allocation is pending when the
+        // file is renamed over an existing snps.csv, which would otherwise make the rename flush all of it
+        if (fallocate(fd, 0, 0, off_t(total)) != 0) { /* not supported here: fine */ }
     }
 
-    timer.mark("H2D + encode + distance kernel");
-    // ---- serialise: D2H row blocks (double-buffered) -> threads format -> ordered writes
-    fo = fopen(tmp_path.c_str(), to_stdout ? "wb" : "w+b");      // read-write: the file is written through a shared mapping
-    if (!fo) { rc = fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); cleanup(); return rc; }
-    setvbuf(fo, nullptr, _IOFBF, 1 << 22);
-    std::vector<const char *> name_ptr(static_cast<size_t>(n));
-    for (int64_t i = 0; i < n; ++i) name_ptr[size_t(i)] = df.names[size_t(i)].c_str();
-    if (!molten) {
-        std::string head = corner ? "snp-dists 0.8.2" : "";
-        for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
-        head.push_back('\n');
-        fwrite(head.data(), 1, head.size(), fo);
-    }
-    fflush(fo);                                          // the matrix rows go straight to the descriptor
-    // Buffered write()s to one file serialise on its inode (and run at ~3 GB/s): a 12 GB snps.csv is
-    // instead written THROUGH A MAPPING -- the file is extended to an upper bound of the text size,
-    // every formatted block is copied into place by all host threads at once (page-cache pages are
-    // populated in parallel), and the file is cut to its real length at the end.
-    if (g_csv_mmap && !to_stdout && !molten && n >= 1024) {
-        size_t bound = size_t(ftell(fo));
-        for (auto &s : df.names) bound += s.size() + 1;
-        bound += size_t(n) * size_t(n) * size_t(eb == 2 ? 6 : 11);
-        map_off = size_t(ftell(fo));
-        if (ftruncate(fileno(fo), off_t(bound)) == 0) {
-            void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, fileno(fo), 0);
-            if (m != MAP_FAILED) { map = static_cast<char *>(m); map_bytes = bound; }
-        }
-        if (!map && ftruncate(fileno(fo), off_t(map_off)) != 0) { rc = fail(BTB_EIO, "cannot size '%s'", tmp_path.c_str()); cleanup(); return rc; }
-    }
+    // ---- serialise: D2H row blocks (double-buffered) -> all host threads format rows in their final place
     const int64_t block_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t(64) << 20) / std::max<int64_t>(1, ld * eb)));
+    const int64_t blocks = (n + block_rows - 1) / block_rows;
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[0]), size_t(block_rows * ld * eb)));
     L1_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_stage[1]), size_t(block_rows * ld * eb)));
-    size_t max_name = 0;
-    for (auto &s : df.names) max_name = std::max(max_name, s.size());
-    // per block: (1) all host threads count the exact text length of their rows, (2) a prefix sum gives
-    // every row its final place -- in the file mapping, or in a contiguous buffer that one write()
-    // pushes out -- and (3) all threads format their rows directly there: the text is written once.
-    std::vector<char> text2[2];
-    if (!molten && !map) {
-        text2[0].resize(size_t(block_rows) * (max_name + size_t(n) * (eb == 2 ? 6 : 11) + 2));
-        text2[1].resize(text2[0].size());
-    }
-    std::vector<size_t> row_len, row_pos;
-    double t_wait = 0, t_count = 0, t_format = 0, t_join = 0;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    auto for_rows = [&](int64_t rows, const std::function<void(int64_t, int64_t)> &fn) {
-        const int T = int(std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 64), rows)));
-        if (T == 1) { fn(0, rows); return; }
-        std::vector<std::thread> pool;
-        const int64_t span = (rows + T - 1) / T;
-        for (int k = 0; k < T; ++k) {
-            const int64_t lo = k * span, hi = std::min(rows, lo + span);
-            if (lo < hi) pool.emplace_back(fn, lo, hi);
-        }
-        for (auto &th : pool) th.join();
-    };
-    std::thread writer;
-    writer_ptr = &writer;
-    std::atomic<bool> write_failed{false};
-    const int fd = fileno(fo);
-    cudaEvent_t ev[2];
     L1_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     L1_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    if (!molten && !map) {
+        size_t max_block = 0;
+        for (int64_t b = 0; b < blocks; ++b)
+            max_block = std::max(max_block, row_pos[size_t(std::min(n, (b + 1) * block_rows))] - row_pos[size_t(b * block_rows)]);
+        ring.init(max_block + 64);
+        const int wfd = fd;
+        writer = std::thread([&ring, wfd, blocks] { ring.run(wfd, blocks); });
+    }
+    double t_wait = 0, t_format = 0, t_ring = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto issue = [&](int64_t b) -> cudaError_t {
         const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
-        if (h_full) return cudaEventRecord(ev[b & 1], st2);      // rows are already on the host
         cudaError_t e = cudaMemcpyAsync(h_stage[b & 1], d_out + size_t(r0 * ld * eb), size_t((r1 - r0) * ld * eb),
                                         cudaMemcpyDeviceToHost, st2);
         if (e != cudaSuccess) return e;
         return cudaEventRecord(ev[b & 1], st2);
     };
-    const int64_t blocks = (n + block_rows - 1) / block_rows;
     L1_CUDA(issue(0));
     for (int64_t b = 0; b < blocks; ++b) {
+        const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows), rows = r1 - r0;
         { const double tw = now(); L1_CUDA(cudaEventSynchronize(ev[b & 1])); t_wait += now() - tw; }
-        if (b + 1 < blocks) L1_CUDA(issue(b + 1));
-        const int64_t r0 = b * block_rows, r1 = std::min(n, r0 + block_rows);
-        if (!molten) {
-            // format block b with `threads` workers while the writer thread still gathers block b-1 into place
-            const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
-            const int64_t rows = r1 - r0;
-            double tt = now();
-            row_len.assign(size_t(rows), 0);
-            row_pos.assign(size_t(rows), 0);
-            for_rows(rows, [&](int64_t lo, int64_t hi) {
-                for (int64_t r = lo; r < hi; ++r)
-                    row_len[size_t(r)] = strlen(name_ptr[size_t(r0 + r)]) + row_text_len(src_rows + size_t(r) * size_t(ld) * size_t(eb), eb, n) + 1;
-            });
-            size_t w = 0;
-            for (int64_t r = 0; r < rows; ++r) { row_pos[size_t(r)] = w; w += row_len[size_t(r)]; }
-            t_count += now() - tt; tt = now();
-            if (writer.joinable()) writer.join();        // the write() of block b-1 is done: its buffer parity is not ours
-            if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
-            t_join += now() - tt; tt = now();
-            char *dst = nullptr;
-            if (map) {
-                if (map_off + w > map_bytes) { rc = fail(BTB_EIO, "snps.csv text exceeds its bound"); cleanup(); return rc; }
-                dst = map + map_off;
-                map_off += w;
-            } else {
-                if (w > text2[b & 1].size()) { rc = fail(BTB_EIO, "snps.csv text exceeds its bound"); cleanup(); return rc; }
-                dst = text2[b & 1].data();
-            }
-            std::atomic<bool> bad_len{false};
-            for_rows(rows, [&](int64_t lo, int64_t hi) {
-                for (int64_t r = lo; r < hi; ++r) {
-                    char *q = dst + row_pos[size_t(r)];
-                    const char *nm = name_ptr[size_t(r0 + r)];
-                    const size_t nl = strlen(nm);
-                    memcpy(q, nm, nl);
-                    q += nl;
-                    q += format_row(src_rows + size_t(r) * size_t(ld) * size_t(eb), eb, n, sep, q);
-                    *q++ = '\n';
-                    if (size_t(q - (dst + row_pos[size_t(r)])) != row_len[size_t(r)]) bad_len = true;
-                }
-            });
-            if (bad_len) { rc = fail(BTB_EIO, "internal error: a formatted row does not have its predicted length"); cleanup(); return rc; }
-            t_format += now() - tt;
-            if (!map) {
-                const char *wp = dst;
-                writer = std::thread([&write_failed, fd, wp, w]() {
-                    const char *p = wp;
-                    size_t left = w;
-                    while (left) {
-                        ssize_t k = write(fd, p, left);
-                        if (k <= 0) { write_failed = true; return; }
-                        p += k; left -= size_t(k);
-                    }
-                });
-            }
-        } else {
+        if (b + 1 < blocks) L1_CUDA(issue(b + 1));                // into the other staging buffer: block b - 1 is formatted
+        const char *src_rows = h_stage[b & 1];
+        if (molten) {
+            std::string text;
             for (int64_t r = r0; r < r1; ++r)
                 for (int64_t i = 0; i < n; ++i) {
-                    const char *src_rows = h_full ? h_full + size_t(r0 * ld * eb) : h_stage[b & 1];
                     const uint32_t v = eb == 2 ? reinterpret_cast<const uint16_t *>(src_rows)[(r - r0) * ld + i]
                                                : reinterpret_cast<const uint32_t *>(src_rows)[(r - r0) * ld + i];
-                    fprintf(fo, "%s%c%s%c%u\n", df.names[size_t(r)].c_str(), sep, df.names[size_t(i)].c_str(), sep, v);
+                    text += df.names[size_t(r)]; text.push_back(sep); text += df.names[size_t(i)]; text.push_back(sep);
+                    text += std::to_string(v); text.push_back('\n');
+                    if (text.size() > (size_t(8) << 20)) { if (!write_all(fd, text.data(), text.size())) L1_FAIL(BTB_EIO, "write to '%s' failed", out_path); text.clear(); }
                 }
+            if (!write_all(fd, text.data(), text.size())) L1_FAIL(BTB_EIO, "write to '%s' failed", out_path);
+            continue;
         }
+        char *dst = nullptr;                                      // where file offset row_pos[r0] lives
+        if (map) {
+            dst = map + row_pos[size_t(r0)];
+            const double tr = now();
+            for (int spins = 0; prealloc_done.load(std::memory_order_acquire) < row_pos[size_t(r1)] && !prealloc_over.load(std::memory_order_acquire); ++spins)
+                if (spins < 100) std::this_thread::yield(); else usleep(100);
+            t_ring += now() - tr;
+        } else {
+            const double tr = now();
+            dst = ring.acquire(b);
+            t_ring += now() - tr;
+            if (!dst) L1_FAIL(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
+        }
+        const double tf = now();
+        std::atomic<bool> bad_len{false};
+        parallel_rows(rows, threads, [&](int64_t lo, int64_t hi) {
+            for (int64_t r = lo; r < hi; ++r) {
+                const size_t at = row_pos[size_t(r0 + r)] - row_pos[size_t(r0)];
+                char *q = dst + at;
+                memcpy(q, df.names[size_t(r0 + r)].data(), name_len[size_t(r0 + r)]);
+                q += name_len[size_t(r0 + r)];
+                q += format_row(src_rows + size_t(r) * size_t(ld) * size_t(eb), eb, n, sep, q);
+                *q++ = '\n';
+                if (size_t(q - dst) != row_pos[size_t(r0 + r) + 1] - row_pos[size_t(r0)]) bad_len = true;
+            }
+        });
+        t_format += now() - tf;
+        if (bad_len) L1_FAIL(BTB_EIO, "internal error: a formatted row does not have its predicted length");
+        if (!map) ring.submit(b, row_pos[size_t(r1)] - row_pos[size_t(r0)]);
     }
-    if (writer.joinable()) writer.join();
-    if (write_failed) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    if (!molten && !map) {
+        const double tr = now();
+        const bool ok = ring.finish(blocks);
+        t_ring += now() - tr;
+        if (writer.joinable()) writer.join();
+        if (!ok) L1_FAIL(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
+    }
     if (map) {
+        prealloc_limit = 0;
+        if (prealloc.joinable()) prealloc.join();
         munmap(map, map_bytes);
         map = nullptr;
-        if (ftruncate(fileno(fo), off_t(map_off)) != 0) { rc = fail(BTB_EIO, "cannot size '%s'", tmp_path.c_str()); cleanup(); return rc; }
+        if (ftruncate(fd, off_t(total)) != 0) L1_FAIL(BTB_EIO, "cannot size '%s'", tmp_path.c_str());
     }
     timer.mark("D2H + format + write snps.csv");
-    if (timer.on) fprintf(stderr, "[btb timing]     (wait for D2H %.3f s, count row lengths %.3f s, wait for write() %.3f s, format in place %.3f s)\n",
-                          t_wait, t_count, t_join, t_format);
-    if (fclose(fo) != 0) { fo = nullptr; rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); cleanup(); return rc; }
-    fo = nullptr;
-    // unlink first: replacing an existing file by rename makes ext4 flush the new file's data synchronously
-    if (!to_stdout) unlink(out_path);
-    if (!to_stdout && rename(tmp_path.c_str(), out_path) != 0) { rc = fail(BTB_EIO, "cannot rename to '%s'", out_path); cleanup(); return rc; }
+    if (timer.on) fprintf(stderr, "[btb timing]     (%s: wait for D2H %.3f s, format rows in place %.3f s, wait for the %s %.3f s)\n",
+                          map_bytes ? "mapped file" : "write()", t_wait, t_format, map_bytes ? "preallocating helper" : "writer thread", t_ring);
+    if (!to_stdout) {
+        const int cfd = fd;
+        fd = -1;
+        if (close(cfd) != 0) { discard_output(tmp_path); L1_FAIL(BTB_EIO, "closing '%s' failed", tmp_path.c_str()); }
+        rc = commit_output(tmp_path, out_path, g_replace_unlink_first != 0);
+        if (rc != BTB_OK) { cleanup(); return rc; }
+    }
     timer.mark("close + rename");
     cleanup();
     timer.mark("free device + pinned buffers");
     return BTB_OK;
 #undef L1_CUDA
 #undef L1_TRY
+#undef L1_FAIL
 }

@@ -305,8 +305,10 @@ extern "C" int btb_comm_last_timings(const btb_comm *c, double *seconds, int cap
 namespace btb {
 
 // This rank's block rows [lo, hi) of the matrix: distance kernels band by band, every finished band's
-// cells -- the rows from the diagonal on and the mirrored strip below -- copied to the host matrix
-// while the next band is computed.  d_out is the rank's full-size device matrix.
+// cells -- the rows from the diagonal on and the mirrored strip below -- copied to the matrix `out`
+// while the next band is computed.  d_out is the rank's full-size device matrix; `out` is host memory
+// (level 2: the job's one host matrix) or a peer-accessible device matrix (level 1, several GPUs in one
+// process: the shares are assembled on the first device, over NVLink, and serialised from there).
 int share_compute_and_copy(int eng, const void *d_ops, int64_t n, int64_t len, int sigma, int64_t lo, int64_t hi,
                            uint8_t *d_out, int eb, int64_t d_ld, void *out, int64_t out_ld, cudaStream_t st,
                            cudaStream_t st_out, cudaEvent_t ev) {
@@ -315,7 +317,7 @@ int share_compute_and_copy(int eng, const void *d_ops, int64_t n, int64_t len, i
         if (r1 <= r0 || c1 <= c0) return cudaSuccess;
         return cudaMemcpy2DAsync(ho + size_t(r0 * out_ld + c0) * size_t(eb), size_t(out_ld) * size_t(eb),
                                  d_out + size_t(r0 * d_ld + c0) * size_t(eb), size_t(d_ld) * size_t(eb),
-                                 size_t(c1 - c0) * size_t(eb), size_t(r1 - r0), cudaMemcpyDeviceToHost, st_out);
+                                 size_t(c1 - c0) * size_t(eb), size_t(r1 - r0), cudaMemcpyDefault, st_out);
     };
     const int64_t step = std::max<int64_t>(2, int64_t(g_comm_band_rows) / 2 * 2);
     for (int64_t b0 = lo; b0 < hi; b0 += step) {

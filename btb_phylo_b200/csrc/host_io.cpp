@@ -4,12 +4,14 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statfs.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include <time.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -34,6 +36,46 @@ StageTimer::~StageTimer() {
     if (!on) return;
     fprintf(stderr, "[btb timing] %s: total %.3f s\n", what, now_s() - t0);
     for (auto &m : marks) fprintf(stderr, "[btb timing]   %-28s %8.3f s\n", m.first.c_str(), m.second);
+}
+
+int open_output_temp(const char *final_path, std::string &tmp_path, int *fd) {
+    std::string dir = ".", base = final_path;
+    const size_t slash = base.rfind('/');
+    if (slash != std::string::npos) { dir = slash == 0 ? "/" : base.substr(0, slash); base = base.substr(slash + 1); }
+    tmp_path = dir + "/." + base + ".XXXXXX";
+    std::vector<char> name(tmp_path.begin(), tmp_path.end());
+    name.push_back(0);
+    const int f = mkstemp(name.data());
+    if (f < 0) return fail(BTB_EIO, "cannot create a temporary file next to '%s': %s", final_path, strerror(errno));
+    tmp_path = name.data();
+    const mode_t um = umask(0);
+    umask(um);
+    fchmod(f, 0666 & ~um);
+    *fd = f;
+    return BTB_OK;
+}
+
+int commit_output(const std::string &tmp_path, const char *final_path, bool unlink_first) {
+    if (unlink_first) unlink(final_path);
+    if (rename(tmp_path.c_str(), final_path) != 0) {
+        const int e = errno;
+        unlink(tmp_path.c_str());
+        return fail(BTB_EIO, "cannot rename to '%s': %s", final_path, strerror(e));
+    }
+    return BTB_OK;
+}
+
+void discard_output(const std::string &tmp_path) {
+    if (!tmp_path.empty()) unlink(tmp_path.c_str());
+}
+
+bool on_memory_fs(const char *path) {
+    std::string dir = path;
+    const size_t slash = dir.rfind('/');
+    dir = slash == std::string::npos ? "." : (slash == 0 ? "/" : dir.substr(0, slash));
+    struct statfs sf;
+    if (statfs(dir.c_str(), &sf) != 0) return false;
+    return sf.f_type == 0x01021994 /* TMPFS_MAGIC */ || sf.f_type == 0x858458f6 /* RAMFS_MAGIC */;
 }
 
 FileBytes::~FileBytes() {

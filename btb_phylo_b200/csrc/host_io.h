@@ -79,6 +79,18 @@ struct StageTimer {
     ~StageTimer();
 };
 
+// Output files are written under a unique temporary name in the target's directory (mkstemp) and moved
+// over the target with one rename(): the replace is atomic, a failed run leaves the old file alone, and
+// two runs writing the same path do not collide.  open_output_temp returns the descriptor (mode 0666 &
+// ~umask) and the temporary path; commit_output renames (with `unlink_first` the target is removed first --
+// "replace_unlink_first": ext4 flushes a file that replaces another one by rename synchronously, which
+// costs seconds for a 12 GB snps.csv; off by default because it is not atomic); discard_output removes it.
+int open_output_temp(const char *final_path, std::string &tmp_path, int *fd);
+int commit_output(const std::string &tmp_path, const char *final_path, bool unlink_first);
+void discard_output(const std::string &tmp_path);
+// true when `path`'s directory is a tmpfs / ramfs (page cache only: mapped writes scale with threads there)
+bool on_memory_fs(const char *path);
+
 // ViewBovine label of one sample name (ASCII restatement of btbphylo/phylogeny.py:206-216).
 std::string process_sample_name(const std::string &name);
 // snps.csv helpers behind btb_csv_row_names / btb_relabel_csv.

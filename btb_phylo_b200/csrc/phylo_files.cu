@@ -22,6 +22,7 @@ namespace btb {
 int require_device(int device);
 std::vector<int> usable_devices();
 std::vector<int> worker_devices(int n_gpus);
+extern int g_replace_unlink_first;
 int first_usable_device();
 }
 using namespace btb;
@@ -426,9 +427,11 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
     timer.mark("k3 compact + D2H");
 
     // ---- write: >name\n + L bases + \n per sample, one line per sequence --------------------------
-    std::string tmp_path = std::string(out_fasta) + ".tmp";
-    FILE *fo = fopen(tmp_path.c_str(), "wb");
-    if (!fo) return fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str());
+    std::string tmp_path;
+    int tfd = -1;
+    BTB_TRY(open_output_temp(out_fasta, tmp_path, &tfd));
+    FILE *fo = fdopen(tfd, "wb");
+    if (!fo) { close(tfd); discard_output(tmp_path); return fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); }
     setvbuf(fo, nullptr, _IOFBF, 1 << 22);
     int rc = BTB_OK;
     for (int64_t r = 0; r < n && rc == BTB_OK; ++r) {
@@ -439,10 +442,8 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
     }
     if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
     timer.mark("write snps.fas");
-    if (rc == BTB_OK) unlink(out_fasta);                // see btb_snp_dists: avoid the replace-by-rename flush
-    if (rc == BTB_OK && rename(tmp_path.c_str(), out_fasta) != 0) rc = fail(BTB_EIO, "cannot rename to '%s'", out_fasta);
-    if (rc != BTB_OK) remove(tmp_path.c_str());
-    return rc;
+    if (rc != BTB_OK) { discard_output(tmp_path); return rc; }
+    return commit_output(tmp_path, out_fasta, g_replace_unlink_first != 0);
 }
 
 }  // namespace

@@ -35,9 +35,9 @@ def test_reference_arm_line():
 @pytest.mark.gpu
 @pytest.mark.timeout(900)
 def test_gpu_arm_line():
-    d = run_bench(["--steps", "3", "--warmup", "3"], 6400, 3000)
+    d = run_bench(["--steps", "20", "--warmup", "3"], 6400, 3000)      # 20 steps: a 1 ms timed region is at the mercy of any hiccup
     assert BASE | {"gpu_launches", "clocks", "roofline"} <= set(d)
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 3 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["gpu_launches"] >= 2 * d["steps"] and d["data"] == "synthetic"
     r = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "tensor"
