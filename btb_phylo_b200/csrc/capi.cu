@@ -537,7 +537,9 @@ struct DenseFasta {
 };
 
 // File -> dense pinned rows.  Error texts follow snp-dists 0.8.2.
-int read_dense(const char *path, int threads, DenseFasta &df) {
+// `on_framed` (optional) runs as soon as the record names and the sequence count are known -- before the
+// sequence bytes are read -- so that the caller can start preparing its output beside the read.
+int read_dense(const char *path, int threads, DenseFasta &df, const std::function<void()> *on_framed = nullptr) {
     // Fast path for what snp-sites writes (one unwrapped line per record, equal lengths): frame by
     // prediction (host_io.h) and pread every record straight into the pinned rows.  The host checks
     // that no line break hides inside a record; anything unexpected takes the exact path below.
@@ -551,6 +553,9 @@ int read_dense(const char *path, int threads, DenseFasta &df) {
             df.n = int64_t(recs.size());
             df.len = recs[0].seq_len;
             df.stride = std::max<int64_t>(16, (df.len + 15) / 16 * 16);
+            df.names.resize(recs.size());
+            for (size_t i = 0; i < recs.size(); ++i) df.names[i] = recs[i].name;
+            if (on_framed) (*on_framed)();
             BTB_TRY(df.alloc(size_t(df.n * df.stride)));
             std::atomic<bool> ok{true};
             auto work = [&](int64_t lo, int64_t hi) {
@@ -572,12 +577,9 @@ int read_dense(const char *path, int threads, DenseFasta &df) {
                 }
                 for (auto &th : pool) th.join();
             }
-            if (ok) {
-                df.names.resize(recs.size());
-                for (size_t i = 0; i < recs.size(); ++i) df.names[i] = std::move(recs[i].name);
-                return BTB_OK;
-            }
+            if (ok) return BTB_OK;
             df.release();
+            on_framed = nullptr;                    // the exact path below sees the same names: the output is already being prepared
         }
     }
     FileBytes fb;
@@ -591,8 +593,10 @@ int read_dense(const char *path, int threads, DenseFasta &df) {
     df.n = int64_t(recs.size());
     df.len = walk_record(fb, recs[0], nullptr);
     df.stride = std::max<int64_t>(16, (df.len + 15) / 16 * 16);
-    BTB_TRY(df.alloc(size_t(df.n * df.stride)));
     df.names.resize(recs.size());
+    for (size_t i = 0; i < recs.size(); ++i) df.names[i] = recs[i].name;
+    if (on_framed) (*on_framed)();
+    BTB_TRY(df.alloc(size_t(df.n * df.stride)));
     std::vector<int64_t> lens(recs.size(), 0);
     auto work = [&](int64_t lo, int64_t hi) {
         std::vector<uint8_t> tmp;
@@ -965,22 +969,8 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     StageTimer timer("btb_snp_dists");
     BTB_TRY(require_device(first_usable_device()));
     timer.mark("device init");
+    int rc = BTB_OK;
     DenseFasta df;
-    int rc = read_dense(in_fasta, threads, df);
-    timer.mark("read + parse snps.fas");
-    if (rc != BTB_OK) { if (!quiet) fprintf(stderr, "%s\n", last_error().c_str()); return rc; }
-    if (!quiet) fprintf(stderr, "Read %lld sequences of length %lld\n", (long long)df.n, (long long)df.len);
-    if (n_samples) *n_samples = df.n;
-    if (seq_len) *seq_len = df.len;
-    if (labels) {                                        // printed instead of the record names
-        if (n_labels != df.n)
-            return fail(BTB_EINVAL, "%lld labels given for %lld sequences", (long long)n_labels, (long long)df.n);
-        BTB_TRY(split_labels(labels, n_labels, df.names));
-    }
-    const int64_t n = df.n, len = df.len;
-    const int eb = len < 65536 ? 2 : 4;
-    const int64_t ld = (n + 7) / 8 * 8;
-
     cudaStream_t st = nullptr, st2 = nullptr;
     BTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     BTB_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
@@ -992,17 +982,19 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
     std::string tmp_path;
     char *map = nullptr;               // snps.csv written through a mapping (tmpfs, see below)
     size_t map_bytes = 0;
-    std::thread prealloc;              // fallocate of the mapped file, chunk by chunk, beside everything else
-    std::atomic<size_t> prealloc_limit{0}, prealloc_done{0};
-    std::atomic<bool> prealloc_over{false};    // the helper has stopped (finished, or fallocate is not supported here)
+    std::thread prealloc;              // fallocate of the mapped file, beside the read and the distance stage
+    std::atomic<size_t> prealloc_limit{0};
     TextRing ring;                     // write() mode: formatted blocks on their way to the writer thread
     std::thread writer;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    auto stop_prealloc = [&]() {
+        prealloc_limit = 0;
+        if (prealloc.joinable()) prealloc.join();
+    };
     auto cleanup = [&]() {
         ring.abort();
         if (writer.joinable()) writer.join();
-        prealloc_limit = 0;
-        if (prealloc.joinable()) prealloc.join();
+        stop_prealloc();
         if (map) { munmap(map, map_bytes); map = nullptr; }
         cudaFree(d_seqs); cudaFree(d_ops); cudaFree(d_out); cudaFree(d_rowlen);
         if (h_stage[0]) cudaFreeHost(h_stage[0]);
@@ -1024,54 +1016,96 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
 #define L1_TRY(call) do { rc = (call); if (rc != BTB_OK) { cleanup(); return rc; } } while (0)
 #define L1_FAIL(...) do { rc = fail(__VA_ARGS__); cleanup(); return rc; } while (0)
 
-    // ---- the output file is opened (and, on tmpfs, sized, mapped and preallocated by a helper thread)
-    //      while the GPUs work
-    if (!to_stdout) L1_TRY(open_output_temp(out_path, tmp_path, &fd));
-    std::string head;
-    if (!molten) {
-        head = corner ? "snp-dists 0.8.2" : "";
-        for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += df.names[size_t(i)]; }
-        head.push_back('\n');
-        if (!write_all(fd, head.data(), head.size())) L1_FAIL(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
-    }
-    std::vector<size_t> name_len(static_cast<size_t>(n));
-    size_t names_total = 0;
-    for (int64_t i = 0; i < n; ++i) { name_len[size_t(i)] = df.names[size_t(i)].size(); names_total += name_len[size_t(i)]; }
+    // ---- the output file is opened (and, on tmpfs, sized, mapped and preallocated by a helper thread) as
+    //      soon as the record names are known: beside the read of the sequences and the distance stage.
     // Buffered write()s to one file serialise on its inode whatever the number of writers (measured on
     // the B200 boxes, tools/io_probe.cpp: 5.4 GB/s on the ext4 disk, 3.2 GB/s on tmpfs, for 1 or 16 writers;
     // 16 threads writing 16 FILES reach 32-36 GB/s).  On tmpfs a shared mapping of the preallocated file
     // takes 8.8 GB/s from 16 threads (page faults need no inode lock); on ext4 mapped writes are slower
     // than write() (4.5-5.1 GB/s: page_mkwrite journals every page).  So: tmpfs -> the file is sized to an
-    // upper bound of the text, mapped, and preallocated chunk by chunk by a helper thread that starts NOW
-    // (beside the upload and the distance kernels) and stops at the exact text size once that is known;
-    // all host threads format their rows straight into the mapping, block by block, each block as soon as
-    // the helper has passed its end (threads that fault fresh pages in while fallocate runs slow both down:
-    // 1.66 s of formatting instead of 0.5 s, measured); the file is cut to its real length at the end.  Anything else -> formatted blocks go through a ring to one writer thread and write().
-    const bool want_map = !to_stdout && !molten && n >= 1024 && (g_csv_mmap == 1 || (g_csv_mmap < 0 && on_memory_fs(out_path)));
-    if (want_map) {
-        const size_t bound = head.size() + names_total + size_t(n) + size_t(n) * size_t(n) * size_t(eb == 2 ? 6 : 11);
-        if (ftruncate(fd, off_t(bound)) == 0) {
-            void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-            if (m != MAP_FAILED) { map = static_cast<char *>(m); map_bytes = bound; }
-            else if (ftruncate(fd, off_t(head.size())) != 0) L1_FAIL(BTB_EIO, "cannot size '%s'", tmp_path.c_str());
+    // upper bound of the text, mapped, and preallocated by a helper thread (fallocate in chunks, stopping
+    // at the exact text size once that is known); when the helper is done all host threads format their rows
+    // straight into the mapping (formatting WHILE fallocate runs is three times slower, measured: 1.6 s
+    // instead of 0.5 s -- page faults and fallocate contend -- so the two are not overlapped); the file is
+    // cut to its real length at the end.  Anything else -> formatted blocks go through a ring to one writer
+    // thread and write().
+    std::string head;                  // what the output was prepared with
+    int64_t prepared_n = -1;
+    int prep_rc = BTB_OK;
+    std::string prep_err;
+    std::vector<std::string> label_names;
+    if (labels) BTB_TRY(split_labels(labels, n_labels, label_names));
+    auto prepare_output = [&]() -> int {
+        const std::vector<std::string> &names = labels ? label_names : df.names;
+        const int64_t n = df.n;
+        const int eb = df.len < 65536 ? 2 : 4;
+        if (labels && int64_t(label_names.size()) != n) return BTB_OK;          // reported by the caller below
+        if (!to_stdout && fd < 0) BTB_TRY(open_output_temp(out_path, tmp_path, &fd));
+        head.clear();
+        size_t names_total = 0;
+        if (!molten) {
+            head = corner ? "snp-dists 0.8.2" : "";
+            for (int64_t i = 0; i < n; ++i) { head.push_back(sep); head += names[size_t(i)]; names_total += names[size_t(i)].size(); }
+            head.push_back('\n');
+            if (!write_all(fd, head.data(), head.size())) return fail(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
         }
-        if (map) {
-            prealloc_limit = bound;
-            const int pfd = fd;
-            const size_t from = head.size();
-            prealloc_done = from;
-            prealloc = std::thread([pfd, from, &prealloc_limit, &prealloc_done, &prealloc_over] {
-                constexpr size_t kChunk = size_t(128) << 20;
-                for (size_t done = from; done < prealloc_limit.load(std::memory_order_acquire);) {
-                    const size_t len = std::min(kChunk, prealloc_limit.load(std::memory_order_acquire) - done);
-                    if (fallocate(pfd, 0, off_t(done), off_t(len)) != 0) break;       // unsupported: the formatters fault the pages in
-                    done += len;
-                    prealloc_done.store(done, std::memory_order_release);
-                }
-                prealloc_over.store(true, std::memory_order_release);
-            });
+        prepared_n = n;
+        const bool want_map = !to_stdout && !molten && n >= 1024 && (g_csv_mmap == 1 || (g_csv_mmap < 0 && on_memory_fs(out_path)));
+        if (!want_map) return BTB_OK;
+        const size_t bound = head.size() + names_total + size_t(n) + size_t(n) * size_t(n) * size_t(eb == 2 ? 6 : 11);
+        if (ftruncate(fd, off_t(bound)) != 0) return BTB_OK;
+        void *m = mmap(nullptr, bound, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) return ftruncate(fd, off_t(head.size())) == 0 ? BTB_OK : fail(BTB_EIO, "cannot size '%s'", tmp_path.c_str());
+        map = static_cast<char *>(m);
+        map_bytes = bound;
+        prealloc_limit = bound;
+        const int pfd = fd;
+        const size_t from = head.size();
+        prealloc = std::thread([pfd, from, &prealloc_limit] {
+            constexpr size_t kChunk = size_t(128) << 20;
+            for (size_t done = from; done < prealloc_limit.load(std::memory_order_acquire);) {
+                const size_t len = std::min(kChunk, prealloc_limit.load(std::memory_order_acquire) - done);
+                if (fallocate(pfd, 0, off_t(done), off_t(len)) != 0) break;       // unsupported: the formatters fault the pages in
+                done += len;
+            }
+        });
+        return BTB_OK;
+    };
+    const std::function<void()> on_framed = [&]() { prep_rc = prepare_output(); if (prep_rc != BTB_OK) prep_err = last_error(); };
+    rc = read_dense(in_fasta, threads, df, &on_framed);
+    timer.mark("read + parse snps.fas");
+    if (rc != BTB_OK) {
+        const std::string msg = last_error();
+        if (!quiet) fprintf(stderr, "%s\n", msg.c_str());
+        cleanup();
+        return fail(rc, "%s", msg.c_str());
+    }
+    if (prep_rc != BTB_OK) { rc = fail(prep_rc, "%s", prep_err.c_str()); cleanup(); return rc; }
+    if (!quiet) fprintf(stderr, "Read %lld sequences of length %lld\n", (long long)df.n, (long long)df.len);
+    if (n_samples) *n_samples = df.n;
+    if (seq_len) *seq_len = df.len;
+    if (labels) {                                        // printed instead of the record names
+        if (n_labels != df.n) L1_FAIL(BTB_EINVAL, "%lld labels given for %lld sequences", (long long)n_labels, (long long)df.n);
+        df.names = label_names;
+    }
+    const int64_t n = df.n, len = df.len;
+    const int eb = len < 65536 ? 2 : 4;
+    const int64_t ld = (n + 7) / 8 * 8;
+    {
+        // the output was prepared from the names of the framing pass; if the exact parse that followed a
+        // rejected prediction saw other records (it never should), prepare it again from scratch
+        std::string want = molten ? std::string() : std::string(corner ? "snp-dists 0.8.2" : "");
+        if (!molten) { for (int64_t i = 0; i < n; ++i) { want.push_back(sep); want += df.names[size_t(i)]; } want.push_back('\n'); }
+        if (prepared_n != n || want != head) {
+            stop_prealloc();
+            if (map) { munmap(map, map_bytes); map = nullptr; map_bytes = 0; }
+            if (!to_stdout && fd >= 0 && (ftruncate(fd, 0) != 0 || lseek(fd, 0, SEEK_SET) != 0)) L1_FAIL(BTB_EIO, "cannot rewind '%s'", tmp_path.c_str());
+            if (to_stdout && prepared_n >= 0 && !head.empty()) L1_FAIL(BTB_EFORMAT, "the alignment changed while it was read");
+            L1_TRY(prepare_output());
         }
     }
+    std::vector<size_t> name_len(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) name_len[size_t(i)] = df.names[size_t(i)].size();
 
     // ---- distance stage -------------------------------------------------------------------------------------
     std::vector<int> devs = worker_devices(n_gpus);
@@ -1164,10 +1198,7 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         char *dst = nullptr;                                      // where file offset row_pos[r0] lives
         if (map) {
             dst = map + row_pos[size_t(r0)];
-            const double tr = now();
-            for (int spins = 0; prealloc_done.load(std::memory_order_acquire) < row_pos[size_t(r1)] && !prealloc_over.load(std::memory_order_acquire); ++spins)
-                if (spins < 100) std::this_thread::yield(); else usleep(100);
-            t_ring += now() - tr;
+            if (prealloc.joinable()) { const double tr = now(); prealloc.join(); t_ring += now() - tr; }    // see above: not overlapped
         } else {
             const double tr = now();
             dst = ring.acquire(b);
@@ -1199,10 +1230,13 @@ static int snp_dists_impl(const char *in_fasta, const char *out_path, int allcha
         if (!ok) L1_FAIL(BTB_EIO, "write to '%s' failed", to_stdout ? "stdout" : tmp_path.c_str());
     }
     if (map) {
-        prealloc_limit = 0;
-        if (prealloc.joinable()) prealloc.join();
-        munmap(map, map_bytes);
-        map = nullptr;
+        stop_prealloc();
+        {   // tearing down 3 million page-table entries takes 0.1-0.2 s and nothing waits for it
+            char *m = map;
+            const size_t mb = map_bytes;
+            map = nullptr;
+            std::thread([m, mb] { munmap(m, mb); }).detach();
+        }
         if (ftruncate(fd, off_t(total)) != 0) L1_FAIL(BTB_EIO, "cannot size '%s'", tmp_path.c_str());
     }
     timer.mark("D2H + format + write snps.csv");
