@@ -1381,9 +1381,15 @@ int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 te
 int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
 int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
 int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
-int g_umma_coop = 1;           // "umma_coop": 0 launches the CTA-pair kernel without the cooperative attribute -- only for
-                               // profilers (ncu cannot replay a cooperative cluster launch); the grid is one CTA per SM, so
-                               // all CTAs are co-resident whenever the GPU is otherwise idle
+// "umma_coop": 0 launches the CTA-pair kernel without the cooperative attribute -- only for profilers (ncu cannot
+// replay a cooperative cluster launch); the grid is one CTA per SM, so all CTAs are co-resident whenever the GPU
+// is otherwise idle.  The default is 1 unless a profiler has injected itself into the process (Nsight Compute
+// sets these variables for its target), so that a profiled run lists this kernel like any other.
+static bool profiler_attached() {
+    return getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") || getenv("CUDA_INJECTION64_PATH") ||
+           getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+}
+int g_umma_coop = profiler_attached() ? 0 : 1;
 int g_umma_fp4_pair = 1;       // "umma_fp4_pair": cta_group::2 version of the FP4 full-tile kernel (0: single-CTA kernel)
 int g_umma_tile_bk = 128;      // "umma_tile_bk": K bytes per stage of the FP4 full-tile kernel (128: 3 stages; 64: 6 stages -- measured equal)
 int g_umma_dbg_max_ctas = 0;   // experiment: cap the grid of the FP4 full-tile kernel (0 = one CTA per SM)

@@ -344,3 +344,74 @@ def test_allchars_heavy_gap_content_at_scale(capi, oracle):
     # default mode on the same bytes (N and gaps ignored)
     _, c = gpu_matrix(capi, seqs, 1, 1, allchars=False)
     assert (c[17] == oracle.snp_dists_rows(seqs, threads=8, row0=17, row1=18)[0]).all()
+
+
+def _rows_from_base(base, n, mutations, alphabet, seed):
+    """n rows = `base` with `mutations` random substitutions each (torch, on the GPU)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    L = base.shape[0]
+    rows = base[None, :].repeat(n, 1)
+    pos = torch.randint(0, L, (n, mutations), generator=g, device="cuda")
+    sym = torch.tensor(list(alphabet), dtype=torch.uint8, device="cuda")[torch.randint(0, len(alphabet), (n, mutations), generator=g, device="cuda")]
+    rows.scatter_(1, pos, sym)
+    return rows
+
+
+def test_fp4_exact_at_the_dense_guard(capi, oracle):
+    """The dense kind::mxf4 path is admitted while 3 * len < 2^24 (common.cuh umma_fp4_dense): fp32
+    accumulators must then hold every partial sum exactly.  Rows at the guard whose dot products are as
+    large as the code allows: near-identical rows over C/G/T only, majority-zero coding OFF, so every site
+    carries two 1-nibbles and dot(i, j) ~ 2 * len = 1.1e7.  Checked against the oracle, bit for bit."""
+    from btb_phylo_b200 import device
+    L = ((1 << 24) - 512) // 3                       # 5,592,234: 3 * L = 2^24 - 514
+    n = 96
+    g = torch.Generator(device="cuda")
+    g.manual_seed(71)
+    base = torch.tensor(list(b"CGT"), dtype=torch.uint8, device="cuda")[torch.randint(0, 3, (L,), generator=g, device="cuda")]
+    rows = _rows_from_base(base, n, 300, b"ACGT", 72)
+    rows[5] = rows[4]                                # an identical pair: distance 0 out of a dot of ~1.1e7
+    stride = (L + 15) // 16 * 16
+    seqs = torch.full((n, stride), ord("."), dtype=torch.uint8, device="cuda")
+    seqs[:, :L] = rows
+    capi.check(capi.lib().btb_set_option(b"umma_major_zero", 0))
+    try:
+        plan = device.DistancePlan(seqs, length=L, engine=capi.ENGINE_UMMA)
+        assert plan.sigma == capi.SIGMA_DENSE4
+        assert capi.lib().btb_dist_operand_bytes(capi.ENGINE_UMMA, n, L, plan.sigma) == n * ((3 * L + 1) // 2 + 127) // 128 * 128 + 4 * n   # the nibble layout, not int8
+        plan.encode()
+        out = plan.alloc_matrix()
+        plan.compute(out)
+        torch.cuda.synchronize()
+    finally:
+        capi.check(capi.lib().btb_set_option(b"umma_major_zero", 1))
+    got = out[:, :n].cpu().numpy().astype(np.int64)
+    want = oracle.snp_dists_rows(rows.cpu().numpy(), threads=16).astype(np.int64)
+    assert got[4, 5] == 0 and (got == want).all()
+    # one site more and the guard sends the rows to the int8 kernels (int32 accumulators)
+    assert capi.lib().btb_dist_operand_bytes(capi.ENGINE_UMMA, n, L + 200, plan.sigma) == n * (((L + 200) * 3 + 127) // 128 * 128) + 4 * n
+
+
+def test_fp4_exact_at_the_general_guard(capi, oracle):
+    """General alphabets (validity + one-hot nibble planes, V.V - X.X with the negate-A bit) are admitted
+    while len < 2^24: V.V reaches len.  Near-identical rows of len = 2^24 - 256 with a few N."""
+    from btb_phylo_b200 import device
+    L = (1 << 24) - 256
+    n = 40
+    g = torch.Generator(device="cuda")
+    g.manual_seed(73)
+    base = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (L,), generator=g, device="cuda")]
+    rows = _rows_from_base(base, n, 500, b"ACGTN-", 74)
+    rows[7] = rows[3]
+    seqs = torch.full((n, L), ord("."), dtype=torch.uint8, device="cuda")       # L is a multiple of 16
+    seqs[:, :L] = rows
+    plan = device.DistancePlan(seqs, length=L, engine=capi.ENGINE_UMMA)
+    assert plan.sigma == 4                            # ignored bytes present: not dense
+    assert capi.lib().btb_dist_operand_bytes(capi.ENGINE_UMMA, n, L, plan.sigma) == n * 5 * ((L + 255) // 256 * 128) + 4 * n
+    plan.encode()
+    out = plan.alloc_matrix()
+    plan.compute(out)
+    torch.cuda.synchronize()
+    got = out[:, :n].cpu().numpy().astype(np.int64)
+    want = oracle.snp_dists_rows(rows.cpu().numpy(), threads=16).astype(np.int64)
+    assert got[3, 7] == 0 and (got == want).all()
