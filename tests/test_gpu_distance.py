@@ -378,7 +378,7 @@ def test_fp4_exact_at_the_dense_guard(capi, oracle):
     try:
         plan = device.DistancePlan(seqs, length=L, engine=capi.ENGINE_UMMA)
         assert plan.sigma == capi.SIGMA_DENSE4
-        assert capi.lib().btb_dist_operand_bytes(capi.ENGINE_UMMA, n, L, plan.sigma) == n * ((3 * L + 1) // 2 + 127) // 128 * 128 + 4 * n   # the nibble layout, not int8
+        assert capi.lib().btb_dist_operand_bytes(capi.ENGINE_UMMA, n, L, plan.sigma) == n * (((3 * L + 1) // 2 + 127) // 128 * 128) + 4 * n   # the nibble layout, not int8
         plan.encode()
         out = plan.alloc_matrix()
         plan.compute(out)
