@@ -39,6 +39,7 @@ SIGNATURES = {
     "btb_extract_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, p_i64, c_vp, c_i64]),
     "btb_plane_words": (c_i64, [c_i64]),
     "btb_pack_planes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "btb_pack_planes_state": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "btb_column_mask": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "btb_select_columns": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "btb_compact_columns": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),

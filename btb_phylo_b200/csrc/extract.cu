@@ -5,14 +5,16 @@
 // two distinct bases occur; kept columns are emitted upper-cased in genome order.
 //
 //   k1 pack_planes   : FASTA text -> 3 bit-planes per sample (code bit 0, code bit 1, validity),
-//                      32 columns per word (bit order: see plane_bit).  code = (byte >> 1) & 3
+//                      32 columns per word, column 32 w + cl at bit cl.  code = (byte >> 1) & 3
 //                      (A=0 C=1 T=2 G=3).  4 bytes are classified at a time with SWAR logic.
 //                      3 bits per base instead of 8 is what lets 50,000 x 4.35 Mb stay in 180 GB.
-//   k2 column_mask   : OR/AND reduction over samples -> seenA, seenC, seenG, seenT, anyInvalid.
+//   k2 column_mask   : OR/AND reduction over samples -> seenA, seenC, seenG, seenT, anyInvalid.  The
+//                      level-1/2 paths get this from k1 itself (btb_pack_planes_state: the state is
+//                      accumulated while the planes are written); the kernel remains for planes that
+//                      are already there (level 3, and the rare re-staged records).
 //   k3 select/compact: keep-mask, popc + shuffle-scan stream compaction of the kept column
 //                      indices, then a gather of those columns for every sample.
-// All three are HBM-bound streaming kernels: bytes = N*G (text) + 3/8 N*G (planes written, read
-// once more by k2) + 2 N*L.
+// All three are HBM-bound streaming kernels: bytes = N*G (text) + 3/8 N*G (planes written) + 2 N*L.
 #include <algorithm>
 #include <vector>
 
@@ -22,19 +24,15 @@ namespace btb {
 
 constexpr int kPackThreads = 256;
 constexpr int kMinLineW = 32;                            // shorter lines go through the host walk (<= 1 line end per 32 columns)
-template <int WPT> struct PackCfg {                      // WPT = plane words (32 columns each) per thread
-    static constexpr int kCols = kPackThreads * 32 * WPT;                     // columns per CTA
-    static constexpr int kStageBytes = kCols + kCols / kMinLineW * 2 + 64;    // staged text incl. terminators
-};
-int g_pack_wpt = 4;                                     // plane words per thread: 4 (128 columns, 16-byte plane stores) or 1
+// One CTA packs kPackWords plane words (32 columns each, one per thread) of every sample it is given.
+// 250 words = 8000 columns: with 60..80-column lines the CTA's text span is just under 2 x 4096 bytes, so the
+// 256 threads classify it in two rounds of 16-byte chunks with next to no idle lanes.
+constexpr int kPackWords = 250;
+constexpr int kPackCols = kPackWords * 32;
+constexpr int kSpanBytes = kPackCols + kPackCols / kMinLineW * 2 + 64;          // text bytes a CTA can touch per sample
+constexpr int kBitWords = (kSpanBytes + 31) / 32 + 4;                           // flag bits of the span, + the words a funnel shift may touch
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
-
-// smem skew: 4 bytes of padding per 32 so that threads 32..36 bytes apart hit distinct banks.  Needed
-// when a thread owns 32 columns (neighbours 8.25 words apart); with 128 columns per thread the
-// neighbours are 33-34 words apart, which is conflict-free as it is.
-template <bool SKEW>
-__device__ __forceinline__ uint32_t skew(uint32_t p) { return SKEW ? p + ((p >> 5) << 2) : p; }
 
 __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     uint4 v;
@@ -43,158 +41,162 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint8_t *p) {
     return v;
 }
 
-// ------------------------------------------------------------------------------------------ k1
-// Bit order inside a plane word: column c = 32 w + cl sits at bit 8 (cl & 3) + (cl >> 2), i.e.
-// byte j of the word holds the columns 4 g + j, bit g.  That is the order in which a 4-byte SWAR
-// classification produces its flags (one flag per byte lane), so k1 needs no bit transposition;
-// k2 is bit-parallel and order-agnostic, k3 undoes the permutation once on the G-bit keep mask.
-__host__ __device__ inline int plane_bit(int cl) { return 8 * (cl & 3) + (cl >> 2); }
-
-// SWAR classification of 4 text bytes.  Flags come out at bit 0 of every byte lane:
-//   valid <=> byte is one of ACGTacgt   (exact; checked exhaustively in tests/test_capi_host.py)
-//   code  = (byte >> 1) & 3             (A 0, C 1, T 2, G 3)
-// hi3 collects bit5|bit6|bit7 of every byte at bit 5: a byte < 0x20 (control character, e.g. a
-// stray CR/LF inside a line) clears it.
-struct Class4 { uint32_t v, b0, b1, hi3; };
-// The bits of every byte lane are lined up at bit 7 with LEFT shifts (the compiler issues them as
-// IMAD.SHL on the FMA pipe, leaving the ALU pipe to the LOP3s); the three flags are then moved to
-// bit 0 of their lane.  hi3 keeps bit5|bit6|bit7 of every byte at bit 7.
-__device__ __forceinline__ Class4 classify4(uint32_t w) {
-    const uint32_t y0 = w << 7, y1 = w << 6, y2 = w << 5, y3 = w << 4, y4 = w << 3, y5 = w << 2, y6 = w << 1;
-    const uint32_t t1 = y0 & (y1 | ~y2);
-    const uint32_t t2 = y2 & ~y1 & ~y0;
-    const uint32_t f = (~y4 & t1) | (y4 & t2);
-    const uint32_t g = ~w & y6 & ~y3;
-    const uint32_t v7 = f & g & 0x80808080u;
-    Class4 c;
-    c.v = v7 >> 7;
-    c.b0 = (v7 & y1) >> 7;
-    c.b1 = (v7 & y2) >> 7;
-    c.hi3 = w | y6 | y5;
-    return c;
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
 }
 
-template <int kPackWordsPerThread>
+// ------------------------------------------------------------------------------------------ k1
+// Bit order inside a plane word: column c = 32 w + cl is bit cl.
+__host__ __device__ inline int plane_bit(int cl) { return cl; }
+
+// SWAR classification of 4 text bytes: one flag per byte lane, at bit 7 of the lane.
+//   v   <=> byte is one of ACGTacgt   (exact; checked exhaustively in tests/test_capi_host.py)
+//   b0, b1 = bits 1, 2 of a valid byte: code = (byte >> 1) & 3  (A 0, C 1, T 2, G 3)
+//   ctl <=> byte < 0x20 (a control character: the line terminators, and nothing else in a well-formed file)
+// Bit k of every byte is lined up at bit 7 with a LEFT shift (IMAD.SHL on the FMA pipe, leaving the ALU pipe to
+// the LOP3s).  With b_k those aligned copies:  valid = ~b7 & b6 & ~b3 & R,  R = b4 ? (b2 & ~b1 & ~b0) : (b0 & (b1 | ~b2))
+// = (u = b2 & ~b1;  b4 ? (u & ~b0) : (b0 & ~u)) -- four LOP3 in all (the decomposition was found by exhaustive search).
+struct Class4 { uint32_t v, b0, b1, ctl; };
+__device__ __forceinline__ Class4 classify4(uint32_t w) {
+    const uint32_t b0 = w << 7, b1 = w << 6, b2 = w << 5, b3 = w << 4, b4 = w << 3, b5 = w << 2, b6 = w << 1;
+    constexpr int A = 0xF0, B = 0xCC, C = 0xAA;
+    const uint32_t u = lop3<(B & ~A) & 0xFF>(b1, b2, 0u);                          // b2 & ~b1
+    const uint32_t R = lop3<((C & A & ~B) | (~C & B & ~A)) & 0xFF>(u, b0, b4);     // b4 ? (u & ~b0) : (b0 & ~u)
+    const uint32_t p = lop3<(~A & B & ~C) & 0xFF>(w, b6, b3);                      // ~b7 & b6 & ~b3
+    Class4 c;
+    c.v = lop3<(A & B & C) & 0xFF>(p, R, 0x80808080u);
+    c.b0 = c.v & b1;
+    c.b1 = c.v & b2;
+    c.ctl = lop3<(~(A | B | C)) & 0xFF>(w, b6, b5) & 0x80808080u;                  // none of bits 7, 6, 5
+    return c;
+}
+// the four lane flags (bits 7, 15, 23, 31) as a nibble, lane 0 (the first text byte) lowest: one multiply gathers
+// them into bits 28..31 (all partial products land on distinct bits, so nothing carries)
+__device__ __forceinline__ uint32_t gather4(uint32_t flags7) { return (flags7 * 0x00204081u) >> 28; }
+
+// k1 with k2 fused in.  grid.x = blocks of kPackCols columns, grid.y = groups of samples; a CTA walks through its
+// samples one after the other:
+//   phase A  the CTA's text span (bases AND line terminators, as they lie in the file) is read once, 16 bytes per
+//            thread and step, coalesced, classified in registers, and the four flags of every text byte go to
+//            four bit arrays in shared memory, in TEXT order -- no staging of the text, no realignment of bytes;
+//   phase B  every thread builds its own plane word (32 columns) from those bit arrays at the BIT level: the
+//            columns are 32 consecutive flag bits, except that after the `rem` bases left on the current line the
+//            text skips e terminator bytes (at most one line end per word since W >= 32) -- three words, three
+//            funnel shifts and one masked merge per plane.  The control-character plane must be empty at the
+//            columns and the terminator bytes must be the expected ones (checked where a line ends: two byte
+//            loads), else the record is flagged and the host re-stages it through its exact parser.
+// The column state (seenA, seenC, seenG, seenT, anyInvalid: what k2 used to recompute from the planes) is
+// accumulated in registers over the CTA's samples and merged into `state` once per launch: plain read-modify-
+// write when the CTA has every sample of the launch (each state word then belongs to exactly one thread; launches
+// on one stream are ordered), atomicOr otherwise.
+// Bytes: N*G text read once + 3/8 N*G planes written; nothing is read twice.
 __global__ void __launch_bounds__(kPackThreads)
 pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const int64_t *__restrict__ rec_off,
-                   const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t first,
+                   const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t n_chunk, int64_t first,
                    int64_t n_total, int64_t G, int64_t words, uint32_t *__restrict__ planes,
-                   int32_t *__restrict__ flags) {
-    constexpr bool kSkew = kPackWordsPerThread == 1;
-    constexpr int kPackCols = PackCfg<kPackWordsPerThread>::kCols;
-    constexpr int kPackStageBytes = PackCfg<kPackWordsPerThread>::kStageBytes;
-    __shared__ __align__(16) uint8_t stage[kPackStageBytes + kPackStageBytes / 8 + 64];
-    const int64_t i = blockIdx.y;
+                   int32_t *__restrict__ flags, uint32_t *__restrict__ state) {
+    __shared__ __align__(16) uint32_t bits[2][4][kBitWords];       // [buffer][v, b0, b1, ctl][text bit]
     const int64_t c0 = int64_t(blockIdx.x) * kPackCols;
-    const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
-    const int64_t rec = rec_off[i];
-    const int64_t wbase = (c0 >> 5) + kPackWordsPerThread * threadIdx.x;     // first plane word of this thread
-    uint32_t *p0 = planes + (0 * n_total + first + i) * words + wbase;
-    uint32_t *p1 = planes + (1 * n_total + first + i) * words + wbase;
-    uint32_t *pv = planes + (2 * n_total + first + i) * words + wbase;
-    const bool owns = wbase < words;                      // words is a multiple of 4: all of this thread's words or none
-    if (c0 >= G || (W && W < kMinLineW)) {                // padding words / layout the host must re-stage
-        if (owns) {
-#pragma unroll
-            for (int k = 0; k < kPackWordsPerThread; ++k) p0[k] = p1[k] = pv[k] = 0;
+    const int64_t w = (c0 >> 5) + threadIdx.x;                      // this thread's plane word
+    const bool owns = threadIdx.x < kPackWords && w < words;
+    const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);           // genome lengths fit 32 bits (the tools use int)
+    const uint32_t ce = (c0 >= G) ? cb : (G32 - cb < uint32_t(kPackCols) ? G32 : cb + uint32_t(kPackCols));   // end of this CTA's columns
+    const uint32_t c = cb + 32u * threadIdx.x;                      // first column of this thread's word
+    const int64_t per = (n_chunk + gridDim.y - 1) / gridDim.y;
+    const int64_t s_lo = int64_t(blockIdx.y) * per, s_hi = s_lo + per < n_chunk ? s_lo + per : n_chunk;
+    uint32_t sA = 0, sC = 0, sG = 0, sT = 0, sInv = 0;
+    uint32_t parity = 0;                                           // bit-array buffer of the next sample that gets that far
+    auto is_marker = [](uint32_t b) { return b == '>' || b == '@' || b == '+'; };
+    auto byte_at = [&](int64_t a) -> uint32_t { return a < text_bytes ? uint32_t(text[a]) : 0x20u; };
+    for (int64_t i = s_lo; i < s_hi; ++i) {
+        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+        const int64_t rec = rec_off[i];
+        uint32_t *p0 = planes + (0 * n_total + first + i) * words + w;
+        uint32_t *p1 = planes + (1 * n_total + first + i) * words + w;
+        uint32_t *pv = planes + (2 * n_total + first + i) * words + w;
+        if (cb >= ce || (W && W < kMinLineW)) {            // padding words / a layout the host must re-stage
+            if (owns) { *p0 = 0; *p1 = 0; *pv = 0; }
+            if (cb < ce && threadIdx.x == 0) atomicOr(&flags[i], 1);
+            continue;                                       // (uniform for the CTA: no barrier is skipped by a part of it)
         }
-        if (c0 < G && threadIdx.x == 0) atomicOr(&flags[i], 1);
-        return;
-    }
-    // genome lengths fit 32 bits (the tools use int): 32-bit divisions only
-    const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);
-    const uint32_t ce = G32 - cb < uint32_t(kPackCols) ? G32 : cb + uint32_t(kPackCols);      // end of this CTA's columns
-    auto off = [&](uint32_t c) -> int64_t { return W ? int64_t(c) + int64_t(c / W) * e : int64_t(c); };
-    const int64_t lo = rec + off(cb);
-    int64_t hi = rec + off(ce - 1) + 1 + e;               // incl. the terminator after the last column
-    if (hi > text_bytes) hi = text_bytes;
-    const int64_t alo = lo & ~int64_t(15);
-    const int nchunk = int((hi - alo + 15) >> 4) + 1;      // +1: the funnel shift may touch one word beyond
-    for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
-        uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
-        if (alo + 16 * int64_t(j) < text_bytes) v = ld_nc_v4(text + alo + 16 * int64_t(j));
-        uint32_t *d = reinterpret_cast<uint32_t *>(stage + skew<kSkew>(16u * j));
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    __syncthreads();
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
-    auto word_at = [&](uint32_t q) { return sw[kSkew ? q + (q >> 3) : q]; };     // q = unskewed word index
-    const uint32_t c = cb + 32u * kPackWordsPerThread * threadIdx.x;
-    uint32_t out_v[kPackWordsPerThread], out_0[kPackWordsPerThread], out_1[kPackWordsPerThread];
-    uint32_t nonctl = 0x80808080u;
-    bool irregular = false, marker = false;
-    const uint32_t line = (W && c < ce) ? c / W : 0u;
-    uint32_t pos = W ? c - line * W : 0u;                  // column inside the current line
-    uint32_t o = uint32_t(rec + int64_t(c) + int64_t(line) * e - alo);      // byte offset inside the staged span
-    // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the
-    // parser the tools share (it opens the next record / a quality block): the host must re-index
-    auto is_marker = [](uint8_t b) { return b == '>' || b == '@' || b == '+'; };
-    if (c < ce && pos == 0 && (W || c == 0)) marker = is_marker(stage[skew<kSkew>(o)]);
+        auto off = [&](uint32_t col) -> int64_t { return W ? int64_t(col) + int64_t(col / W) * e : int64_t(col); };
+        const int64_t lo = rec + off(cb);
+        int64_t hi = rec + off(ce - 1) + 1 + e;           // incl. the terminator after the last column
+        if (hi > text_bytes) hi = text_bytes;
+        const int64_t alo = lo & ~int64_t(15);
+        const int nchunk = int((hi - alo + 15) >> 4) + 1;  // + 1: phase B may look one word beyond
+        uint32_t(*buf)[kBitWords] = bits[parity];
+        parity ^= 1u;
+        // ---- phase A: classify the text, 16 bytes per thread and step
+        for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
+            uint4 t4 = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+            if (alo + 16 * int64_t(j) < text_bytes) t4 = ld_nc_v4(text + alo + 16 * int64_t(j));
+            const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+            uint32_t hv = 0, h0 = 0, h1 = 0, hc = 0;
 #pragma unroll
-    for (int wi = 0; wi < kPackWordsPerThread; ++wi) {
-        uint32_t fv = 0, f0 = 0, f1 = 0;
-        const uint32_t cw = c + 32u * wi;
-        if (cw < ce) {
-            const uint32_t ncols = ce - cw < 32u ? ce - cw : 32u;
-            // Branch-free for every lane: the 32 columns are the bytes o .. o+31, except that after the
-            // `rem` bases left on the current line the text skips e terminator bytes (at most one line
-            // end per word since W >= 32).  A[g] reads group g before the line end, B[g] after it.
-            const uint32_t rem = W ? W - pos : 0xFFFFu;
-            const uint32_t qa = o >> 2, sa = (o & 3u) * 8u, ob = o + e, qb = ob >> 2, sb = (ob & 3u) * 8u;
-            // groups are visited last to first so that the plane words build up as F = 2 F + flags
-            // (an IMAD on the FMA pipe): group g ends at bit g of its byte lane
-            const uint32_t bg = rem >> 2, bm = (1u << (8u * (rem & 3u))) - 1u;       // break group / its byte mask
-            const bool partial = ncols < 32u;              // only the last word of a row
-            uint32_t tail[8];
-            if (partial) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int have = int(ncols) - 4 * g;
-                    tail[g] = have >= 4 ? 0xFFFFFFFFu : (have <= 0 ? 0u : (1u << (8 * have)) - 1u);
-                }
+            for (int k = 0; k < 4; ++k) {
+                const Class4 f = classify4(tw[k]);
+                hv += gather4(f.v) << (4 * k); h0 += gather4(f.b0) << (4 * k);
+                h1 += gather4(f.b1) << (4 * k); hc += gather4(f.ctl) << (4 * k);
             }
-            uint32_t na = word_at(qa + 8), nb = word_at(qb + 8);
-#pragma unroll
-            for (int g = 7; g >= 0; --g) {
-                const uint32_t ca = word_at(qa + g), cbw = word_at(qb + g);
-                const uint32_t A = __funnelshift_r(ca, na, sa), B = __funnelshift_r(cbw, nb, sb);
-                na = ca; nb = cbw;
-                // bytes of this group that still belong to the current line come from A, the rest from B
-                const uint32_t m = uint32_t(g) < bg ? 0xFFFFFFFFu : (uint32_t(g) == bg ? bm : 0u);
-                uint32_t w = (A & m) | (B & ~m);
-                if (partial) w = (w & tail[g]) | (0x20202020u & ~tail[g]);     // last word of the row: blank columns >= G
-                const Class4 k = classify4(w);
-                fv = fv * 2u + k.v; f0 = f0 * 2u + k.b0; f1 = f1 * 2u + k.b1;
-                nonctl &= k.hi3;
-            }
-            if (rem <= ncols) {                             // a line ends inside (or exactly at the end of) this word
-                if (cw + rem < G32) {                       // ... and more bases follow: the terminator must be there
-                    const uint32_t t = o + rem;
-                    if (e == 1) irregular |= stage[skew<kSkew>(t)] != '\n';
-                    else irregular |= (stage[skew<kSkew>(t)] != '\r') | (stage[skew<kSkew>(t + 1)] != '\n');
-                    marker |= is_marker(stage[skew<kSkew>(t + e)]);      // first byte of the next line
-                }
-                o += 32u + e;
-                pos = 32u - rem;
-            } else {
-                o += 32u;
-                pos += 32u;
-            }
+            reinterpret_cast<uint16_t *>(buf[0])[j] = uint16_t(hv);
+            reinterpret_cast<uint16_t *>(buf[1])[j] = uint16_t(h0);
+            reinterpret_cast<uint16_t *>(buf[2])[j] = uint16_t(h1);
+            reinterpret_cast<uint16_t *>(buf[3])[j] = uint16_t(hc);
         }
-        out_v[wi] = fv; out_0[wi] = f0; out_1[wi] = f1;
+        __syncthreads();                                   // (the other buffer is free again: everyone is past its phase B)
+        // ---- phase B: this thread's 32 columns, taken from the bit arrays
+        if (c < ce) {
+            const uint32_t ncols = ce - c < 32u ? ce - c : 32u;
+            const uint32_t line = W ? c / W : 0u;
+            const uint32_t pos = W ? c - line * W : 0u;    // column inside the current line
+            const uint32_t rem = W ? W - pos : 0xFFFFu;    // bases left on that line
+            const int64_t at = rec + int64_t(c) + int64_t(line) * e;       // text offset of column c
+            const uint32_t o = uint32_t(at - alo);         // = bit index in the arrays
+            const uint32_t q = o >> 5, sh = o & 31u;
+            const uint32_t M = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;          // columns before the line end
+            const uint32_t colmask = ncols >= 32u ? 0xFFFFFFFFu : (1u << ncols) - 1u;  // last word of a row: columns < G
+            auto take = [&](const uint32_t *a) {
+                const uint32_t a0 = a[q], a1 = a[q + 1], a2 = a[q + 2];
+                const uint32_t x0 = __funnelshift_r(a0, a1, sh), x1 = __funnelshift_r(a1, a2, sh);
+                return ((x0 & M) | (__funnelshift_r(x0, x1, e) & ~M)) & colmask;
+            };
+            const uint32_t fv = take(buf[0]), f0 = take(buf[1]), f1 = take(buf[2]), fc = take(buf[3]);
+            bool irregular = fc != 0;                      // a control character among the bases
+            bool marker = false;
+            // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
+            // the tools share (it opens the next record / a quality block): the host must re-index
+            if (pos == 0 && (W || c == 0)) marker = is_marker(byte_at(at));
+            if (rem <= ncols && c + rem < G32) {           // a line ends inside (or at the end of) this word and more bases follow
+                const int64_t t = at + rem;
+                if (e == 1) irregular |= byte_at(t) != '\n';
+                else irregular |= (byte_at(t) != '\r') | (byte_at(t + 1) != '\n');
+                marker |= is_marker(byte_at(t + e));       // first byte of the next line
+            }
+            if (owns) { *p0 = f0; *p1 = f1; *pv = fv; }
+            sA |= fv & ~f1 & ~f0; sC |= fv & ~f1 & f0; sT |= fv & f1 & ~f0; sG |= fv & f1 & f0;
+            sInv |= ~fv & colmask;
+            if (irregular) atomicOr(&flags[i], 1);
+            if (marker) atomicOr(&flags[i], 2);
+        } else if (owns) {
+            *p0 = 0; *p1 = 0; *pv = 0;                     // padding words of the last column block
+        }
     }
-    if (owns) {
-        if constexpr (kPackWordsPerThread == 4) {
-            *reinterpret_cast<uint4 *>(p0) = make_uint4(out_0[0], out_0[1], out_0[2], out_0[3]);
-            *reinterpret_cast<uint4 *>(p1) = make_uint4(out_1[0], out_1[1], out_1[2], out_1[3]);
-            *reinterpret_cast<uint4 *>(pv) = make_uint4(out_v[0], out_v[1], out_v[2], out_v[3]);
+    if (state && owns && c < ce && s_hi > s_lo) {
+        uint32_t *d = state + w;
+        if (gridDim.y == 1) {
+            d[0] |= sA; d[words] |= sC; d[2 * words] |= sG; d[3 * words] |= sT; d[4 * words] |= sInv;
         } else {
-#pragma unroll
-            for (int k = 0; k < kPackWordsPerThread; ++k) { p0[k] = out_0[k]; p1[k] = out_1[k]; pv[k] = out_v[k]; }
+            if (sA) atomicOr(d, sA);
+            if (sC) atomicOr(d + words, sC);
+            if (sG) atomicOr(d + 2 * words, sG);
+            if (sT) atomicOr(d + 3 * words, sT);
+            if (sInv) atomicOr(d + 4 * words, sInv);
         }
     }
-    if (irregular || (nonctl & 0x80808080u) != 0x80808080u) atomicOr(&flags[i], 1);
-    if (marker) atomicOr(&flags[i], 2);
 }
 
 // ------------------------------------------------------------------------------------------ k2
@@ -356,27 +358,44 @@ using namespace btb;
 // =============================================================================== C-ABI, level 3
 extern "C" int64_t btb_plane_words(int64_t G) { return plane_words(G); }
 
+namespace btb {
+// k1 (+ k2 when d_colstate != nullptr: the column state of these samples is OR-ed into it)
+int pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off, const int32_t *d_line_w,
+                const int32_t *d_eol, int64_t n_chunk, int64_t first, int64_t n_total, int64_t G, uint32_t *d_planes,
+                int32_t *d_flags, uint32_t *d_colstate, cudaStream_t stream) {
+    const int64_t words = plane_words(G);
+    const int64_t gx = (words + kPackWords - 1) / kPackWords;
+    // sample groups: one CTA per column block takes ALL samples of the launch (plain state merge) unless that
+    // leaves the GPU short of CTAs and every group still gets enough samples to make its atomics cheap
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int64_t gy = 1;
+    if (gx < int64_t(sms) * 4) gy = std::max<int64_t>(1, std::min<int64_t>((int64_t(sms) * 6 + gx - 1) / gx, n_chunk / (d_colstate ? 24 : 1)));
+    gy = std::max<int64_t>(1, std::min<int64_t>(gy, std::min<int64_t>(n_chunk, 65535)));
+    pack_planes_kernel<<<dim3((unsigned)gx, (unsigned)gy), kPackThreads, 0, stream>>>(
+        d_text, text_bytes, d_rec_off, d_line_w, d_eol, n_chunk, first, n_total, G, words, d_planes, d_flags, d_colstate);
+    BTB_CUDA(cudaGetLastError());
+    return BTB_OK;
+}
+}  // namespace btb
+
 extern "C" int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
                                const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
                                int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream) {
     if (!d_text || !d_rec_off || !d_line_w || !d_eol || !d_planes || !d_flags || n_chunk <= 0 || G <= 0)
         return fail(BTB_EINVAL, "btb_pack_planes: bad argument");
-    const int64_t words = plane_words(G);
-    const int wpt = g_pack_wpt == 4 ? 4 : 1;
-    const int64_t cols = wpt == 4 ? PackCfg<4>::kCols : PackCfg<1>::kCols;
-    const int64_t gx = (words * 32 + cols - 1) / cols;
-    for (int64_t y0 = 0; y0 < n_chunk; y0 += 65535) {
-        const int64_t ny = std::min<int64_t>(65535, n_chunk - y0);
-        dim3 grid((unsigned)gx, (unsigned)ny);
-        if (wpt == 4)
-            pack_planes_kernel<4><<<grid, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-                d_text, text_bytes, d_rec_off + y0, d_line_w + y0, d_eol + y0, first + y0, n_total, G, words, d_planes, d_flags + y0);
-        else
-            pack_planes_kernel<1><<<grid, kPackThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-                d_text, text_bytes, d_rec_off + y0, d_line_w + y0, d_eol + y0, first + y0, n_total, G, words, d_planes, d_flags + y0);
-    }
-    BTB_CUDA(cudaGetLastError());
-    return BTB_OK;
+    return pack_planes(d_text, text_bytes, d_rec_off, d_line_w, d_eol, n_chunk, first, n_total, G, d_planes, d_flags, nullptr,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int btb_pack_planes_state(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
+                                     const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
+                                     int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags,
+                                     uint32_t *d_colstate, void *stream) {
+    if (!d_text || !d_rec_off || !d_line_w || !d_eol || !d_planes || !d_flags || !d_colstate || n_chunk <= 0 || G <= 0)
+        return fail(BTB_EINVAL, "btb_pack_planes_state: bad argument");
+    return pack_planes(d_text, text_bytes, d_rec_off, d_line_w, d_eol, n_chunk, first, n_total, G, d_planes, d_flags, d_colstate,
+                       static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int btb_column_mask(const uint32_t *d_planes, int64_t n, int64_t n_total, int64_t G,

@@ -22,6 +22,9 @@ namespace btb {
 int require_device(int device);
 std::vector<int> usable_devices();
 std::vector<int> worker_devices(int n_gpus);
+int pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off, const int32_t *d_line_w,
+                const int32_t *d_eol, int64_t n_chunk, int64_t first, int64_t n_total, int64_t G, uint32_t *d_planes,
+                int32_t *d_flags, uint32_t *d_colstate, cudaStream_t stream);
 extern int g_replace_unlink_first;
 int first_usable_device();
 }
@@ -67,11 +70,10 @@ void parallel_for(int64_t n, int threads, const std::function<void(int64_t, int6
     for (auto &th : pool) th.join();
 }
 
-// After all samples are packed: reduce, select, gather.  Leaves L in *L_out, the kept-column
-// indices in d_idx, the keep bitmask in d_keep.
-int reduce_and_select(const uint32_t *d_planes, int64_t n, int64_t G, int pure_mode, uint32_t *d_state,
-                      uint32_t *d_keep, uint32_t *d_idx, uint32_t *d_count, int64_t *L_out, cudaStream_t st) {
-    BTB_TRY(btb_column_mask(d_planes, n, n, G, d_state, 0, st));
+// After all samples are packed (and their column state accumulated by k1): select.  Leaves L in *L_out, the
+// kept-column indices in d_idx, the keep bitmask in d_keep.
+int select_only(int64_t G, int pure_mode, uint32_t *d_state, uint32_t *d_keep, uint32_t *d_idx, uint32_t *d_count,
+                int64_t *L_out, cudaStream_t st) {
     BTB_TRY(btb_select_columns(d_state, G, pure_mode, d_keep, d_idx, d_count, st));
     uint32_t L = 0;
     BTB_CUDA(cudaMemcpyAsync(&L, d_count, 4, cudaMemcpyDeviceToHost, st));
@@ -106,6 +108,7 @@ extern "C" int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64
     BTB_TRY(el.alloc(size_t(chunk_rows * 4)));
     BTB_TRY(flags.alloc(size_t(n * 4)));
     BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(n * 4), st.s));
+    BTB_CUDA(cudaMemsetAsync(state.p, 0, size_t(5 * words * 4), st.s));
     BTB_CUDA(cudaMemsetAsync(lw.p, 0, size_t(chunk_rows * 4), st.s));
     BTB_CUDA(cudaMemsetAsync(el.p, 0, size_t(chunk_rows * 4), st.s));
     std::vector<int64_t> h_off(static_cast<size_t>(chunk_rows));
@@ -115,12 +118,12 @@ extern "C" int btb_extract_host(const uint8_t *seqs, int64_t n, int64_t G, int64
         const int64_t rows = std::min(chunk_rows, n - r0);
         BTB_CUDA(cudaMemcpy2DAsync(text.p, size_t(d_stride), seqs + r0 * row_stride, size_t(row_stride), size_t(G),
                                    size_t(rows), cudaMemcpyHostToDevice, st.s));
-        BTB_TRY(btb_pack_planes(text.as<uint8_t>(), rows * d_stride, off.as<int64_t>(), lw.as<int32_t>(),
-                                el.as<int32_t>(), rows, r0, n, G, planes.as<uint32_t>(), flags.as<int32_t>() + r0, st.s));
+        // k1 with the column state accumulated on the way (no second pass over the planes)
+        BTB_TRY(pack_planes(text.as<uint8_t>(), rows * d_stride, off.as<int64_t>(), lw.as<int32_t>(), el.as<int32_t>(), rows, r0, n, G,
+                            planes.as<uint32_t>(), flags.as<int32_t>() + r0, state.as<uint32_t>(), st.s));
     }
     int64_t L = 0;
-    BTB_TRY(reduce_and_select(planes.as<uint32_t>(), n, G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(),
-                              idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
+    BTB_TRY(select_only(G, pure_mode, state.as<uint32_t>(), keepw.as<uint32_t>(), idx.as<uint32_t>(), count.as<uint32_t>(), &L, st.s));
     *n_snps = L;
     if (keep) {
         std::vector<uint32_t> hk(static_cast<size_t>(words));
@@ -164,6 +167,7 @@ struct ExtractCtx {
     std::vector<int64_t> h_off;
     std::vector<int32_t> h_lw, h_el;
     double t_wait = 0, t_fill = 0, t_enqueue = 0;      // BTB_TIMING: where run_chunk spends its time
+    bool restaged = false;                             // a record was packed twice (see pack_all)
 
     ~ExtractCtx() {
         for (int k = 0; k < 2; ++k)
@@ -183,6 +187,7 @@ struct ExtractCtx {
         BTB_TRY(d_lw.alloc(size_t(nloc * 4)));
         BTB_TRY(d_el.alloc(size_t(nloc * 4)));
         BTB_CUDA(cudaMemsetAsync(flags.p, 0, size_t(nloc * 4), st.s));
+        BTB_CUDA(cudaMemsetAsync(state.p, 0, size_t(5 * words * 4), st.s));
         size_t max_rec = 0;
         for (int64_t i = s0; i < s1; ++i) max_rec = std::max(max_rec, recs[size_t(i)].raw_len + 64);
         // 64 MB chunks keep the H2D pipeline busy; larger pinned buffers only cost allocation time
@@ -257,8 +262,10 @@ struct ExtractCtx {
         BTB_CUDA(cudaMemcpyAsync(d_off.as<int64_t>() + l0, h_off.data() + l0, size_t(cnt) * 8, cudaMemcpyHostToDevice, st.s));
         BTB_CUDA(cudaMemcpyAsync(d_lw.as<int32_t>() + l0, h_lw.data() + l0, size_t(cnt) * 4, cudaMemcpyHostToDevice, st.s));
         BTB_CUDA(cudaMemcpyAsync(d_el.as<int32_t>() + l0, h_el.data() + l0, size_t(cnt) * 4, cudaMemcpyHostToDevice, st.s));
-        BTB_TRY(btb_pack_planes(d_text[b].as<uint8_t>(), int64_t(total), d_off.as<int64_t>() + l0, d_lw.as<int32_t>() + l0,
-                                d_el.as<int32_t>() + l0, cnt, l0, nloc, G, planes.as<uint32_t>(), flags.as<int32_t>() + l0, st.s));
+        // k1 + k2 in one pass: the planes are written and the column state of these samples is OR-ed into `state`
+        BTB_TRY(pack_planes(d_text[b].as<uint8_t>(), int64_t(total), d_off.as<int64_t>() + l0, d_lw.as<int32_t>() + l0,
+                            d_el.as<int32_t>() + l0, cnt, l0, nloc, G, planes.as<uint32_t>(), flags.as<int32_t>() + l0,
+                            state.as<uint32_t>(), st.s));
         BTB_CUDA(cudaEventRecord(done[b], st.s));
         used[b] = true;
         t_enqueue += wall_s() - tw2;
@@ -291,12 +298,18 @@ struct ExtractCtx {
         for (int64_t i = s0; i < s1; ++i) {
             if (!h_flags[size_t(i - s0)]) continue;
             if (!src.fb) return kRetryExact;
+            restaged = true;
             FastaRecord &r = recs[size_t(i)];
             r.seq_len = walk_record(*src.fb, r, nullptr);
             r.regular = false;
             if (r.seq_len != G) { *bad = i; return BTB_OK; }
             BTB_TRY(run_chunk(src, recs, G, b, i, i + 1, true));
             b ^= 1;
+        }
+        if (restaged) {
+            // the first packing of those records (with the layout their first line promised) has already been OR-ed
+            // into the column state, which cannot be undone: recompute it from the final planes (k2)
+            BTB_TRY(btb_column_mask(planes.as<uint32_t>(), nloc, nloc, G, state.as<uint32_t>(), 0, st.s));
         }
         BTB_CUDA(cudaStreamSynchronize(st.s));
         if (getenv("BTB_TIMING"))
@@ -381,13 +394,12 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
         int64_t bad = -1;
         BTB_TRY(c.pack_all(src, recs, G, &bad));
         if (bad >= 0) { std::lock_guard<std::mutex> lock(bad_mutex); if (bad_record < 0 || bad < bad_record) bad_record = int(bad); return BTB_OK; }
-        BTB_TRY(btb_column_mask(c.planes.as<uint32_t>(), c.nloc, c.nloc, G, c.state.as<uint32_t>(), 0, c.st.s));
         BTB_CUDA(cudaMemcpyAsync(h_state[size_t(c.slot)].data(), c.state.p, size_t(5 * words * 4), cudaMemcpyDeviceToHost, c.st.s));
         BTB_CUDA(cudaStreamSynchronize(c.st.s));
         return BTB_OK;
     }));
     if (bad_record >= 0) return unequal(recs[size_t(bad_record)]);
-    timer.mark("stage + H2D + k1 pack + k2 mask");
+    timer.mark("stage + H2D + k1 pack (column state fused in)");
 
     // exchange: OR the per-device column states on the host (5 words per 32 columns, a few MB)
     for (int d = 1; d < n_dev; ++d)

@@ -71,7 +71,7 @@ int         btb_device_count(int *count);                 /* number of usable sm
  *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (for ncu)
  *     "umma_prefetch" [0], "umma_tile_bk" [128], "umma_cta_group" [1], "umma_cg2_variant" [0]: measured alternatives
  *       (L2 prefetch distance, 64-byte K blocks with six stages, int8 CTA pairs) kept for the record, see DESIGN.md
- *   extraction: "pack_wpt" [4] plane words per thread of k1; "ingest_predict" [1] predicted FASTA framing
+ *   extraction: "ingest_predict" [1] predicted FASTA framing
  *   level 1/2:  "csv_mmap" [0] write snps.csv through a file mapping; "dense_pageable" [1] large snps.fas into
  *               pageable host memory; "host_stream" [0] + "host_stream_rows" [64] streamed level-2 call
  * btb_query also answers "ingest_last_predicted", "host_stream_last", "umma_max_active_clusters_cg1|2" and
@@ -172,14 +172,23 @@ int64_t btb_plane_words(int64_t G);
  * 16-byte boundary).  Sample i's bases start at d_text + rec_off[i]; its lines are line_w[i] bases
  * followed by eol[i] line-terminator bytes (line_w = 0: unwrapped; otherwise >= 32).  Writes three
  * planes per sample (code bit 0, code bit 1, ACGT validity; code = (byte >> 1) & 3), plane p of
- * sample i at d_planes + ((p * n_total + first + i) * words); column c = 32 w + cl is bit
- * 8 (cl & 3) + (cl >> 2) of word w (the order a 4-byte SWAR classification produces).  d_flags[i] is
+ * sample i at d_planes + ((p * n_total + first + i) * words); column c = 32 w + cl is bit cl of
+ * word w.  d_flags[i] is
  * OR-ed with 1 when a line terminator is not where the layout says or a control byte sits among the
  * bases (the caller then re-stages that record unwrapped), and with 2 when a line of the region starts
  * with '>', '@' or '+' (the region is then not one record: the caller must frame the file again). */
 int btb_pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
                     const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
                     int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags, void *stream);
+
+/* k1 with k2 fused in: as btb_pack_planes, and the column state of these samples (see btb_column_mask) is
+ * OR-ed into d_colstate (5 x btb_plane_words(G) words, zeroed by the caller before the first chunk) in the
+ * same pass -- the planes are never read back for it.  Launches that share a d_colstate must be issued on one
+ * stream.  This is what btb_snp_sites and btb_extract_host use. */
+int btb_pack_planes_state(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_off,
+                          const int32_t *d_line_w, const int32_t *d_eol, int64_t n_chunk, int64_t first,
+                          int64_t n_total, int64_t G, uint32_t *d_planes, int32_t *d_flags,
+                          uint32_t *d_colstate, void *stream);
 
 /* k2: per-column reduction over samples [0, n) -> 5 words per 32 columns in d_colstate:
  * seenA, seenC, seenG, seenT, anyInvalid.  accumulate != 0 ORs into existing state. */

@@ -73,7 +73,7 @@ def test_level3_pack_wrapped_text(capi, oracle):
     f = flags.cpu().numpy()
     assert f[7] == 1 and f[8] == 1 and (f[:7] == 0).all()
     pl = planes.cpu().numpy().view(np.uint32).reshape(3, n, words)
-    order = np.array([8 * (cl & 3) + (cl >> 2) for cl in range(32)], dtype=np.uint32)     # plane bit of column cl
+    order = np.arange(32, dtype=np.uint32)                                                   # plane bit of column cl
     bits = lambda w: ((w[:, None] >> order[None, :]) & 1).reshape(-1)[:G]
     for i in range(n):
         if i in (7, 8):

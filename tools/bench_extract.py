@@ -137,8 +137,18 @@ def main():
     t_pack = timed(pack_all, reps=3)
     pack_bytes = n_res * (G + G // 60) + n_res * 3 * words * 4
     state = torch.zeros(5 * words, dtype=torch.int32, device="cuda")
+
+    def pack_all_fused():                                  # what btb_snp_sites runs: k1 with the column state (k2) fused in
+        state.zero_()
+        for first in range(0, n_res, chunk_n):
+            m = min(chunk_n, n_res - first)
+            _capi.check(lib.btb_pack_planes_state(P(d_text), text_bytes, P(d_off), P(d_lw), P(d_el), m, first, n_res, G, P(planes), P(flags[first:]), P(state), st))
+
+    t_fused = timed(pack_all_fused, reps=3)
+    state_fused = state.clone()
     t_mask = timed(lambda: _capi.check(lib.btb_column_mask(P(planes), n_res, n_res, G, P(state), 0, st)))
     mask_bytes = n_res * 3 * words * 4
+    fused_equals_k2 = bool((state_fused == state).all().item())
     keep = torch.zeros(words, dtype=torch.int32, device="cuda")
     idx = torch.zeros(words * 32, dtype=torch.int32, device="cuda")
     cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -162,6 +172,9 @@ def main():
     out = {
         "stage": "extraction (snp-sites -c)", "n_samples": n, "genome": G, "fasta_bytes": size, "number_of_snps": meta["number_of_snps"],
         "resident_samples_for_kernel_timing": n_res, "irregular_flags": irregular,
+        "k1_pack_with_column_state": {"seconds": t_fused, "algorithmic_bytes": pack_bytes, "GBps": pack_bytes / t_fused / 1e9,
+                                      "frac_of_hbm_peak": pack_bytes / t_fused / 1e9 / hbm, "records_per_launch": chunk_n,
+                                      "state_equals_separate_k2": fused_equals_k2},
         "k1_pack": {"seconds": t_pack, "algorithmic_bytes": pack_bytes, "GBps": pack_bytes / t_pack / 1e9, "frac_of_hbm_peak": pack_bytes / t_pack / 1e9 / hbm},
         "k2_column_mask": {"seconds": t_mask, "algorithmic_bytes": mask_bytes, "GBps": mask_bytes / t_mask / 1e9, "frac_of_hbm_peak": mask_bytes / t_mask / 1e9 / hbm},
         "k3_select": {"seconds": t_sel}, "k3_compact": {"seconds": t_cmp, "L": L},
