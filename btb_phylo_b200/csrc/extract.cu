@@ -24,13 +24,19 @@ namespace btb {
 
 constexpr int kPackThreads = 256;
 constexpr int kMinLineW = 32;                            // shorter lines go through the host walk (<= 1 line end per 32 columns)
-// One CTA packs kPackWords plane words (32 columns each, one per thread) of every sample it is given.
-// 250 words = 8000 columns: with 60..80-column lines the CTA's text span is just under 2 x 4096 bytes, so the
-// 256 threads classify it in two rounds of 16-byte chunks with next to no idle lanes.
-constexpr int kPackWords = 250;
-constexpr int kPackCols = kPackWords * 32;
-constexpr int kSpanBytes = kPackCols + kPackCols / kMinLineW * 2 + 64;          // text bytes a CTA can touch per sample
-constexpr int kBitWords = (kSpanBytes + 31) / 32 + 4;                           // flag bits of the span, + the words a funnel shift may touch
+// One CTA packs kPackThreadsB x WPT plane words (32 columns each, WPT consecutive words per thread) of every sample it
+// is given.  250 x WPT words = 8000 x WPT columns: with 60..80-column lines the CTA's text span is just under
+// 2 x WPT x 4096 bytes, so the 256 threads classify it in 2 x WPT rounds of 16-byte chunks with next to no idle lanes.
+constexpr int kPackThreadsB = 250;                       // threads that own plane words
+template <int WPT> struct PackCfg {
+    static constexpr int kWords = kPackThreadsB * WPT;
+    static constexpr int kCols = kWords * 32;
+    static constexpr int kSpanBytes = kCols + kCols / kMinLineW * 2 + 64;       // text bytes a CTA can touch per sample
+    static constexpr int kStageBytes = (kSpanBytes + 16 + 15) / 16 * 16;
+    static constexpr int kBitWords = (kSpanBytes + 31) / 32 + 4;                // flag bits of the span + what a funnel shift may touch
+    static constexpr int kSmemBytes = 3 * kStageBytes + 2 * 3 * kBitWords * 4 + 64;
+};
+int g_pack_wpt = 2;                                      // "pack_wpt": plane words per thread of k1 (1, 2 or 4)
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 
@@ -53,148 +59,270 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 __host__ __device__ inline int plane_bit(int cl) { return cl; }
 
 // SWAR classification of 4 text bytes: one flag per byte lane, at bit 7 of the lane.
-//   v   <=> byte is one of ACGTacgt   (exact; checked exhaustively in tests/test_capi_host.py)
-//   b0, b1 = bits 1, 2 of a valid byte: code = (byte >> 1) & 3  (A 0, C 1, T 2, G 3)
-//   ctl <=> byte < 0x20 (a control character: the line terminators, and nothing else in a well-formed file)
-// Bit k of every byte is lined up at bit 7 with a LEFT shift (IMAD.SHL on the FMA pipe, leaving the ALU pipe to
-// the LOP3s).  With b_k those aligned copies:  valid = ~b7 & b6 & ~b3 & R,  R = b4 ? (b2 & ~b1 & ~b0) : (b0 & (b1 | ~b2))
-// = (u = b2 & ~b1;  b4 ? (u & ~b0) : (b0 & ~u)) -- four LOP3 in all (the decomposition was found by exhaustive search).
-struct Class4 { uint32_t v, b0, b1, ctl; };
+//   v  <=> byte is one of ACGTacgt   (exact; checked exhaustively in tests/test_capi_host.py)
+//   f1 = bit 2 of a valid byte, f0 = bit 1 of a valid byte: code = (byte >> 1) & 3  (A 0, C 1, T 2, G 3)
+//   f0 is ALSO set for a control character (byte < 0x20: the line terminators, and nothing else in a well-formed
+//   file).  A control character is never valid, so "f0 without v" marks it: the planes need no fourth flag.
+// Bit k of every byte is lined up at bit 7 with a LEFT shift (IMAD.SHL: the FMA pipe, which has twice the ALU
+// pipe's rate and little else to do here).  With b_k those aligned copies and m7 = 0x80 where bit 7 is clear:
+//   valid = m7 & b6 & ~b3 & R,   R = b4 ? (b2 & ~b1 & ~b0) : (b0 & (b1 | ~b2)) = (u = b2 & ~b1;  b4 ? (u & ~b0) : (b0 & ~u))
+// (that two-LOP3 form of R was found by exhaustive search) -- eight LOP3 per four bytes in all.
+struct Class4 { uint32_t v, f0, f1; };
 __device__ __forceinline__ Class4 classify4(uint32_t w) {
     const uint32_t b0 = w << 7, b1 = w << 6, b2 = w << 5, b3 = w << 4, b4 = w << 3, b5 = w << 2, b6 = w << 1;
     constexpr int A = 0xF0, B = 0xCC, C = 0xAA;
+    const uint32_t m7 = lop3<(~A & B) & 0xFF>(w, 0x80808080u, 0u);                 // bit 7 of the lane where the byte's is clear
     const uint32_t u = lop3<(B & ~A) & 0xFF>(b1, b2, 0u);                          // b2 & ~b1
     const uint32_t R = lop3<((C & A & ~B) | (~C & B & ~A)) & 0xFF>(u, b0, b4);     // b4 ? (u & ~b0) : (b0 & ~u)
-    const uint32_t p = lop3<(~A & B & ~C) & 0xFF>(w, b6, b3);                      // ~b7 & b6 & ~b3
+    const uint32_t p = lop3<(A & B & ~C) & 0xFF>(m7, b6, b3);                      // ~b7 & b6 & ~b3
+    const uint32_t ctl = lop3<(A & ~B & ~C) & 0xFF>(m7, b6, b5);                   // none of bits 7, 6, 5
     Class4 c;
-    c.v = lop3<(A & B & C) & 0xFF>(p, R, 0x80808080u);
-    c.b0 = c.v & b1;
-    c.b1 = c.v & b2;
-    c.ctl = lop3<(~(A | B | C)) & 0xFF>(w, b6, b5) & 0x80808080u;                  // none of bits 7, 6, 5
+    c.v = p & R;
+    c.f0 = lop3<((A & B) | C) & 0xFF>(c.v, b1, ctl);
+    c.f1 = c.v & b2;
     return c;
 }
-// the four lane flags (bits 7, 15, 23, 31) as a nibble, lane 0 (the first text byte) lowest: one multiply gathers
-// them into bits 28..31 (all partial products land on distinct bits, so nothing carries)
-__device__ __forceinline__ uint32_t gather4(uint32_t flags7) { return (flags7 * 0x00204081u) >> 28; }
+// The flags of 16 text bytes (four registers, flag = 0x80 in its byte lane) as 16 bits in text order: byte-wise dot
+// products with the weights 1, 2, 4, 8 (16, 32, 64, 128 for the second register of a pair) -- IDP4A, FMA pipe --
+// give 128 x the flag byte of a register pair; the two pairs are joined and the factor 128 dropped with IMAD / IMAD.HI.
+__device__ __forceinline__ uint32_t gather16(uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3) {
+    const uint32_t lo = __dp4a(g1, 0x80402010u, __dp4a(g0, 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(g3, 0x80402010u, __dp4a(g2, 0x08040201u, 0u));
+    return __umulhi(hi * 256u + lo, 1u << 25);                                      // >> 7
+}
 
-// k1 with k2 fused in.  grid.x = blocks of kPackCols columns, grid.y = groups of samples; a CTA walks through its
-// samples one after the other:
-//   phase A  the CTA's text span (bases AND line terminators, as they lie in the file) is read once, 16 bytes per
-//            thread and step, coalesced, classified in registers, and the four flags of every text byte go to
-//            four bit arrays in shared memory, in TEXT order -- no staging of the text, no realignment of bytes;
-//   phase B  every thread builds its own plane word (32 columns) from those bit arrays at the BIT level: the
+// ---- async bulk copies (TMA) into shared memory, completion on an mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "PACK_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PACK_DONE;\n\t"
+        "bra PACK_WAIT;\n\t"
+        "PACK_DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// k1 with k2 fused in.  grid.x = blocks of PackCfg::kCols columns, grid.y = groups of samples; a CTA walks through
+// its samples one after the other, two samples' text in flight:
+//   stage    the CTA's text span of a sample (bases AND line terminators, as they lie in the file: 8.2 KB per
+//            8000 columns of 60-column lines) comes in by ONE async bulk copy (TMA, cp.async.bulk) into a ring of
+//            three shared-memory buffers, issued two samples ahead by an elected thread; its bytes complete an
+//            mbarrier;
+//   phase A  the span is classified in place, 16 bytes per thread and step, and the three flags of every text
+//            byte go to three bit arrays in shared memory, in TEXT order -- no realignment of bytes;
+//   phase B  every thread builds its own plane words (32 columns each) from those bit arrays at the BIT level: the
 //            columns are 32 consecutive flag bits, except that after the `rem` bases left on the current line the
 //            text skips e terminator bytes (at most one line end per word since W >= 32) -- three words, three
-//            funnel shifts and one masked merge per plane.  The control-character plane must be empty at the
-//            columns and the terminator bytes must be the expected ones (checked where a line ends: two byte
-//            loads), else the record is flagged and the host re-stages it through its exact parser.
+//            funnel shifts and one masked merge per plane.  No column may hold a control character and the
+//            terminator bytes must be the expected ones (checked where a line ends, in the staged text), else the
+//            record is flagged and the host re-stages it through its exact parser.
+// Everything of phase B that depends only on the line layout (W, e) -- the bit offset of every word, the merge
+// masks, which words hold a line end -- is computed once and kept in registers while the layout stays the same
+// (in a consensus multi-FASTA it never changes); per sample only the record's 16-byte misalignment is new.
 // The column state (seenA, seenC, seenG, seenT, anyInvalid: what k2 used to recompute from the planes) is
 // accumulated in registers over the CTA's samples and merged into `state` once per launch: plain read-modify-
 // write when the CTA has every sample of the launch (each state word then belongs to exactly one thread; launches
 // on one stream are ordered), atomicOr otherwise.
 // Bytes: N*G text read once + 3/8 N*G planes written; nothing is read twice.
+template <int WPT>
 __global__ void __launch_bounds__(kPackThreads)
 pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const int64_t *__restrict__ rec_off,
                    const int32_t *__restrict__ line_w, const int32_t *__restrict__ eol_len, int64_t n_chunk, int64_t first,
                    int64_t n_total, int64_t G, int64_t words, uint32_t *__restrict__ planes,
                    int32_t *__restrict__ flags, uint32_t *__restrict__ state) {
-    __shared__ __align__(16) uint32_t bits[2][4][kBitWords];       // [buffer][v, b0, b1, ctl][text bit]
-    const int64_t c0 = int64_t(blockIdx.x) * kPackCols;
-    const int64_t w = (c0 >> 5) + threadIdx.x;                      // this thread's plane word
-    const bool owns = threadIdx.x < kPackWords && w < words;
-    const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);           // genome lengths fit 32 bits (the tools use int)
-    const uint32_t ce = (c0 >= G) ? cb : (G32 - cb < uint32_t(kPackCols) ? G32 : cb + uint32_t(kPackCols));   // end of this CTA's columns
-    const uint32_t c = cb + 32u * threadIdx.x;                      // first column of this thread's word
+    using Cfg = PackCfg<WPT>;
+    constexpr int kBitWords = Cfg::kBitWords;
+    extern __shared__ __align__(128) uint8_t pack_smem[];
+    uint8_t *stage = pack_smem;                                                            // [3][kStageBytes]
+    uint32_t *bits = reinterpret_cast<uint32_t *>(pack_smem + 3 * Cfg::kStageBytes);       // [2][v, f0, f1][kBitWords]
+    uint64_t *full = reinterpret_cast<uint64_t *>(pack_smem + 3 * Cfg::kStageBytes + 2 * 3 * kBitWords * 4);   // [3]
+    const int64_t c0 = int64_t(blockIdx.x) * Cfg::kCols;
+    const int64_t w = (c0 >> 5) + int64_t(threadIdx.x) * WPT;      // this thread's first plane word
+    const bool owns = threadIdx.x < kPackThreadsB && w < words;    // (words is a multiple of 4: all WPT words or none)
+    const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);          // genome lengths fit 32 bits (the tools use int)
     const int64_t per = (n_chunk + gridDim.y - 1) / gridDim.y;
     const int64_t s_lo = int64_t(blockIdx.y) * per, s_hi = s_lo + per < n_chunk ? s_lo + per : n_chunk;
-    uint32_t sA = 0, sC = 0, sG = 0, sT = 0, sInv = 0;
-    uint32_t parity = 0;                                           // bit-array buffer of the next sample that gets that far
-    auto is_marker = [](uint32_t b) { return b == '>' || b == '@' || b == '+'; };
-    auto byte_at = [&](int64_t a) -> uint32_t { return a < text_bytes ? uint32_t(text[a]) : 0x20u; };
-    for (int64_t i = s_lo; i < s_hi; ++i) {
-        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
-        const int64_t rec = rec_off[i];
-        uint32_t *p0 = planes + (0 * n_total + first + i) * words + w;
-        uint32_t *p1 = planes + (1 * n_total + first + i) * words + w;
-        uint32_t *pv = planes + (2 * n_total + first + i) * words + w;
-        if (cb >= ce || (W && W < kMinLineW)) {            // padding words / a layout the host must re-stage
-            if (owns) { *p0 = 0; *p1 = 0; *pv = 0; }
-            if (cb < ce && threadIdx.x == 0) atomicOr(&flags[i], 1);
-            continue;                                       // (uniform for the CTA: no barrier is skipped by a part of it)
+    uint32_t *const plane0 = planes + (0 * n_total + first) * words + w;      // this thread's words of sample `first`, plane 0
+    const int64_t plane_stride = n_total * words;
+    auto store_words = [&](int64_t i, const uint32_t (&x0)[WPT], const uint32_t (&x1)[WPT], const uint32_t (&xv)[WPT]) {
+        uint32_t *p0 = plane0 + i * words;
+        uint32_t *p1 = p0 + plane_stride;
+        uint32_t *pv = p1 + plane_stride;
+        if constexpr (WPT == 4) {
+            *reinterpret_cast<uint4 *>(p0) = make_uint4(x0[0], x0[1], x0[2], x0[3]);
+            *reinterpret_cast<uint4 *>(p1) = make_uint4(x1[0], x1[1], x1[2], x1[3]);
+            *reinterpret_cast<uint4 *>(pv) = make_uint4(xv[0], xv[1], xv[2], xv[3]);
+        } else if constexpr (WPT == 2) {
+            *reinterpret_cast<uint2 *>(p0) = make_uint2(x0[0], x0[1]);
+            *reinterpret_cast<uint2 *>(p1) = make_uint2(x1[0], x1[1]);
+            *reinterpret_cast<uint2 *>(pv) = make_uint2(xv[0], xv[1]);
+        } else {
+            *p0 = x0[0]; *p1 = x1[0]; *pv = xv[0];
         }
-        auto off = [&](uint32_t col) -> int64_t { return W ? int64_t(col) + int64_t(col / W) * e : int64_t(col); };
-        const int64_t lo = rec + off(cb);
-        int64_t hi = rec + off(ce - 1) + 1 + e;           // incl. the terminator after the last column
+    };
+    const uint32_t zeros[WPT] = {};
+    if (c0 >= G) {                                                  // a block of padding words only
+        if (owns)
+            for (int64_t i = s_lo; i < s_hi; ++i) store_words(i, zeros, zeros, zeros);
+        return;
+    }
+    const uint32_t ce = G32 - cb < uint32_t(Cfg::kCols) ? G32 : cb + uint32_t(Cfg::kCols);   // end of this CTA's columns
+    const uint32_t c = cb + 32u * WPT * threadIdx.x;                // first column of this thread's first word
+    auto active = [&](int64_t i) { const uint32_t W = uint32_t(line_w[i]); return !(W && W < uint32_t(kMinLineW)); };
+    // layout-dependent values, recomputed when (W, e) changes
+    uint32_t W_cur = 0xFFFFFFFFu, e_cur = 0;
+    uint32_t rel_cb = 0, span_len = 0;                              // text offset of column cb relative to the record; bytes to its end
+    uint32_t d_k[WPT], M_k[WPT], cm_k[WPT], rem_k[WPT];            // per word: bit offset - a15, columns before the line end, columns < G, bases left on the line
+    auto relayout = [&](uint32_t W, uint32_t e) {
+        W_cur = W; e_cur = e;
+        rel_cb = cb + (W ? cb / W : 0u) * e;
+        span_len = (ce - 1) + (W ? (ce - 1) / W : 0u) * e + 1 + e - rel_cb;    // incl. the terminator after the last column
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            const uint32_t ck = c + 32u * k;
+            if (ck < ce) {
+                const uint32_t ncols = ce - ck < 32u ? ce - ck : 32u;
+                const uint32_t line = W ? ck / W : 0u;
+                const uint32_t pos = W ? ck - line * W : 0u;
+                rem_k[k] = W ? W - pos : 0xFFFFu;
+                d_k[k] = ck + line * e - rel_cb;
+                M_k[k] = rem_k[k] >= 32u ? 0xFFFFFFFFu : (1u << rem_k[k]) - 1u;
+                cm_k[k] = ncols >= 32u ? 0xFFFFFFFFu : (1u << ncols) - 1u;
+            } else {
+                rem_k[k] = 0xFFFFu; d_k[k] = 0; M_k[k] = 0xFFFFFFFFu; cm_k[k] = 0u;      // a padding word: all zero
+            }
+        }
+    };
+    uint32_t full_bar[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) full_bar[k] = smem_u32(&full[k]);
+    const int64_t text_padded = (text_bytes + 15) & ~int64_t(15);  // the allocation is padded to a 16-byte boundary
+    auto issue = [&](int64_t i, int k) {                            // one thread: bulk copy of sample i's span into stage[k]
+        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+        const int64_t lo = rec_off[i] + int64_t(cb) + int64_t(W ? cb / W : 0u) * e;
+        const int64_t len = int64_t(ce - 1) + int64_t(W ? (ce - 1) / W : 0u) * e + 1 + e - (int64_t(cb) + int64_t(W ? cb / W : 0u) * e);
+        int64_t hi = lo + len;
         if (hi > text_bytes) hi = text_bytes;
         const int64_t alo = lo & ~int64_t(15);
-        const int nchunk = int((hi - alo + 15) >> 4) + 1;  // + 1: phase B may look one word beyond
-        uint32_t(*buf)[kBitWords] = bits[parity];
-        parity ^= 1u;
+        int64_t bytes = (((hi - alo + 15) >> 4) + 1) * 16;          // + 1 chunk: phase B may look one word beyond
+        if (alo + bytes > text_padded) bytes = text_padded - alo;   // (chunks beyond the text read as blanks in phase A)
+        mbar_expect_tx(full_bar[k], uint32_t(bytes));
+        bulk_g2s(smem_u32(stage + k * Cfg::kStageBytes), text + alo, uint32_t(bytes), full_bar[k]);
+    };
+    int64_t nxt = s_lo;                                             // next sample whose text has not been requested (thread 0)
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mbar_init(full_bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < 2; ++k) {
+            while (nxt < s_hi && !active(nxt)) ++nxt;
+            if (nxt < s_hi) issue(nxt++, k);
+        }
+    }
+    __syncthreads();
+    uint32_t sA[WPT] = {}, sC[WPT] = {}, sG[WPT] = {}, sT[WPT] = {}, sInv[WPT] = {};
+    uint32_t k_act = 0, ring = 0, ring_phase = 0;                   // active samples done; their stage buffer and its mbarrier phase
+    auto is_marker = [](uint32_t b) { return b == '>' || b == '@' || b == '+'; };
+    for (int64_t i = s_lo; i < s_hi; ++i) {
+        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+        if (W && W < uint32_t(kMinLineW)) {                 // a layout the host must re-stage
+            if (owns) store_words(i, zeros, zeros, zeros);
+            if (threadIdx.x == 0) atomicOr(&flags[i], 1);
+            continue;                                       // (uniform for the CTA: no barrier is skipped by a part of it)
+        }
+        if (W != W_cur || e != e_cur) relayout(W, e);
+        const int64_t rec = rec_off[i];
+        const int64_t lo = rec + int64_t(rel_cb);
+        const uint32_t a15 = uint32_t(lo) & 15u;
+        const int64_t alo = lo - a15;
+        int64_t hi = lo + span_len;
+        if (hi > text_bytes) hi = text_bytes;
+        const int nchunk = int((hi - alo + 15) >> 4) + 1;
+        const int64_t live = (text_bytes - alo + 15) >> 4;  // chunks that hold text at all
+        uint32_t *buf = bits + (k_act & 1u) * 3 * kBitWords;
+        const uint8_t *stg = stage + ring * Cfg::kStageBytes;
+        mbar_wait(full_bar[ring], ring_phase);
         // ---- phase A: classify the text, 16 bytes per thread and step
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(stg);
+        uint16_t *hvp = reinterpret_cast<uint16_t *>(buf), *h0p = reinterpret_cast<uint16_t *>(buf + kBitWords);
+        uint16_t *h1p = reinterpret_cast<uint16_t *>(buf + 2 * kBitWords);
+#pragma unroll 2
         for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
             uint4 t4 = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
-            if (alo + 16 * int64_t(j) < text_bytes) t4 = ld_nc_v4(text + alo + 16 * int64_t(j));
-            const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
-            uint32_t hv = 0, h0 = 0, h1 = 0, hc = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const Class4 f = classify4(tw[k]);
-                hv += gather4(f.v) << (4 * k); h0 += gather4(f.b0) << (4 * k);
-                h1 += gather4(f.b1) << (4 * k); hc += gather4(f.ctl) << (4 * k);
-            }
-            reinterpret_cast<uint16_t *>(buf[0])[j] = uint16_t(hv);
-            reinterpret_cast<uint16_t *>(buf[1])[j] = uint16_t(h0);
-            reinterpret_cast<uint16_t *>(buf[2])[j] = uint16_t(h1);
-            reinterpret_cast<uint16_t *>(buf[3])[j] = uint16_t(hc);
+            if (j < live) t4 = st4[j];
+            const Class4 g0 = classify4(t4.x), g1 = classify4(t4.y), g2 = classify4(t4.z), g3 = classify4(t4.w);
+            hvp[j] = uint16_t(gather16(g0.v, g1.v, g2.v, g3.v));
+            h0p[j] = uint16_t(gather16(g0.f0, g1.f0, g2.f0, g3.f0));
+            h1p[j] = uint16_t(gather16(g0.f1, g1.f1, g2.f1, g3.f1));
         }
-        __syncthreads();                                   // (the other buffer is free again: everyone is past its phase B)
-        // ---- phase B: this thread's 32 columns, taken from the bit arrays
-        if (c < ce) {
-            const uint32_t ncols = ce - c < 32u ? ce - c : 32u;
-            const uint32_t line = W ? c / W : 0u;
-            const uint32_t pos = W ? c - line * W : 0u;    // column inside the current line
-            const uint32_t rem = W ? W - pos : 0xFFFFu;    // bases left on that line
-            const int64_t at = rec + int64_t(c) + int64_t(line) * e;       // text offset of column c
-            const uint32_t o = uint32_t(at - alo);         // = bit index in the arrays
-            const uint32_t q = o >> 5, sh = o & 31u;
-            const uint32_t M = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;          // columns before the line end
-            const uint32_t colmask = ncols >= 32u ? 0xFFFFFFFFu : (1u << ncols) - 1u;  // last word of a row: columns < G
+        __syncthreads();            // this sample's bit arrays are complete; the stage buffer of the PREVIOUS sample is free
+        if (threadIdx.x == 0) {     // ... and takes the text of the active sample after next
+            while (nxt < s_hi && !active(nxt)) ++nxt;
+            if (nxt < s_hi) issue(nxt++, int(ring == 0 ? 2u : ring - 1u));
+        }
+        // ---- phase B: this thread's words, taken from the bit arrays
+        uint32_t o0[WPT], o1[WPT], ov[WPT];
+        bool irregular = false, marker = false;
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            const uint32_t o = a15 + d_k[k];               // bit index in the arrays = byte index in the stage buffer
+            const uint32_t q = o >> 5, sh = o & 31u, M = M_k[k], cm = cm_k[k];
             auto take = [&](const uint32_t *a) {
                 const uint32_t a0 = a[q], a1 = a[q + 1], a2 = a[q + 2];
                 const uint32_t x0 = __funnelshift_r(a0, a1, sh), x1 = __funnelshift_r(a1, a2, sh);
-                return ((x0 & M) | (__funnelshift_r(x0, x1, e) & ~M)) & colmask;
+                return ((x0 & M) | (__funnelshift_r(x0, x1, e) & ~M)) & cm;
             };
-            const uint32_t fv = take(buf[0]), f0 = take(buf[1]), f1 = take(buf[2]), fc = take(buf[3]);
-            bool irregular = fc != 0;                      // a control character among the bases
-            bool marker = false;
-            // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
-            // the tools share (it opens the next record / a quality block): the host must re-index
-            if (pos == 0 && (W || c == 0)) marker = is_marker(byte_at(at));
-            if (rem <= ncols && c + rem < G32) {           // a line ends inside (or at the end of) this word and more bases follow
-                const int64_t t = at + rem;
-                if (e == 1) irregular |= byte_at(t) != '\n';
-                else irregular |= (byte_at(t) != '\r') | (byte_at(t + 1) != '\n');
-                marker |= is_marker(byte_at(t + e));       // first byte of the next line
+            const uint32_t fv = take(buf), g0 = take(buf + kBitWords), f1 = take(buf + 2 * kBitWords);
+            irregular |= (g0 & ~fv) != 0;                  // a control character among the bases
+            const uint32_t ck = c + 32u * k, rem = rem_k[k];
+            if (cm) {
+                // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
+                // the tools share (it opens the next record / a quality block): the host must re-index
+                if ((W && rem == W) || ck == 0) marker |= is_marker(stg[o]);
+                const uint32_t ncols = ce - ck < 32u ? ce - ck : 32u;
+                if (rem <= ncols && ck + rem < G32) {      // a line ends inside (or at the end of) this word and more bases follow
+                    const uint32_t t = o + rem;            // (inside the staged span: it includes the terminator after the last column)
+                    if (e == 1) irregular |= stg[t] != '\n';
+                    else irregular |= (stg[t] != '\r') | (stg[t + 1] != '\n');
+                    marker |= is_marker(stg[t + e]);       // first byte of the next line
+                }
             }
-            if (owns) { *p0 = f0; *p1 = f1; *pv = fv; }
-            sA |= fv & ~f1 & ~f0; sC |= fv & ~f1 & f0; sT |= fv & f1 & ~f0; sG |= fv & f1 & f0;
-            sInv |= ~fv & colmask;
-            if (irregular) atomicOr(&flags[i], 1);
-            if (marker) atomicOr(&flags[i], 2);
-        } else if (owns) {
-            *p0 = 0; *p1 = 0; *pv = 0;                     // padding words of the last column block
+            o0[k] = g0 & fv; o1[k] = f1; ov[k] = fv;
+            const uint32_t lo2 = fv & ~f1, hi2 = fv & f1;   // codes 0/1 (A, C) and 2/3 (T, G)
+            sA[k] |= lo2 & ~g0; sC[k] |= lo2 & g0; sT[k] |= hi2 & ~g0; sG[k] |= hi2 & g0;
+            sInv[k] |= ~fv & cm;
         }
+        if (owns) store_words(i, o0, o1, ov);
+        if (irregular) atomicOr(&flags[i], 1);
+        if (marker) atomicOr(&flags[i], 2);
+        ++k_act;
+        if (++ring == 3) { ring = 0; ring_phase ^= 1u; }
     }
-    if (state && owns && c < ce && s_hi > s_lo) {
-        uint32_t *d = state + w;
-        if (gridDim.y == 1) {
-            d[0] |= sA; d[words] |= sC; d[2 * words] |= sG; d[3 * words] |= sT; d[4 * words] |= sInv;
-        } else {
-            if (sA) atomicOr(d, sA);
-            if (sC) atomicOr(d + words, sC);
-            if (sG) atomicOr(d + 2 * words, sG);
-            if (sT) atomicOr(d + 3 * words, sT);
-            if (sInv) atomicOr(d + 4 * words, sInv);
+    if (state && owns && s_hi > s_lo) {
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            if (c + 32u * k >= ce) continue;
+            uint32_t *d = state + w + k;
+            if (gridDim.y == 1) {
+                d[0] |= sA[k]; d[words] |= sC[k]; d[2 * words] |= sG[k]; d[3 * words] |= sT[k]; d[4 * words] |= sInv[k];
+            } else {
+                if (sA[k]) atomicOr(d, sA[k]);
+                if (sC[k]) atomicOr(d + words, sC[k]);
+                if (sG[k]) atomicOr(d + 2 * words, sG[k]);
+                if (sT[k]) atomicOr(d + 3 * words, sT[k]);
+                if (sInv[k]) atomicOr(d + 4 * words, sInv[k]);
+            }
         }
     }
 }
@@ -364,16 +492,25 @@ int pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_
                 const int32_t *d_eol, int64_t n_chunk, int64_t first, int64_t n_total, int64_t G, uint32_t *d_planes,
                 int32_t *d_flags, uint32_t *d_colstate, cudaStream_t stream) {
     const int64_t words = plane_words(G);
-    const int64_t gx = (words + kPackWords - 1) / kPackWords;
+    const int wpt = g_pack_wpt == 4 ? 4 : (g_pack_wpt == 1 ? 1 : 2);
+    const int64_t cta_words = int64_t(kPackThreadsB) * wpt;
+    const int64_t gx = (words + cta_words - 1) / cta_words;
     // sample groups: one CTA per column block takes ALL samples of the launch (plain state merge) unless that
     // leaves the GPU short of CTAs and every group still gets enough samples to make its atomics cheap
     int sms = 148;
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     int64_t gy = 1;
-    if (gx < int64_t(sms) * 4) gy = std::max<int64_t>(1, std::min<int64_t>((int64_t(sms) * 6 + gx - 1) / gx, n_chunk / (d_colstate ? 24 : 1)));
+    if (gx < int64_t(sms) * 4) gy = std::max<int64_t>(1, std::min<int64_t>((int64_t(sms) * 4 + gx - 1) / gx, n_chunk / (d_colstate ? 16 : 1)));
     gy = std::max<int64_t>(1, std::min<int64_t>(gy, std::min<int64_t>(n_chunk, 65535)));
-    pack_planes_kernel<<<dim3((unsigned)gx, (unsigned)gy), kPackThreads, 0, stream>>>(
-        d_text, text_bytes, d_rec_off, d_line_w, d_eol, n_chunk, first, n_total, G, words, d_planes, d_flags, d_colstate);
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+#define BTB_PACK_LAUNCH(W_)                                                                                                     \
+    do {                                                                                                                        \
+        BTB_CUDA(cudaFuncSetAttribute(pack_planes_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, PackCfg<W_>::kSmemBytes)); \
+        pack_planes_kernel<W_><<<grid, kPackThreads, PackCfg<W_>::kSmemBytes, stream>>>(                                        \
+            d_text, text_bytes, d_rec_off, d_line_w, d_eol, n_chunk, first, n_total, G, words, d_planes, d_flags, d_colstate);  \
+    } while (0)
+    if (wpt == 4) BTB_PACK_LAUNCH(4); else if (wpt == 1) BTB_PACK_LAUNCH(1); else BTB_PACK_LAUNCH(2);
+#undef BTB_PACK_LAUNCH
     BTB_CUDA(cudaGetLastError());
     return BTB_OK;
 }

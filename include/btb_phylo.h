@@ -71,7 +71,7 @@ int         btb_device_count(int *count);                 /* number of usable sm
  *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (for ncu)
  *     "umma_prefetch" [0], "umma_tile_bk" [128], "umma_cta_group" [1], "umma_cg2_variant" [0]: measured alternatives
  *       (L2 prefetch distance, 64-byte K blocks with six stages, int8 CTA pairs) kept for the record, see DESIGN.md
- *   extraction: "ingest_predict" [1] predicted FASTA framing
+ *   extraction: "pack_wpt" [2] plane words per thread of k1 (1, 2, 4); "ingest_predict" [1] predicted FASTA framing
  *   level 1/2:  "csv_mmap" [0] write snps.csv through a file mapping; "dense_pageable" [1] large snps.fas into
  *               pageable host memory; "host_stream" [0] + "host_stream_rows" [64] streamed level-2 call
  * btb_query also answers "ingest_last_predicted", "host_stream_last", "umma_max_active_clusters_cg1|2" and

@@ -148,7 +148,11 @@ def main():
     state_fused = state.clone()
     t_mask = timed(lambda: _capi.check(lib.btb_column_mask(P(planes), n_res, n_res, G, P(state), 0, st)))
     mask_bytes = n_res * 3 * words * 4
-    fused_equals_k2 = bool((state_fused == state).all().item())
+    # the fused state leaves the padding bits (columns >= G) alone, k2 marks them invalid: compare the real columns
+    real = torch.zeros(words * 32, dtype=torch.bool, device="cuda")
+    real[:G] = True
+    real_words = (real.view(words, 32).to(torch.int64) << torch.arange(32, device="cuda")[None, :]).sum(dim=1).to(torch.int32)
+    fused_equals_k2 = bool(((((state_fused ^ state).view(5, words)) & real_words[None, :]) == 0).all().item())
     keep = torch.zeros(words, dtype=torch.int32, device="cuda")
     idx = torch.zeros(words * 32, dtype=torch.int32, device="cuda")
     cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
