@@ -58,6 +58,7 @@ int get_ingest_predict();
 int get_ingest_last();
 extern int g_umma_tile_mode;
 extern int g_pack_wpt;
+extern int g_pack_gy;
 int umma_max_active_clusters(int cg, int *out);
 int umma_probe(int cg, int every, int64_t *cycles_x100);
 int dist_presence_async(const uint8_t *, int64_t, int64_t, int64_t, uint32_t *, cudaStream_t);
@@ -166,6 +167,7 @@ extern "C" int btb_device_count(int *count) {
 
 extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
+    if (key && !strcmp(key, "pack_gy")) { g_pack_gy = value < 0 ? 0 : value; return BTB_OK; }
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : (value == 1 ? 1 : 2); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }

@@ -34,9 +34,11 @@ template <int WPT> struct PackCfg {
     static constexpr int kSpanBytes = kCols + kCols / kMinLineW * 2 + 64;       // text bytes a CTA can touch per sample
     static constexpr int kStageBytes = (kSpanBytes + 16 + 15) / 16 * 16;
     static constexpr int kBitWords = (kSpanBytes + 31) / 32 + 4;                // flag bits of the span + what a funnel shift may touch
-    static constexpr int kSmemBytes = 3 * kStageBytes + 2 * 3 * kBitWords * 4 + 64;
+    static constexpr int kRing = 2;                                             // stage buffers: the text of this sample and of the next
+    static constexpr int kSmemBytes = kRing * kStageBytes + 2 * 3 * kBitWords * 4 + 64;
 };
 int g_pack_wpt = 2;                                      // "pack_wpt": plane words per thread of k1 (1, 2 or 4)
+int g_pack_gy = 0;                                       // "pack_gy": sample groups per launch (0 = automatic)
 
 __host__ __device__ inline int64_t plane_words(int64_t G) { return ((G + 31) / 32 + 3) / 4 * 4; }
 
@@ -117,8 +119,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // its samples one after the other, two samples' text in flight:
 //   stage    the CTA's text span of a sample (bases AND line terminators, as they lie in the file: 8.2 KB per
 //            8000 columns of 60-column lines) comes in by ONE async bulk copy (TMA, cp.async.bulk) into a ring of
-//            three shared-memory buffers, issued two samples ahead by an elected thread; its bytes complete an
-//            mbarrier;
+//            shared-memory buffers, issued ahead by an elected thread as soon as the buffer of the previous
+//            sample is free; its bytes complete an mbarrier;
 //   phase A  the span is classified in place, 16 bytes per thread and step, and the three flags of every text
 //            byte go to three bit arrays in shared memory, in TEXT order -- no realignment of bytes;
 //   phase B  every thread builds its own plane words (32 columns each) from those bit arrays at the BIT level: the
@@ -144,9 +146,10 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     using Cfg = PackCfg<WPT>;
     constexpr int kBitWords = Cfg::kBitWords;
     extern __shared__ __align__(128) uint8_t pack_smem[];
-    uint8_t *stage = pack_smem;                                                            // [3][kStageBytes]
-    uint32_t *bits = reinterpret_cast<uint32_t *>(pack_smem + 3 * Cfg::kStageBytes);       // [2][v, f0, f1][kBitWords]
-    uint64_t *full = reinterpret_cast<uint64_t *>(pack_smem + 3 * Cfg::kStageBytes + 2 * 3 * kBitWords * 4);   // [3]
+    constexpr int kRing = Cfg::kRing;
+    uint8_t *stage = pack_smem;                                                            // [kRing][kStageBytes]
+    uint32_t *bits = reinterpret_cast<uint32_t *>(pack_smem + kRing * Cfg::kStageBytes);   // [2][v, f0, f1][kBitWords]
+    uint64_t *full = reinterpret_cast<uint64_t *>(pack_smem + kRing * Cfg::kStageBytes + 2 * 3 * kBitWords * 4);   // [kRing]
     const int64_t c0 = int64_t(blockIdx.x) * Cfg::kCols;
     const int64_t w = (c0 >> 5) + int64_t(threadIdx.x) * WPT;      // this thread's first plane word
     const bool owns = threadIdx.x < kPackThreadsB && w < words;    // (words is a multiple of 4: all WPT words or none)
@@ -204,9 +207,9 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             }
         }
     };
-    uint32_t full_bar[3];
+    uint32_t full_bar[kRing];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) full_bar[k] = smem_u32(&full[k]);
+    for (int k = 0; k < kRing; ++k) full_bar[k] = smem_u32(&full[k]);
     const int64_t text_padded = (text_bytes + 15) & ~int64_t(15);  // the allocation is padded to a 16-byte boundary
     auto issue = [&](int64_t i, int k) {                            // one thread: bulk copy of sample i's span into stage[k]
         const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
@@ -223,9 +226,9 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     int64_t nxt = s_lo;                                             // next sample whose text has not been requested (thread 0)
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) mbar_init(full_bar[k], 1);
+        for (int k = 0; k < kRing; ++k) mbar_init(full_bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < kRing - 1; ++k) {               // the buffer of the sample before the current one is refilled in the loop
             while (nxt < s_hi && !active(nxt)) ++nxt;
             if (nxt < s_hi) issue(nxt++, k);
         }
@@ -242,14 +245,14 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             continue;                                       // (uniform for the CTA: no barrier is skipped by a part of it)
         }
         if (W != W_cur || e != e_cur) relayout(W, e);
+        // per sample only the record's start is new; everything below is 32-bit arithmetic relative to it
         const int64_t rec = rec_off[i];
-        const int64_t lo = rec + int64_t(rel_cb);
-        const uint32_t a15 = uint32_t(lo) & 15u;
-        const int64_t alo = lo - a15;
-        int64_t hi = lo + span_len;
-        if (hi > text_bytes) hi = text_bytes;
-        const int nchunk = int((hi - alo + 15) >> 4) + 1;
-        const int64_t live = (text_bytes - alo + 15) >> 4;  // chunks that hold text at all
+        const uint32_t a15 = (uint32_t(rec) + rel_cb) & 15u;        // misalignment of the span's first byte
+        const int64_t room64 = text_bytes - (rec + int64_t(rel_cb)); // bytes from there to the end of the text (matters for the last record only)
+        const uint32_t room = room64 > int64_t(1 << 30) ? (1u << 30) : (room64 > 0 ? uint32_t(room64) : 0u);
+        const uint32_t len = span_len < room ? span_len : room;
+        const int nchunk = int((a15 + len + 15u) >> 4) + 1;         // + 1: phase B may look one word beyond
+        const int live = int((a15 + room + 15u) >> 4);              // chunks that hold text at all
         uint32_t *buf = bits + (k_act & 1u) * 3 * kBitWords;
         const uint8_t *stg = stage + ring * Cfg::kStageBytes;
         mbar_wait(full_bar[ring], ring_phase);
@@ -269,7 +272,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         __syncthreads();            // this sample's bit arrays are complete; the stage buffer of the PREVIOUS sample is free
         if (threadIdx.x == 0) {     // ... and takes the text of the active sample after next
             while (nxt < s_hi && !active(nxt)) ++nxt;
-            if (nxt < s_hi) issue(nxt++, int(ring == 0 ? 2u : ring - 1u));
+            if (nxt < s_hi) issue(nxt++, int(ring == 0 ? uint32_t(kRing - 1) : ring - 1u));
         }
         // ---- phase B: this thread's words, taken from the bit arrays
         uint32_t o0[WPT], o1[WPT], ov[WPT];
@@ -287,15 +290,18 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             irregular |= (g0 & ~fv) != 0;                  // a control character among the bases
             const uint32_t ck = c + 32u * k, rem = rem_k[k];
             if (cm) {
-                // a line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
-                // the tools share (it opens the next record / a quality block): the host must re-index
-                if ((W && rem == W) || ck == 0) marker |= is_marker(stg[o]);
                 const uint32_t ncols = ce - ck < 32u ? ce - ck : 32u;
+                // A line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
+                // the tools share (it opens the next record / a quality block): the host must re-index.  Every line
+                // start is a column of exactly one word -- its first one, or the one after a line end inside it -- and
+                // a marker is never a base: the byte is only looked at when that column is not valid.
+                const bool starts_line = (W && rem == W) || ck == 0;
+                const uint32_t j = starts_line ? 0u : rem;                 // column (bit) of the line start in this word, if < ncols
+                if ((starts_line || rem < ncols) && !((fv >> j) & 1u)) marker |= is_marker(stg[o + j + (starts_line ? 0u : e)]);
                 if (rem <= ncols && ck + rem < G32) {      // a line ends inside (or at the end of) this word and more bases follow
                     const uint32_t t = o + rem;            // (inside the staged span: it includes the terminator after the last column)
                     if (e == 1) irregular |= stg[t] != '\n';
                     else irregular |= (stg[t] != '\r') | (stg[t + 1] != '\n');
-                    marker |= is_marker(stg[t + e]);       // first byte of the next line
                 }
             }
             o0[k] = g0 & fv; o1[k] = f1; ov[k] = fv;
@@ -307,7 +313,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         if (irregular) atomicOr(&flags[i], 1);
         if (marker) atomicOr(&flags[i], 2);
         ++k_act;
-        if (++ring == 3) { ring = 0; ring_phase ^= 1u; }
+        if (++ring == uint32_t(kRing)) { ring = 0; ring_phase ^= 1u; }
     }
     if (state && owns && s_hi > s_lo) {
 #pragma unroll
@@ -495,12 +501,13 @@ int pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_
     const int wpt = g_pack_wpt == 4 ? 4 : (g_pack_wpt == 1 ? 1 : 2);
     const int64_t cta_words = int64_t(kPackThreadsB) * wpt;
     const int64_t gx = (words + cta_words - 1) / cta_words;
-    // sample groups: one CTA per column block takes ALL samples of the launch (plain state merge) unless that
-    // leaves the GPU short of CTAs and every group still gets enough samples to make its atomics cheap
+    // sample groups: about 14 CTAs per SM in all (four are resident at a time; measured best on 48 records of
+    // 4.35 Mb: 3.05 TB/s with 8 groups against 2.4 with 1), but no fewer than four samples per CTA -- its set-up
+    // and the merge of its column state (one coalesced atomicOr per state word and group) have to be worth it
     int sms = 148;
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    int64_t gy = 1;
-    if (gx < int64_t(sms) * 4) gy = std::max<int64_t>(1, std::min<int64_t>((int64_t(sms) * 4 + gx - 1) / gx, n_chunk / (d_colstate ? 16 : 1)));
+    int64_t gy = std::max<int64_t>(1, std::min<int64_t>((int64_t(sms) * 14 + gx - 1) / gx, n_chunk / 4));
+    if (g_pack_gy > 0) gy = g_pack_gy;
     gy = std::max<int64_t>(1, std::min<int64_t>(gy, std::min<int64_t>(n_chunk, 65535)));
     const dim3 grid((unsigned)gx, (unsigned)gy);
 #define BTB_PACK_LAUNCH(W_)                                                                                                     \
