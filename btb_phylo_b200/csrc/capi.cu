@@ -42,17 +42,10 @@ int distance_tiles_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, v
                         cudaStream_t, const int2 *);
 int distance_rows_popc(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, cudaStream_t);
 int distance_rows_umma(const void *, int64_t, int64_t, int, int64_t, int64_t, void *, int, int64_t, int, cudaStream_t);
-extern int g_umma_cta_group;
-extern int g_umma_cg2_variant;
 extern int g_umma_lockstep;
-extern int g_umma_dbg_negate;
-extern int g_umma_dbg_max_ctas;
-extern int g_umma_tile_bk;
 extern int g_umma_fp4_pair;
 extern int g_umma_coop;
 extern int g_umma_major_zero;
-extern int g_umma_dbg_stages;
-extern int g_umma_prefetch;
 void set_ingest_predict(int v);
 int get_ingest_predict();
 int get_ingest_last();
@@ -166,11 +159,9 @@ extern "C" int btb_device_count(int *count) {
 }
 
 extern "C" int btb_set_option(const char *key, int value) {
-    if (key && !strcmp(key, "umma_cta_group")) { g_umma_cta_group = value == 1 ? 1 : 2; return BTB_OK; }
     if (key && !strcmp(key, "pack_gy")) { g_pack_gy = value < 0 ? 0 : value; return BTB_OK; }
     if (key && !strcmp(key, "pack_wpt")) { g_pack_wpt = value == 4 ? 4 : (value == 1 ? 1 : 2); return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4")) { g_umma_fp4 = value ? 1 : 0; return BTB_OK; }
-    if (key && !strcmp(key, "umma_prefetch")) { g_umma_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return BTB_OK; }
     if (key && !strcmp(key, "csv_mmap")) { g_csv_mmap = value < 0 ? -1 : (value ? 1 : 0); return BTB_OK; }
     if (key && !strcmp(key, "csv_prealloc")) { g_csv_prealloc = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "replace_unlink_first")) { g_replace_unlink_first = value ? 1 : 0; return BTB_OK; }
@@ -184,13 +175,8 @@ extern "C" int btb_set_option(const char *key, int value) {
     if (key && !strcmp(key, "umma_coop")) { g_umma_coop = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_major_zero")) { g_umma_major_zero = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_fp4_pair")) { g_umma_fp4_pair = value ? 1 : 0; return BTB_OK; }
-    if (key && !strcmp(key, "umma_tile_bk")) { g_umma_tile_bk = value == 64 ? 64 : 128; return BTB_OK; }
-    if (key && !strcmp(key, "umma_dbg_max_ctas")) { g_umma_dbg_max_ctas = value; return BTB_OK; }
-    if (key && !strcmp(key, "umma_dbg_stages")) { g_umma_dbg_stages = value; return BTB_OK; }
-    if (key && !strcmp(key, "umma_dbg_negate")) { g_umma_dbg_negate = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_tile_mode")) { g_umma_tile_mode = value ? 1 : 0; return BTB_OK; }
     if (key && !strcmp(key, "umma_lockstep")) { g_umma_lockstep = value < 0 ? 0 : value; return BTB_OK; }
-    if (key && !strcmp(key, "umma_cg2_variant")) { g_umma_cg2_variant = value & 3; return BTB_OK; }
     if (key && !strcmp(key, "umma_dense_simplex")) { g_umma_dense_simplex = value < 0 || value > 2 ? 0 : value; return BTB_OK; }
     return fail(BTB_EINVAL, "unknown option");
 }
@@ -204,11 +190,9 @@ extern "C" int btb_query(const char *key, int64_t *value) {
     }
     if (!strcmp(key, "umma_max_active_clusters_cg2")) { BTB_TRY(umma_max_active_clusters(2, &v)); *value = v; return BTB_OK; }
     if (!strcmp(key, "umma_max_active_clusters_cg1")) { BTB_TRY(umma_max_active_clusters(1, &v)); *value = v; return BTB_OK; }
-    if (!strcmp(key, "umma_cta_group")) { *value = g_umma_cta_group; return BTB_OK; }
     if (!strcmp(key, "umma_dense_simplex")) { *value = g_umma_dense_simplex; return BTB_OK; }
     if (!strcmp(key, "umma_tile_mode")) { *value = g_umma_tile_mode; return BTB_OK; }
     if (!strcmp(key, "umma_fp4")) { *value = g_umma_fp4; return BTB_OK; }
-    if (!strcmp(key, "umma_tile_bk")) { *value = g_umma_tile_bk; return BTB_OK; }
     if (!strcmp(key, "umma_fp4_pair")) { *value = g_umma_fp4_pair; return BTB_OK; }
     if (!strcmp(key, "umma_major_zero")) { *value = g_umma_major_zero; return BTB_OK; }
     if (!strcmp(key, "ingest_predict")) { *value = get_ingest_predict(); return BTB_OK; }

@@ -14,8 +14,9 @@
 //   dist_umma_fp4_tile_kernel   one CTA per 256 x 240 unit (two halves share every staged B block)
 //   dist_umma_fp4_kernel        128-row half tiles (small launches, explicit tile lists)
 //   dist_umma_tile_kernel       int8, 256 x 256 tiles as two halves
-//   dist_umma_kernel            int8 half tiles and the older int8 CTA-pair variant
-//   umma_probe_kernel           MMA / commit issue-rate probe (no data movement)
+//   dist_umma_kernel            int8 half tiles
+//   umma_probe_kernel           MMA issue-rate probe (no data movement): the measured tensor-pipe peak bench.py's
+//                               roofline divides by
 // Bound: tensor pipe (at the board's power cap).  DESIGN.md section 4 has the measurements.
 #include <cuda.h>
 
@@ -150,11 +151,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     }
 }
 
-// CTA-pair MMA, arrival on the leader's barrier only (no multicast)
-__device__ __forceinline__ void umma_commit_leader(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
 struct UmmaParams;
 __device__ __forceinline__ void tile_of(const int2 *sq_list, int64_t T, int64_t tile, int &I, int &J) {
     if (sq_list) { const int2 w = sq_list[tile]; I = w.x; J = w.y; }
@@ -186,16 +182,6 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// same for rows of 64 bytes, 64-byte swizzle: 8-row atoms of 512 B, layout type 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
-    d |= uint64_t(512 >> 4) << 32;
-    d |= uint64_t(1) << 46;
-    d |= uint64_t(4) << 61;
-    return d;
-}
-
 // instruction descriptor, kind::i8: D = S32 (2 at [4,6)), A/B = signed 8-bit (1 at [7,10) / [10,13)),
 // both K-major (0 at 15 / 16), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
@@ -219,11 +205,8 @@ struct UmmaParams {
     const int2 *sq_list;       // optional explicit list of square tiles (I, J) replacing the band enumeration
     unsigned int *lockstep;    // optional grid-wide arrival counter: producers start every unit together
     int lock_slack = 0;        // a producer may run this many rounds ahead of the slowest one (0 = strict)
-    int prefetch = 0;          // FP4 full-tile kernel: K blocks of L2 prefetch distance (0 = off)
     int64_t neg_from = INT64_MAX;   // kind::mxf4: K blocks >= neg_from are subtracted (general alphabets: V blocks - X blocks)
-    int64_t b_shift = 0;       // 0: subtract with the instruction descriptor's negate-A bit; else B reads K block kb + b_shift
-                               //    (a sign-flipped copy of the X blocks)
-    unsigned long long *dbg;   // optional per-CTA timeline {start ns, end ns, smid, units} (BTB_UMMA_DEBUG)
+    int64_t b_shift = 0;       // 0: subtract with the instruction descriptor's negate-A bit
 };
 
 // Epilogue of one 128-row x 256-column accumulator buffer: this thread owns matrix row `row`
@@ -356,31 +339,42 @@ __device__ __forceinline__ void drain_accumulator(const UmmaParams &p, uint32_t 
     }
 }
 
-// ATOMS = 128-byte K atoms per pipeline stage (one tcgen05.commit per stage: more atoms = fewer
-// commits); RELAY (CG = 2 only) = the leader's producer forwards the stage release to the peer
-// CTA with a remote mbarrier arrive instead of a multicast commit from the MMA thread.
-template <int CG, int ATOMS = 1, bool RELAY = false>
+// int8 half-tile kernel: one CTA per 128-row x 256-column unit (UMMA 128 x 256 x 32, kind::i8), 4 stages of
+// A 16 KB + B 32 KB, two accumulator buffers so that the epilogue of a unit overlaps the K loop of the next.
 struct UmmaCfg {
-    static constexpr int kARows = 128;                               // A rows loaded per CTA per stage
-    static constexpr int kBRows = CG == 2 ? 128 : 256;               // B rows loaded per CTA per stage
-    static constexpr int kAAtom = kARows * kBlockK;
-    static constexpr int kBAtom = kBRows * kBlockK;
-    static constexpr int kABytes = kAAtom * ATOMS;
-    static constexpr int kBBytes = kBAtom * ATOMS;
+    static constexpr int kARows = 128;                               // A rows loaded per stage
+    static constexpr int kBRows = 256;                               // B rows loaded per stage
+    static constexpr int kABytes = kARows * kBlockK;
+    static constexpr int kBBytes = kBRows * kBlockK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (CG == 2 ? 6 : 4) / ATOMS;
+    static constexpr int kStages = 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int CG, typename OutT, int ATOMS = 1, bool RELAY = false>
+// lockstep: re-align the producers of all CTAs at every unit boundary.  CTAs that stream the same operand panels
+// then sit at the same K offset, so a panel block is fetched from HBM once and hit in L2 by everyone else (needs
+// all CTAs co-resident: cooperative launch).  Round r expects every worker that has a unit in round r;
+// `per_worker` arrivals per worker and round (2 for the CTAs of a pair).
+__device__ __forceinline__ void lockstep_wait(const UmmaParams &p, int64_t u, int64_t worker, int64_t n_workers, int per_worker) {
+    const int64_t round = (u - worker) / n_workers;
+    const int64_t full_rounds = p.units / n_workers;                  // rounds in which every worker has a unit
+    const int64_t last_count = p.units - full_rounds * n_workers;
+    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers * per_worker;
+    if (round > full_rounds - 1) target += last_count * per_worker;
+    target -= int64_t(p.lock_slack) * n_workers * per_worker;
+    __threadfence();
+    atomicAdd(p.lockstep, 1u);
+    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
+}
+
+template <typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
 dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const UmmaParams p) {
-    using Cfg = UmmaCfg<CG, ATOMS, RELAY>;
+    using Cfg = UmmaCfg;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B swizzle atoms (same offset in both CTAs of a pair)
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;    // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -391,46 +385,29 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + Cfg::kABytes; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
-    const bool leader = cta_rank == 0;
-    const int64_t worker = CG == 2 ? blockIdx.x / 2 : blockIdx.x;
-    const int64_t n_workers = CG == 2 ? gridDim.x / 2 : gridDim.x;
+    const int64_t worker = blockIdx.x, n_workers = gridDim.x;
     const int64_t T = tiles_per_dim(p.n);
 
-    if (p.dbg && threadIdx.x == 0) {
-        unsigned long long t; uint32_t sm;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-        p.dbg[blockIdx.x * 4 + 0] = t;
-        p.dbg[blockIdx.x * 4 + 2] = sm;
-    }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar(s), CG);          // one arrive per producer CTA (+ tx bytes)
-            mbar_init(empty_bar(s), 1);          // tcgen05.commit
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull_bar(a), 1);          // tcgen05.commit
-            mbar_init(tempty_bar(a), CG * 4);    // one arrive per epilogue warp of every CTA
-        }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }   // tempty: one arrive per epilogue warp
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<CG>(tmem_slot, 512);
+    if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
     tc_fence_before();
-    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     // unit -> rows of A (m0), rows of B (n0)
     auto unit_coords = [&](int64_t u, int64_t &m0, int64_t &n0, int &I, int &J, int &half) {
-        const int64_t tile = p.tile_lo + (CG == 2 ? u : u / 2);
-        half = CG == 2 ? int(cta_rank) : int(u & 1);
-        tile_of(p.sq_list, T, tile, I, J);
+        half = int(u & 1);
+        tile_of(p.sq_list, T, p.tile_lo + u / 2, I, J);
         m0 = int64_t(I) * BTB_TILE + half * 128;
         n0 = int64_t(J) * BTB_TILE;
     };
@@ -440,89 +417,50 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int64_t fills = 0;                 // stages filled so far (the first ring pass needs no release)
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 int64_t m0, n0; int I, J, half;
                 unit_coords(u, m0, n0, I, J, half);
-                const int64_t b_row = n0 + (CG == 2 ? int64_t(cta_rank) * 128 : 0);
-                if (p.lockstep && u != worker) {
-                    // Re-align the producers of all CTAs at every unit boundary: CTAs that stream the
-                    // same operand panels then sit at the same K offset, so a panel block is fetched
-                    // from HBM once and hit in L2 by everyone else (needs all CTAs co-resident:
-                    // cooperative launch).  round r expects every worker that has a unit in round r.
-                    const int64_t round = (u - worker) / n_workers;
-                    const int64_t total_workers = CG == 2 ? n_workers * 2 : n_workers;
-                    const int64_t full_rounds = p.units / n_workers;          // rounds in which every worker has a unit
-                    const int64_t last_count = p.units - full_rounds * n_workers;
-                    const int64_t per_cta = CG == 2 ? 2 : 1;
-                    // arrivals expected by the time round `round` may start = arrivals of rounds 1..round
-                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * total_workers;
-                    if (round > full_rounds - 1) target += last_count * per_cta;
-                    (void)total_workers;
-                    target -= int64_t(p.lock_slack) * n_workers;
-                    __threadfence();
-                    atomicAdd(p.lockstep, 1u);
-                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
-                }
+                if (p.lockstep && u != worker) lockstep_wait(p, u, worker, n_workers, 1);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    if constexpr (CG == 2 && RELAY) {
-                        // the MMA thread released this stage on the leader only: pass it on
-                        if (leader && fills >= kStages) mbar_arrive_cluster(empty_bar(stage), 1);
-                    }
-                    if constexpr (CG == 2) {
-                        if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                        else mbar_arrive_cluster(full_bar(stage), 0);
-                    } else {
-                        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    }
-#pragma unroll
-                    for (int at = 0; at < ATOMS; ++at) {
-                        const int k0 = int((kb * ATOMS + at) * kBlockK);       // beyond K: zero-filled by TMA
-                        tma_load_2d<CG>(smem_a(stage) + at * Cfg::kAAtom, &map_a, full_bar(stage), k0, int(m0));
-                        tma_load_2d<CG>(smem_b(stage) + at * Cfg::kBAtom, &map_b, full_bar(stage), k0, int(b_row));
-                    }
-                    ++fills;
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    const int k0 = int(kb * kBlockK);                    // beyond K: zero-filled by TMA
+                    tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), k0, int(m0));
+                    tma_load_2d<1>(smem_b(stage), &map_b, full_bar(stage), k0, int(n0));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (leader CTA)
-        if (leader) {
-            // the whole warp walks the pipeline (warp-uniform control flow keeps descriptors in
-            // uniform registers); one elected lane issues the tensor-core instructions
-            constexpr uint32_t idesc = make_i8_idesc(CG == 2 ? 256 : 128, kAccCols);
-            int stage = 0;
-            uint32_t phase = 0;
-            int64_t it = 0;
-            for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
-                const int acc = int(it & 1);
-                const uint32_t acc_phase = uint32_t(it >> 1) & 1;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        // ================================================================= MMA issuer
+        // the whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers);
+        // one elected lane issues the tensor-core instructions
+        constexpr uint32_t idesc = make_i8_idesc(128, kAccCols);
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t it = 0;
+        for (int64_t u = worker; u < p.units; u += n_workers, ++it) {
+            const int acc = int(it & 1);
+            const uint32_t acc_phase = uint32_t(it >> 1) & 1;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kAccCols;
+            for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kAccCols;
-                for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    if (elect_one()) {
+                if (elect_one()) {
+                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
-                        for (int at = 0; at < ATOMS; ++at) {
-                            const uint64_t a_desc = make_kmajor_sw128_desc(smem_a(stage) + at * Cfg::kAAtom);
-                            const uint64_t b_desc = make_kmajor_sw128_desc(smem_b(stage) + at * Cfg::kBAtom);
-#pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                                umma_i8<CG>(d_tmem, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
-                                            idesc, (kb > 0 || at > 0 || k > 0) ? 1u : 0u);
-                        }
-                        if constexpr (CG == 2 && RELAY) umma_commit_leader(empty_bar(stage));
-                        else umma_commit<CG>(empty_bar(stage));
-                        if (kb == p.k_blocks - 1) umma_commit<CG>(tfull_bar(acc));
-                    }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_i8<1>(d_tmem, a_desc + uint64_t(k * kUmmaK >> 4), b_desc + uint64_t(k * kUmmaK >> 4),
+                                   idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit<1>(empty_bar(stage));
+                    if (kb == p.k_blocks - 1) umma_commit<1>(tfull_bar(acc));
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
         __syncwarp();
@@ -539,29 +477,19 @@ dist_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             const int64_t row = m0 + quarter * 32 + lane;
             const bool do_mirror = p.mirror && p.out_mode == 0 && I != J;
-            const int64_t tile_slot = CG == 2 ? u : u / 2;
             drain_accumulator<OutT>(p, tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * kAccCols), row, n0,
-                                    half * 128 + quarter * 32 + lane, tile_slot, do_mirror);
-            // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+                                    half * 128 + quarter * 32 + lane, u / 2, do_mirror);
+            // accumulator buffer drained: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
-                else mbar_arrive_local(tempty_bar(acc));
-            }
+            if (lane == 0) mbar_arrive_local(tempty_bar(acc));
         }
     }
 
-    // teardown: nobody leaves (or frees TMEM) while the partner may still signal or read
+    // teardown: nobody leaves (or frees TMEM) while a warp may still signal or read
     tc_fence_before();
-    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
-    if (p.dbg && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.dbg[blockIdx.x * 4 + 1] = t;
-        p.dbg[blockIdx.x * 4 + 3] = (unsigned long long)((p.units - worker + n_workers - 1) / n_workers);
-    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,18 +553,7 @@ dist_umma_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 int I, J;
                 tile_of(p.sq_list, T, p.tile_lo + u, I, J);
                 const int m0 = I * BTB_TILE, n0 = J * BTB_TILE;
-                if (p.lockstep && u != worker) {
-                    // see dist_umma_kernel: all producers start a round of tiles together (L2 reuse)
-                    const int64_t round = (u - worker) / n_workers;
-                    const int64_t full_rounds = p.units / n_workers;
-                    const int64_t last_count = p.units - full_rounds * n_workers;
-                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
-                    if (round > full_rounds - 1) target += last_count;
-                    target -= int64_t(p.lock_slack) * n_workers;
-                    __threadfence();
-                    atomicAdd(p.lockstep, 1u);
-                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
-                }
+                if (p.lockstep && u != worker) lockstep_wait(p, u, worker, n_workers, 1);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -750,7 +667,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
 dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const UmmaParams p) {
-    using Cfg = UmmaCfg<1>;                                  // A 128 rows + B 256 rows per 128-byte K atom, 4 stages
+    using Cfg = UmmaCfg;                                     // A 128 rows + B 256 rows per 128-byte K atom, 4 stages
     constexpr int kStages = Cfg::kStages;
     constexpr uint32_t kSfCol = 256;                         // scale factors: TMEM columns 256..271
     extern __shared__ uint8_t smem_raw[];
@@ -803,17 +720,7 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 int64_t m0, n0; int I, J, half;
                 unit_coords(u, m0, n0, I, J, half);
-                if (p.lockstep && u != worker) {                 // see dist_umma_kernel
-                    const int64_t round = (u - worker) / n_workers;
-                    const int64_t full_rounds = p.units / n_workers;
-                    const int64_t last_count = p.units - full_rounds * n_workers;
-                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
-                    if (round > full_rounds - 1) target += last_count;
-                    target -= int64_t(p.lock_slack) * n_workers;
-                    __threadfence();
-                    atomicAdd(p.lockstep, 1u);
-                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
-                }
+                if (p.lockstep && u != worker) lockstep_wait(p, u, worker, n_workers, 1);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -879,38 +786,26 @@ dist_umma_fp4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // come from a host-built work list in row-band order; cells are written where column >= row and
 // mirrored where column > row, so any set of whole block rows covers exactly the same cells as the
 // square-tile enumeration.
-constexpr int kUnitColMask = 0xffff, kUnitPrefA = 1 << 16, kUnitPrefB = 1 << 17;   // work-list entry .y
-// BK = K bytes per pipeline stage: 128 (3 stages x 62 KB, 128-byte swizzle) or 64 (6 stages x 31 KB,
-// 64-byte swizzle).  The ring is refilled at the pace  (load latency + consume time) / stages  per
-// stage; measured on C4 the load latency of a 62 KB stage is ~2,550 clk against 960 clk of MMA work,
-// so three stages starve the tensor pipe (80 % active; two stages: 56 %) while the same 186 KB cut
-// into six stages keep five of them in flight.
-template <int BK>
-struct Fp4TileCfgT {
+// (Measured and dropped, see DESIGN.md: six 31 KB stages with 64-byte swizzle, an L2 prefetch running 2-64 K blocks
+// ahead, two stages -- none changed the time by more than noise, or lost: one SM takes in ~53 B/clk of TMA traffic.)
+constexpr int kUnitColMask = 0xffff;                                  // work-list entry .y: the 240-column block
+struct Fp4TileCfg {
     static constexpr int kBN = 240;
-    static constexpr int kBK = BK;
-    static constexpr int kABytes = 256 * BK;                          // 32 KB / 16 KB
-    static constexpr int kBBytes = kBN * BK;                          // 30 KB / 15 KB
-    static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB / 31 KB (multiples of 1024)
-    static constexpr int kStages = BK == 128 ? 3 : 6;
+    static constexpr int kABytes = 256 * kBlockK;                     // 32 KB
+    static constexpr int kBBytes = kBN * kBlockK;                     // 30 KB
+    static constexpr int kStageBytes = kABytes + kBBytes;             // 62 KB (a multiple of 1024)
+    static constexpr int kStages = 3;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 1024;   // + align slack, barriers, column sums
 };
-struct Fp4TileCfg : Fp4TileCfgT<128> {
-    static constexpr int kPrefetch = 0;                               // K blocks the optional L2 prefetch runs ahead (measured: no gain,
-                                                                      // the kernel sits at the L2 -> SM throughput cap, not on DRAM latency)
-};
 
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
-
-template <typename OutT, int kStages = Fp4TileCfg::kStages, int BK = 128>
+template <typename OutT>
 __global__ void __launch_bounds__(kThreadsWide, 1)
 dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const UmmaParams p) {
-    using Cfg = Fp4TileCfgT<BK>;
-    auto make_desc = [](uint32_t addr) { return BK == 128 ? make_kmajor_sw128_desc(addr) : make_kmajor_sw64_desc(addr); };
+    using Cfg = Fp4TileCfg;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int BK = kBlockK;
+    auto make_desc = [](uint32_t addr) { return make_kmajor_sw128_desc(addr); };
     constexpr uint32_t kHalf1Col = 256, kSfCol = 496;         // accumulators at 0..239 and 256..495, scale factors 496..511
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -950,39 +845,11 @@ dist_umma_fp4_tile_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const int64_t pf = p.prefetch;
             for (int64_t u = worker; u < p.units; u += n_workers) {
                 const int2 w = p.worklist[u];
                 const int m0 = w.x * BTB_TILE, n0 = (w.y & kUnitColMask) * Cfg::kBN;
-                // next unit of this CTA: its first K blocks are prefetched while this unit finishes
-                const int2 wn = u + n_workers < p.units ? p.worklist[u + n_workers] : make_int2(0, 0);
-                if (u == worker)
-                    for (int64_t kb = 0; kb < pf && kb < p.k_blocks; ++kb) {
-                        if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(kb * BK), m0);
-                        if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int(kb * BK), n0);
-                    }
-                if (p.lockstep && u != worker) {                 // see dist_umma_kernel
-                    const int64_t round = (u - worker) / n_workers;
-                    const int64_t full_rounds = p.units / n_workers;
-                    const int64_t last_count = p.units - full_rounds * n_workers;
-                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers;
-                    if (round > full_rounds - 1) target += last_count;
-                    target -= int64_t(p.lock_slack) * n_workers;
-                    __threadfence();
-                    atomicAdd(p.lockstep, 1u);
-                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
-                }
+                if (p.lockstep && u != worker) lockstep_wait(p, u, worker, n_workers, 1);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
-                    if (pf) {
-                        const int64_t ka = kb + pf;
-                        if (ka < p.k_blocks) {
-                            if (w.y & kUnitPrefA) tma_prefetch_2d(&map_a, int(ka * BK), m0);
-                            if (w.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka + (ka >= p.neg_from ? p.b_shift : 0)) * BK), n0);
-                        } else if (ka - p.k_blocks < p.k_blocks) {
-                            if (wn.y & kUnitPrefA) tma_prefetch_2d(&map_a, int((ka - p.k_blocks) * BK), wn.x * BTB_TILE);
-                            if (wn.y & kUnitPrefB) tma_prefetch_2d(&map_b, int((ka - p.k_blocks) * BK), (wn.y & kUnitColMask) * Cfg::kBN);
-                        }
-                    }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     tma_load_2d<1>(smem_a(stage), &map_a, full_bar(stage), int(kb * BK), m0);
@@ -1143,17 +1010,7 @@ dist_umma_fp4_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const int2 w = p.worklist[u];
                 const int m0 = w.x * 512 + int(cta_rank) * 256;
                 const int n0 = (w.y & kUnitColMask) * Cfg::kBN + int(cta_rank) * (Cfg::kBN / 2);
-                if (p.lockstep && u != worker) {                 // see dist_umma_kernel; every CTA of every pair arrives
-                    const int64_t round = (u - worker) / n_workers;
-                    const int64_t full_rounds = p.units / n_workers;
-                    const int64_t last_count = p.units - full_rounds * n_workers;
-                    int64_t target = (round <= full_rounds - 1 ? round : full_rounds - 1) * n_workers * 2;
-                    if (round > full_rounds - 1) target += last_count * 2;
-                    target -= int64_t(p.lock_slack) * n_workers * 2;
-                    __threadfence();
-                    atomicAdd(p.lockstep, 1u);
-                    while (int64_t(*reinterpret_cast<volatile unsigned int *>(p.lockstep)) < target) __nanosleep(64);
-                }
+                if (p.lockstep && u != worker) lockstep_wait(p, u, worker, n_workers, 2);
                 for (int64_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
@@ -1363,7 +1220,8 @@ static int get_encode_fn(EncodeTiledFn *fn) {
 }
 
 // 2-D uint8 tensor [rows][kbytes], box = 128 K-bytes x box_rows rows, 128B swizzle, OOB rows read as 0
-static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int64_t kbytes, int box_rows, int box_k = kBlockK) {
+static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, int64_t kbytes, int box_rows) {
+    constexpr int box_k = kBlockK;
     EncodeTiledFn enc;
     BTB_TRY(get_encode_fn(&enc));
     cuuint64_t dims[2] = {cuuint64_t(kbytes), cuuint64_t(rows)};
@@ -1371,7 +1229,7 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
     cuuint32_t box[2] = {cuuint32_t(box_k), cuuint32_t(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(BTB_ECUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
     return BTB_OK;
@@ -1380,7 +1238,6 @@ static int make_operand_map(CUtensorMap *map, const void *base, int64_t rows, in
 int g_umma_dense_simplex = 2;  // dense code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron (default, see common.cuh)
 int g_umma_fp4 = 1;            // kind::mxf4 paths (see common.cuh); 0 = int8 only
 int g_umma_fp4_general = 1;    // kind::mxf4 for alphabets with ignored bytes / more than four symbols
-int g_umma_prefetch = Fp4TileCfg::kPrefetch;   // "umma_prefetch": L2 prefetch distance of the FP4 full-tile kernel in K blocks
 // "umma_coop": 0 launches the CTA-pair kernel without the cooperative attribute -- only for profilers (ncu cannot
 // replay a cooperative cluster launch); the grid is one CTA per SM, so all CTAs are co-resident whenever the GPU
 // is otherwise idle.  The default is 1 unless a profiler has injected itself into the process (Nsight Compute
@@ -1391,202 +1248,169 @@ static bool profiler_attached() {
 }
 int g_umma_coop = profiler_attached() ? 0 : 1;
 int g_umma_fp4_pair = 1;       // "umma_fp4_pair": cta_group::2 version of the FP4 full-tile kernel (0: single-CTA kernel)
-int g_umma_tile_bk = 128;      // "umma_tile_bk": K bytes per stage of the FP4 full-tile kernel (128: 3 stages; 64: 6 stages -- measured equal)
-int g_umma_dbg_max_ctas = 0;   // experiment: cap the grid of the FP4 full-tile kernel (0 = one CTA per SM)
-int g_umma_dbg_stages = 0;     // experiment: 2 = run the FP4 full-tile kernel with two pipeline stages
-int g_umma_dbg_negate = 0;     // experiment: negate every K block of the FP4 kernels (probes the descriptor bit)
 int g_umma_tile_mode = 1;      // 1: one CTA per full 256x256 tile (shared B block), 0: half-tile units
 int g_umma_lockstep = 1;       // 0: off; k >= 1: producers of all CTAs start each unit at most k-1 rounds apart (L2 reuse), cooperative launch
-int g_umma_cg2_variant = 0;    // experiment knob, see UmmaCfg
-int g_umma_cta_group = 1;     // 1 = single-CTA 128x256 UMMA, 2 = CTA pairs (256x256); btb_set_option
 
-// Arrival counters of the lockstep barrier.  Every launch takes the next of 64 slots (128 bytes apart) and
-// clears it on its own stream: a launch on another stream can then never reset a counter a running
-// kernel is still waiting on (the launches need the whole GPU, so 64 launches later a slot is long free).
-static int lock_slot(int dev, unsigned int **slot) {
-    static unsigned int *pool[16] = {nullptr};
-    static std::atomic<unsigned> next[16];
-    static std::mutex m;
-    if (dev < 0 || dev >= 16) return fail(BTB_EINVAL, "device ordinal too large");
-    {
-        std::lock_guard<std::mutex> lock(m);
-        if (!pool[dev]) BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&pool[dev]), 64 * 128));
+// Arrival counters of the lockstep barrier.  A launch OWNS its counter until the kernel has finished: the slot is
+// taken from a per-device pool, cleared on the launching stream, and an event recorded behind the kernel marks
+// when it may be handed out again -- so a launch queued on another stream can never clear a counter that a
+// running (or still pending) kernel waits on.  When all slots are pending the oldest one is waited for.
+namespace {
+struct LockSlot { unsigned int *ptr = nullptr; cudaEvent_t done = nullptr; bool pending = false; };
+struct LockPool { unsigned int *mem = nullptr; std::vector<LockSlot> slots; size_t next = 0; };
+std::mutex g_lock_mutex;
+std::vector<LockPool> g_lock_pools;            // indexed by device ordinal
+constexpr int kLockSlots = 64;
+
+int lock_acquire(unsigned int **ptr, int *slot_index, cudaStream_t stream) {
+    int dev = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_lock_mutex);
+    if (int(g_lock_pools.size()) <= dev) g_lock_pools.resize(size_t(dev) + 1);
+    LockPool &pool = g_lock_pools[size_t(dev)];
+    if (!pool.mem) {
+        BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&pool.mem), kLockSlots * 128));
+        pool.slots.resize(kLockSlots);
+        for (int k = 0; k < kLockSlots; ++k) {
+            pool.slots[size_t(k)].ptr = pool.mem + k * 32;          // 128 bytes apart
+            BTB_CUDA(cudaEventCreateWithFlags(&pool.slots[size_t(k)].done, cudaEventDisableTiming));
+        }
     }
-    *slot = pool[dev] + (next[dev].fetch_add(1) % 64u) * 32u;
+    int pick = -1;
+    for (int k = 0; k < kLockSlots && pick < 0; ++k) {
+        LockSlot &sl = pool.slots[(pool.next + size_t(k)) % kLockSlots];
+        if (!sl.pending || cudaEventQuery(sl.done) == cudaSuccess) pick = int((pool.next + size_t(k)) % kLockSlots);
+    }
+    if (pick < 0) {                                                  // every slot belongs to a kernel still in flight
+        pick = int(pool.next % kLockSlots);
+        BTB_CUDA(cudaEventSynchronize(pool.slots[size_t(pick)].done));
+    }
+    cudaGetLastError();                                              // cudaErrorNotReady from the queries is not an error
+    pool.next = size_t(pick) + 1;
+    pool.slots[size_t(pick)].pending = false;
+    BTB_CUDA(cudaMemsetAsync(pool.slots[size_t(pick)].ptr, 0, 4, stream));
+    *ptr = pool.slots[size_t(pick)].ptr;
+    *slot_index = pick;
+    return BTB_OK;
+}
+// behind the kernel launch, on its stream
+int lock_commit(int slot_index, cudaStream_t stream) {
+    int dev = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_lock_mutex);
+    LockSlot &sl = g_lock_pools[size_t(dev)].slots[size_t(slot_index)];
+    BTB_CUDA(cudaEventRecord(sl.done, stream));
+    sl.pending = true;
     return BTB_OK;
 }
 
-template <int CG, typename OutT, int ATOMS = 1, bool RELAY = false>
-static int launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
-    using Cfg = UmmaCfg<CG, ATOMS, RELAY>;
-    auto kernel = dist_umma_kernel<CG, OutT, ATOMS, RELAY>;
-    BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    int dev = 0, sms = 0;
-    BTB_CUDA(cudaGetDevice(&dev));
-    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+// cooperative launch of a kernel whose producers run in lockstep (when `lockstep` and the launch has more units
+// than workers); a plain launch otherwise
+template <typename Kernel>
+int launch_lockstep(Kernel kernel, dim3 grid, dim3 block, int smem_bytes, int cluster, bool want_lockstep, bool cooperative,
+                    const CUtensorMap &ma, const CUtensorMap &mb, UmmaParams p, cudaStream_t stream) {
+    BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    int64_t ctas = CG == 2 ? std::min<int64_t>(sms / 2, p.units) * 2 : std::min<int64_t>(sms, p.units);
-    cfg.gridDim = dim3(unsigned(ctas));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[2];
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = size_t(smem_bytes);
     cfg.stream = stream;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    UmmaParams q = p;
-    cudaLaunchAttribute attrs2[2];
-    if (g_umma_lockstep && p.units > ctas / (CG == 2 ? 2 : 1) && dev < 16) {
-        unsigned int *slot = nullptr;
-        BTB_TRY(lock_slot(dev, &slot));
-        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
-        q.lockstep = slot; q.lock_slack = g_umma_lockstep - 1;
-        attrs2[0] = attr[0];
-        attrs2[1].id = cudaLaunchAttributeCooperative;
-        attrs2[1].val.cooperative = 1;
-        cfg.attrs = attrs2;
-        cfg.numAttrs = 2;
-    }
-    unsigned long long *d_dbg = nullptr;
-    const bool debug = getenv("BTB_UMMA_DEBUG") != nullptr;
-    if (debug) {
-        BTB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_dbg), size_t(ctas) * 32));
-        BTB_CUDA(cudaMemset(d_dbg, 0, size_t(ctas) * 32));
-        q.dbg = d_dbg;
-    }
-    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, q));
-    if (debug) {
-        BTB_CUDA(cudaStreamSynchronize(stream));
-        std::vector<unsigned long long> h(size_t(ctas) * 4);
-        BTB_CUDA(cudaMemcpy(h.data(), d_dbg, size_t(ctas) * 32, cudaMemcpyDeviceToHost));
-        cudaFree(d_dbg);
-        unsigned long long t0 = ~0ull;
-        for (int64_t c = 0; c < ctas; ++c) t0 = std::min(t0, h[size_t(c) * 4]);
-        fprintf(stderr, "[umma debug] CG=%d ctas=%lld units=%lld k_blocks=%lld\n", CG, (long long)ctas, (long long)p.units, (long long)p.k_blocks);
-        for (int64_t c = 0; c < ctas; ++c)
-            fprintf(stderr, "[umma debug] cta %3lld sm %3llu start %9.1f us end %9.1f us units %llu\n", (long long)c, h[size_t(c) * 4 + 2],
-                    (h[size_t(c) * 4] - t0) * 1e-3, (h[size_t(c) * 4 + 1] - t0) * 1e-3, h[size_t(c) * 4 + 3]);
-    }
-    return BTB_OK;
-}
-
-template <typename OutT>
-static int launch_umma_tile(const CUtensorMap &ma, const CUtensorMap &mb, const UmmaParams &p, cudaStream_t stream) {
-    auto kernel = dist_umma_tile_kernel<OutT>;
-    BTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::kSmemBytes));
-    int dev = 0, sms = 0;
-    BTB_CUDA(cudaGetDevice(&dev));
-    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t ctas = std::min<int64_t>(sms, p.units);
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    cfg.gridDim = dim3(unsigned(ctas));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = TileCfg::kSmemBytes;
-    cfg.stream = stream;
     cfg.numAttrs = 0;
-    UmmaParams q = p;
-    if (g_umma_lockstep && p.units > ctas && dev < 16) {
-        unsigned int *slot = nullptr;
-        BTB_TRY(lock_slot(dev, &slot));
-        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
-        q.lockstep = slot; q.lock_slack = g_umma_lockstep - 1;
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+    if (cluster > 1) {
+        attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+        attr[cfg.numAttrs].val.clusterDim.x = unsigned(cluster);
+        attr[cfg.numAttrs].val.clusterDim.y = 1;
+        attr[cfg.numAttrs].val.clusterDim.z = 1;
+        ++cfg.numAttrs;
     }
-    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, q));
+    int slot = -1;
+    if (want_lockstep) {
+        unsigned int *counter = nullptr;
+        BTB_TRY(lock_acquire(&counter, &slot, stream));
+        p.lockstep = counter;
+        p.lock_slack = g_umma_lockstep - 1;
+        if (cooperative) {
+            attr[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
+            attr[cfg.numAttrs].val.cooperative = 1;
+            ++cfg.numAttrs;
+        }
+    }
+    BTB_CUDA(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p));
+    if (slot >= 0) BTB_TRY(lock_commit(slot, stream));
+    return BTB_OK;
+}
+}  // namespace
+
+static int device_sms(int *sms) {
+    int dev = 0;
+    BTB_CUDA(cudaGetDevice(&dev));
+    BTB_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
     return BTB_OK;
 }
 
-// how many CTA pairs of the CG = 2 kernel the device can keep resident at once
+// how many CTA pairs of the FP4 pair kernel (cg = 2) / CTAs of the int8 kernel (cg = 1) the device keeps resident
 int umma_max_active_clusters(int cg, int *out) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    cfg.gridDim = dim3(cg == 2 ? 148 : 148);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = cg == 2 ? UmmaCfg<2>::kSmemBytes : UmmaCfg<1>::kSmemBytes;
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(cg == 2 ? kThreadsWide : kThreads);
+    cfg.dynamicSmemBytes = cg == 2 ? Fp4PairCfg::kSmemBytes : UmmaCfg::kSmemBytes;
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.x = cg == 2 ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (cg == 2) {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_kernel<2, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<2>::kSmemBytes));
-        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_kernel<2, uint16_t>, &cfg));
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_pair_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4PairCfg::kSmemBytes));
+        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_fp4_pair_kernel<uint16_t>, &cfg));
     } else {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_kernel<1, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
-        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_kernel<1, uint16_t>, &cfg));
+        BTB_CUDA(cudaFuncSetAttribute(dist_umma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::kSmemBytes));
+        BTB_CUDA(cudaOccupancyMaxActiveClusters(out, dist_umma_kernel<uint16_t>, &cfg));
     }
     return BTB_OK;
 }
 
 // ---- explicit work lists (device resident, cached per device) ----------------------------------
-// kind 0: square tiles (I, J >= I) of block rows [lo, hi); kind 1: rectangular 256 x 240 tiles (I, j).
-// Both in band order relative to `lo`: bands of kBand block rows, column-major inside a band.
+// kind 0: square tiles (I, J >= I) of block rows [lo, hi); kind 1: rectangular 256 x 240 tiles (I, j);
+// kind 2: CTA-pair units (P, j) of 512 rows x 240 columns.  All in band order relative to `lo`: bands of
+// kBand block rows, column-major inside a band.
 struct DevList { int64_t n, lo, hi; int kind; int2 *d; int64_t count; };
-static std::vector<DevList> g_lists[16];
+static std::vector<std::vector<DevList>> g_lists;            // indexed by device ordinal
 static std::mutex g_lists_mutex;
 
 int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_out, int64_t *count) {
     int dev = 0;
     BTB_CUDA(cudaGetDevice(&dev));
-    if (dev >= 16) return fail(BTB_EINVAL, "device ordinal too large");
     std::lock_guard<std::mutex> lock(g_lists_mutex);
-    for (auto &e : g_lists[dev])
+    if (int(g_lists.size()) <= dev) g_lists.resize(size_t(dev) + 1);
+    std::vector<DevList> &lists = g_lists[size_t(dev)];
+    for (auto &e : lists)
         if (e.n == n && e.lo == lo && e.hi == hi && e.kind == kind) { *d_out = e.d; *count = e.count; return BTB_OK; }
-    if (g_lists[dev].size() > 512) {                     // (never reached by one alignment: a list per band and kind)
+    if (lists.size() > 512) {                            // (never reached by one alignment: a list per band and kind)
         BTB_CUDA(cudaDeviceSynchronize());
-        for (auto &e : g_lists[dev]) cudaFree(e.d);
-        g_lists[dev].clear();
+        for (auto &e : lists) cudaFree(e.d);
+        lists.clear();
     }
     const int64_t T = tiles_per_dim(n);
     std::vector<int2> h;
-    if (kind == 0) {
-        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
-            const int64_t r1 = std::min(hi, r0 + kBand);
+    for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
+        const int64_t r1 = std::min(hi, r0 + kBand);
+        if (kind == 0) {
             for (int64_t J = r0; J < T; ++J)
                 for (int64_t I = r0; I < r1 && I <= J; ++I) h.push_back(make_int2(int(I), int(J)));
-        }
-    } else {
-        const int64_t NJ = (n + Fp4TileCfg::kBN - 1) / Fp4TileCfg::kBN;
-        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
-            const int64_t r1 = std::min(hi, r0 + kBand);
+        } else if (kind == 1) {
+            const int64_t NJ = (n + Fp4TileCfg::kBN - 1) / Fp4TileCfg::kBN;
             for (int64_t j = (r0 * BTB_TILE) / Fp4TileCfg::kBN; j < NJ; ++j)
                 for (int64_t I = r0; I < r1; ++I)
                     if ((I * BTB_TILE) / Fp4TileCfg::kBN <= j) h.push_back(make_int2(int(I), int(j)));
-        }
-    }
-    if (kind == 2) {
-        // CTA-pair units (P, j): 512 rows x 240 columns, same band order (4 pair rows per band)
-        h.clear();
-        const int64_t NJ = (n + Fp4PairCfg::kBN - 1) / Fp4PairCfg::kBN;
-        for (int64_t r0 = lo; r0 < hi; r0 += kBand) {
-            const int64_t r1 = std::min(hi, r0 + kBand);
+        } else {
+            const int64_t NJ = (n + Fp4PairCfg::kBN - 1) / Fp4PairCfg::kBN;
             for (int64_t j = (r0 * BTB_TILE) / Fp4PairCfg::kBN; j < NJ; ++j)
                 for (int64_t P = r0 / 2; P < (r1 + 1) / 2; ++P)
                     if ((P * 512) / Fp4PairCfg::kBN <= j) h.push_back(make_int2(int(P), int(j)));
-        }
-    } else if (kind == 1) {
-        // L2 prefetch duty: the grid runs the list in rounds of one unit per SM; within a round the
-        // first unit that touches an A panel (block row) / a B panel (column block) prefetches it
-        int sms = 0;
-        BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        for (size_t r0 = 0; r0 < h.size(); r0 += size_t(sms)) {
-            const size_t r1 = std::min(h.size(), r0 + size_t(sms));
-            for (size_t a = r0; a < r1; ++a) {
-                bool first_a = true, first_b = true;
-                for (size_t b = r0; b < a; ++b) {
-                    if (h[b].x == h[a].x) first_a = false;
-                    if ((h[b].y & kUnitColMask) == (h[a].y & kUnitColMask)) first_b = false;
-                }
-                h[a].y |= (first_a ? kUnitPrefA : 0) | (first_b ? kUnitPrefB : 0);
-            }
         }
     }
     DevList e{n, lo, hi, kind, nullptr, int64_t(h.size())};
@@ -1602,122 +1426,64 @@ int get_rows_list(int64_t n, int64_t lo, int64_t hi, int kind, const int2 **d_ou
         cudaStreamDestroy(cs);
         if (ce != cudaSuccess) { cudaFree(e.d); return fail(BTB_ECUDA, "work list upload failed: %s", cudaGetErrorString(ce)); }
     }
-    g_lists[dev].push_back(e);
+    lists.push_back(e);
     *d_out = e.d;
     *count = e.count;
     return BTB_OK;
 }
 
-// FP4 full-tile kernel over the block rows [row_lo, row_hi); *launched = 0 when the range is too
+static UmmaParams base_params(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_from, void *d_out, int64_t out_ld, int out_mode, int mirror) {
+    UmmaParams p;
+    p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = 0;
+    p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
+    p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr; p.sq_list = nullptr;
+    p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;             // tetrahedron code (row sums) / V - X planes
+    p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
+    if (neg_from >= 0) p.neg_from = neg_from;
+    return p;
+}
+
+// FP4 full-tile kernels over the block rows [row_lo, row_hi); *launched = 0 when the range is too
 // small to fill the GPU twice (the caller then uses the half-tile kernel)
 static int launch_fp4_rows(const uint8_t *A, int64_t n, int64_t kb, int64_t neg_from, int64_t row_lo, int64_t row_hi, void *d_out,
                            int out_elem_bytes, int64_t out_ld, int mirror, cudaStream_t stream, int *launched) {
     *launched = 0;
-    int dev = 0, sms = 0;
-    BTB_CUDA(cudaGetDevice(&dev));
-    BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0;
+    BTB_TRY(device_sms(&sms));
     const int2 *d_units = nullptr;
     int64_t n_units = 0;
-    if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && (row_hi % 2 == 0 || row_hi == tiles_per_dim(n)) && dev < 16) {
+    CUtensorMap ma, mb;
+    if (g_umma_fp4_pair && out_elem_bytes == 2 && row_lo % 2 == 0 && (row_hi % 2 == 0 || row_hi == tiles_per_dim(n))) {
         // CTA pairs: 512-row units, B split between the two SMs of a pair
         BTB_TRY(get_rows_list(n, row_lo, row_hi, 2, &d_units, &n_units));
         if (n_units >= 2 * int64_t(sms / 2)) {
-            CUtensorMap ma, mb;
             BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
             BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4PairCfg::kBN / 2));
-            UmmaParams p;
-            p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = 0; p.units = n_units;
-            p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
-            p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
-            p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;
-            p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-            if (neg_from >= 0) p.neg_from = neg_from;
-            const int64_t pairs = std::min<int64_t>(sms / 2, p.units);
-            cudaLaunchConfig_t cfg = {};
-            cudaLaunchAttribute attr[2];
-            cfg.gridDim = dim3(unsigned(pairs * 2));
-            cfg.blockDim = dim3(kThreadsWide);
-            cfg.dynamicSmemBytes = Fp4PairCfg::kSmemBytes;
-            cfg.stream = stream;
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (g_umma_lockstep && p.units > pairs) {
-                unsigned int *slot = nullptr;
-                BTB_TRY(lock_slot(dev, &slot));
-                BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
-                p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
-                attr[1].id = cudaLaunchAttributeCooperative;
-                attr[1].val.cooperative = 1;
-                cfg.numAttrs = g_umma_coop ? 2 : 1;
-            }
-            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_pair_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4PairCfg::kSmemBytes));
+            UmmaParams p = base_params(A, n, kb, neg_from, d_out, out_ld, 0, mirror);
+            p.units = n_units; p.worklist = d_units;
             // the lockstep barrier needs every pair resident: never launch more pairs than the device can hold
-            static int max_pairs[16] = {0};
-            if (!max_pairs[dev]) {
-                int m = 0;
-                cudaLaunchConfig_t probe = cfg;
-                probe.gridDim = dim3(unsigned(sms / 2 * 2));
-                probe.numAttrs = 1;                       // cluster dimension only
-                BTB_CUDA(cudaOccupancyMaxActiveClusters(&m, dist_umma_fp4_pair_kernel<uint16_t>, &probe));
-                max_pairs[dev] = std::max(1, m);
-            }
-            if (pairs > max_pairs[dev]) cfg.gridDim = dim3(unsigned(max_pairs[dev] * 2));
-            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_pair_kernel<uint16_t>, ma, mb, p));
+            int max_pairs = 0;
+            BTB_TRY(umma_max_active_clusters(2, &max_pairs));
+            const int64_t pairs = std::min<int64_t>(std::min<int64_t>(sms / 2, std::max(1, max_pairs)), p.units);
+            BTB_TRY(launch_lockstep(dist_umma_fp4_pair_kernel<uint16_t>, dim3(unsigned(pairs * 2)), dim3(kThreadsWide), Fp4PairCfg::kSmemBytes, 2,
+                                    g_umma_lockstep && p.units > pairs, g_umma_coop != 0, ma, mb, p, stream));
             *launched = 1;
             return BTB_OK;
         }
     }
     BTB_TRY(get_rows_list(n, row_lo, row_hi, 1, &d_units, &n_units));
-    if (n_units < 2 * int64_t(sms) || dev >= 16) return BTB_OK;
-    CUtensorMap ma, mb;
-    const int bk = (g_umma_tile_bk == 64 && out_elem_bytes == 2 && g_umma_dbg_stages != 2) ? 64 : 128;
-    BTB_TRY(make_operand_map(&ma, A, n, kb, 256, bk));
-    BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN, bk));
-    UmmaParams p;
-    p.n = n; p.k_blocks = kb / bk; p.tile_lo = 0; p.units = n_units;
-    p.out = d_out; p.ld = out_ld; p.out_mode = 0; p.mirror = mirror;
-    p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = d_units; p.sq_list = nullptr;
-    p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;            // tetrahedron code (row sums) / V - X planes
-    p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-    if (neg_from >= 0) p.neg_from = neg_from * (kBlockK / bk);
-    if (g_umma_dbg_negate) p.neg_from = 0;
-    p.prefetch = g_umma_prefetch;
-    unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
-    if (g_umma_dbg_max_ctas > 0) ctas = std::min<unsigned>(ctas, unsigned(g_umma_dbg_max_ctas));
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(kThreadsWide);
-    cfg.dynamicSmemBytes = Fp4TileCfg::kSmemBytes;
-    cfg.stream = stream;
-    cfg.numAttrs = 0;
-    if (g_umma_lockstep && p.units > ctas) {
-        unsigned int *slot = nullptr;
-        BTB_TRY(lock_slot(dev, &slot));
-        BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
-        p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-    }
-    if (bk == 64) {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t, 6, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfgT<64>::kSmemBytes));
-        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t, 6, 64>, ma, mb, p));
-    } else if (out_elem_bytes == 2 && g_umma_dbg_stages == 2) {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
-        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t, 2>, ma, mb, p));
-    } else if (out_elem_bytes == 2) {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
-        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint16_t>, ma, mb, p));
-    } else {
-        BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fp4TileCfg::kSmemBytes));
-        BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_tile_kernel<uint32_t>, ma, mb, p));
-    }
+    if (n_units < 2 * int64_t(sms)) return BTB_OK;
+    BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+    BTB_TRY(make_operand_map(&mb, A, n, kb, Fp4TileCfg::kBN));
+    UmmaParams p = base_params(A, n, kb, neg_from, d_out, out_ld, 0, mirror);
+    p.units = n_units; p.worklist = d_units;
+    const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+    if (out_elem_bytes == 2)
+        BTB_TRY(launch_lockstep(dist_umma_fp4_tile_kernel<uint16_t>, dim3(ctas), dim3(kThreadsWide), Fp4TileCfg::kSmemBytes, 1,
+                                g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream));
+    else
+        BTB_TRY(launch_lockstep(dist_umma_fp4_tile_kernel<uint32_t>, dim3(ctas), dim3(kThreadsWide), Fp4TileCfg::kSmemBytes, 1,
+                                g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream));
     *launched = 1;
     return BTB_OK;
 }
@@ -1728,11 +1494,12 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
     const int64_t tiles = tile_hi - tile_lo;
     if (tiles <= 0) return BTB_OK;
     const int64_t kb = umma_k_bytes(len, sigma);
-    const int cg = g_umma_cta_group == 1 ? 1 : 2;
     const uint8_t *A = static_cast<const uint8_t *>(d_operands);
     const uint8_t *B = sigma_dense(sigma) ? A : A + n * kb;   // dense: one operand serves both sides
     if (kb == 0) return fail(BTB_EINVAL, "UMMA engine needs len > 0");
     const int64_t neg_from = umma_fp4_general(sigma, len) ? umma_fp4_plane_bytes(len) / kBlockK : -1;
+    int sms = 0;
+    BTB_TRY(device_sms(&sms));
     CUtensorMap ma, mb;
     if (!sq_list && umma_use_fp4(sigma, len) && g_umma_tile_mode == 1 && out_mode == 0) {
         // whole bands of block rows (the full matrix, the level-1/2 band launches): rectangular full tiles
@@ -1750,93 +1517,48 @@ int distance_tiles_umma(const void *d_operands, int64_t n, int64_t len, int sigm
         }
     }
     if (umma_use_fp4(sigma, len)) {
+        // FP4 half-tile units: small launches and explicit tile lists
         BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
         BTB_TRY(make_operand_map(&mb, A, n, kb, 256));
-        UmmaParams p;
-        p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles * 2;
-        p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 1; p.worklist = nullptr; p.sq_list = sq_list;
-        p.dense = neg_from < 0 ? 3 : 0; p.bias = 0;
-        p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-        if (neg_from >= 0) p.neg_from = neg_from;
-        if (g_umma_dbg_negate) p.neg_from = 0;
-        int dev = 0, sms = 0;
-        BTB_CUDA(cudaGetDevice(&dev));
-        BTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        UmmaParams p = base_params(A, n, kb, neg_from, d_out, out_ld, out_mode, mirror);
+        p.tile_lo = tile_lo; p.units = tiles * 2; p.sq_list = sq_list;
         const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        cfg.gridDim = dim3(ctas);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = UmmaCfg<1>::kSmemBytes;
-        cfg.stream = stream;
-        cfg.numAttrs = 0;
-            if (g_umma_lockstep && p.units > ctas && dev < 16) {
-                unsigned int *slot = nullptr;
-                BTB_TRY(lock_slot(dev, &slot));
-                BTB_CUDA(cudaMemsetAsync(slot, 0, 4, stream));
-                p.lockstep = slot; p.lock_slack = g_umma_lockstep - 1;
-            attr[0].id = cudaLaunchAttributeCooperative;
-            attr[0].val.cooperative = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-        }
-        if (out_elem_bytes == 2) {
-            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
-            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_kernel<uint16_t>, ma, mb, p));
-        } else {
-            BTB_CUDA(cudaFuncSetAttribute(dist_umma_fp4_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<1>::kSmemBytes));
-            BTB_CUDA(cudaLaunchKernelEx(&cfg, dist_umma_fp4_kernel<uint32_t>, ma, mb, p));
-        }
-        BTB_CUDA(cudaGetLastError());
-        return BTB_OK;
+        if (out_elem_bytes == 2)
+            return launch_lockstep(dist_umma_fp4_kernel<uint16_t>, dim3(ctas), dim3(kThreads), UmmaCfg::kSmemBytes, 1,
+                                   g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
+        return launch_lockstep(dist_umma_fp4_kernel<uint32_t>, dim3(ctas), dim3(kThreads), UmmaCfg::kSmemBytes, 1,
+                               g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
     }
-    int sms_now = 148, dev_now = 0;
-    if (cudaGetDevice(&dev_now) == cudaSuccess) cudaDeviceGetAttribute(&sms_now, cudaDevAttrMultiProcessorCount, dev_now);
-    // full tiles only pay off once every SM gets at least two of them; small problems keep the
-    // half-tile units (twice the parallelism)
-    if (cg == 1 && g_umma_tile_mode == 1 && tiles >= 2 * int64_t(sms_now)) {
-        BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
-        BTB_TRY(make_operand_map(&mb, B, n, kb, 256));
-        UmmaParams p;
-        p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo; p.units = tiles;
-        p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
-        p.dbg = nullptr; p.lockstep = nullptr; p.fp32acc = 0; p.worklist = nullptr; p.sq_list = sq_list;
-        p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
-        p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
-        p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-        return out_elem_bytes == 2 ? launch_umma_tile<uint16_t>(ma, mb, p, stream) : launch_umma_tile<uint32_t>(ma, mb, p, stream);
-    }
-    BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
-    BTB_TRY(make_operand_map(&mb, B, n, kb, cg == 2 ? 128 : 256));
+    // kind::i8 (rows beyond the fp32-exact range of the FP4 paths, or "umma_fp4" = 0)
     UmmaParams p;
-    p.n = n;
-    const int variant = cg == 2 ? g_umma_cg2_variant : 0;      // bit 0: 2 atoms per stage, bit 1: relay
-    const int atoms = (variant & 1) ? 2 : 1;
-    p.k_blocks = (kb / kBlockK + atoms - 1) / atoms;
-    p.tile_lo = tile_lo;
-    p.units = cg == 2 ? tiles : tiles * 2;
-    p.out = d_out;
-    p.ld = out_ld;
-    p.out_mode = out_mode;
-    p.mirror = mirror;
-    p.dbg = nullptr;
-    p.lockstep = nullptr;
-    p.fp32acc = 0;
-    p.worklist = nullptr; p.sq_list = sq_list;
+    p.n = n; p.k_blocks = kb / kBlockK; p.tile_lo = tile_lo;
+    p.out = d_out; p.ld = out_ld; p.out_mode = out_mode; p.mirror = mirror;
+    p.lockstep = nullptr; p.fp32acc = 0; p.worklist = nullptr; p.sq_list = sq_list;
     p.dense = sigma_dense(sigma) ? (g_umma_dense_simplex == 2 ? 3 : g_umma_dense_simplex ? 2 : 1) : 0;
     p.bias = int32_t(g_umma_dense_simplex ? 3 * len : len);
     p.rowsum = reinterpret_cast<const int32_t *>(A + n * kb);
-    if (cg == 2 && out_elem_bytes == 2) {
-        switch (variant & 3) {
-            case 1: return launch_umma<2, uint16_t, 2, false>(ma, mb, p, stream);
-            case 2: return launch_umma<2, uint16_t, 1, true>(ma, mb, p, stream);
-            case 3: return launch_umma<2, uint16_t, 2, true>(ma, mb, p, stream);
-            default: return launch_umma<2, uint16_t>(ma, mb, p, stream);
-        }
+    // full tiles only pay off once every SM gets at least two of them; small problems keep the
+    // half-tile units (twice the parallelism)
+    if (g_umma_tile_mode == 1 && tiles >= 2 * int64_t(sms)) {
+        BTB_TRY(make_operand_map(&ma, A, n, kb, 256));
+        BTB_TRY(make_operand_map(&mb, B, n, kb, 256));
+        p.units = tiles;
+        const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+        if (out_elem_bytes == 2)
+            return launch_lockstep(dist_umma_tile_kernel<uint16_t>, dim3(ctas), dim3(kThreads), TileCfg::kSmemBytes, 1,
+                                   g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
+        return launch_lockstep(dist_umma_tile_kernel<uint32_t>, dim3(ctas), dim3(kThreads), TileCfg::kSmemBytes, 1,
+                               g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
     }
-    if (cg == 2) return launch_umma<2, uint32_t>(ma, mb, p, stream);
-    return out_elem_bytes == 2 ? launch_umma<1, uint16_t>(ma, mb, p, stream) : launch_umma<1, uint32_t>(ma, mb, p, stream);
+    BTB_TRY(make_operand_map(&ma, A, n, kb, 128));
+    BTB_TRY(make_operand_map(&mb, B, n, kb, 256));
+    p.units = tiles * 2;
+    const unsigned ctas = unsigned(std::min<int64_t>(sms, p.units));
+    if (out_elem_bytes == 2)
+        return launch_lockstep(dist_umma_kernel<uint16_t>, dim3(ctas), dim3(kThreads), UmmaCfg::kSmemBytes, 1,
+                               g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
+    return launch_lockstep(dist_umma_kernel<uint32_t>, dim3(ctas), dim3(kThreads), UmmaCfg::kSmemBytes, 1,
+                           g_umma_lockstep && p.units > ctas, true, ma, mb, p, stream);
 }
 
 

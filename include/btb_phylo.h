@@ -68,17 +68,20 @@ int         btb_device_count(int *count);                 /* number of usable sm
  *     "umma_tile_mode" [1]     full-tile kernels when a launch has >= 2 units per SM (0: half-tile units only)
  *     "umma_dense_simplex" [2] dense int8 code: 0 one-hot, 1 +-1 simplex, 2 0/1 tetrahedron
  *     "umma_lockstep" [1]      0 off, k >= 1: TMA producers of all CTAs start a unit at most k-1 rounds apart
- *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (for ncu)
- *     "umma_prefetch" [0], "umma_tile_bk" [128], "umma_cta_group" [1], "umma_cg2_variant" [0]: measured alternatives
- *       (L2 prefetch distance, 64-byte K blocks with six stages, int8 CTA pairs) kept for the record, see DESIGN.md
+ *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (set automatically when
+ *                              a profiler is attached: ncu cannot replay a cooperative cluster launch)
  *   extraction: "pack_wpt" [2] plane words per thread of k1 (1, 2, 4); "ingest_predict" [1] predicted FASTA framing
- *   level 1/2:  "csv_mmap" [0] write snps.csv through a file mapping; "dense_pageable" [1] large snps.fas into
- *               pageable host memory; "host_stream" [0] + "host_stream_rows" [64] streamed level-2 call
- * btb_query also answers "ingest_last_predicted", "host_stream_last", "umma_max_active_clusters_cg1|2" and
- * "probe_cg<1|2>_e<k>" (MMA issue probe, cycles x 100 per stage).
+ *   level 1/2:  "dense_pageable" [1] large snps.fas into pageable host memory; "host_stream" [0] +
+ *               "host_stream_rows" [64] streamed level-2 call;
+ *               "comm_band_rows" [16] block rows per launch + copy band of a rank's share (btb_dist_matrix_host_comm);
+ *               "csv_mmap" [-1] snps.csv through a file mapping (-1: on tmpfs only); "csv_prealloc" [1]; "replace_unlink_first" [0];
+ *               "multi_gpu_oversubscribe" [0] (tests) several workers per device when n_gpus exceeds the devices
+ * btb_query also answers "ingest_last_predicted", "host_stream_last", "comm_last_path", "umma_max_active_clusters_cg1|2" and
+ * "probe_cg<1|2>_e<k>" (tensor-pipe issue probe: cycles x 100 per stage of 8 MMAs 128 x 240 x 64 per SM, a commit every
+ * k stages -- the measured peak bench.py's roofline divides by).
  * The environment variable BTB_OPTIONS="key=value,..." sets options for the Python binding. */
 int         btb_set_option(const char *key, int value);
-/* introspection: "umma_cta_group", "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
+/* introspection: the option values, "umma_max_active_clusters_cg1" / "_cg2" (resident CTAs / CTA pairs) */
 int         btb_query(const char *key, int64_t *value);
 
 /* =====================================================================================

@@ -1,6 +1,6 @@
 """GPU (-m gpu): the distance stage (k4) through the C-ABI against the CPU oracle, bit-exact.
-Both engines (POPC bit-planes; tcgen05: kind::mxf4 on 0/1 nibble codes with CTA pairs, single CTAs and
-half-tile units, and the kind::i8 kernels), default and -a / -k modes, ragged sizes, tile-packed
+Both engines (POPC bit-planes; tcgen05: kind::mxf4 on 0/1 nibble codes with CTA pairs (cg = 2), single
+CTAs (cg = 1) and half-tile units, and the kind::i8 kernels), default and -a / -k modes, ragged sizes, tile-packed
 output, rank shares by tiles and by block rows, uint16 / uint32 output, the level-2 host call."""
 import ctypes
 
@@ -26,7 +26,7 @@ def to_device(seqs):
 def gpu_matrix(capi, seqs, engine, cg, allchars=False, keepcase=False, out_dtype=None):
     from btb_phylo_b200 import device
     if cg:
-        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+        capi.check(capi.lib().btb_set_option(b"umma_fp4_pair", 1 if cg == 2 else 0))
     plan = device.DistancePlan(to_device(seqs), length=seqs.shape[1], allchars=allchars, keepcase=keepcase,
                                engine=engine, out_dtype=out_dtype)
     plan.encode()
@@ -75,7 +75,7 @@ def test_dense_alignments_use_compact_encodings(capi, oracle, name, engine, cg, 
 
 def test_kernel_variants_agree(capi, oracle):
     """Every tuning variant of the tensor-core engine gives the same integers: dense codes
-    (one-hot / +-1 simplex / 0-1 tetrahedron with row sums), CTA-pair stage shapes and release paths."""
+    (one-hot / +-1 simplex / 0-1 tetrahedron with row sums), CTA pairs or single CTAs, lockstep on or off."""
     lib = capi.lib()
     dense = synth.snp_alignment(700, 3001, seed=12)
     general = synth.snp_alignment(700, 3001, seed=13, heavy_n=0.1)
@@ -114,10 +114,8 @@ def test_kernel_variants_agree(capi, oracle):
                 _, got = gpu_matrix(capi, general, 1, 1)
                 assert (got == want_g).all(), (general_fp4, tile_mode)
         capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
-        # tuning knobs of the FP4 full-tile kernels: CTA pairs (cta_group::2), 64-byte K blocks with six
-        # stages, L2 prefetch, loose lockstep
-        for key, values, reset in ((b"umma_fp4_pair", (0, 1), None), (b"umma_tile_bk", (64, 128), 128),
-                                   (b"umma_prefetch", (8, 0), 0), (b"umma_lockstep", (3, 0, 1), 1)):
+        # tuning knobs of the FP4 full-tile kernels: CTA pairs (cta_group::2) or single CTAs, loose / no lockstep
+        for key, values, reset in ((b"umma_fp4_pair", (0, 1), None), (b"umma_lockstep", (3, 0, 1), 1)):
             before = ctypes.c_int64(0)
             lib.btb_query(key, ctypes.byref(before))
             for v in values:
@@ -127,21 +125,12 @@ def test_kernel_variants_agree(capi, oracle):
                 _, got = gpu_matrix(capi, big, 1, 1)
                 assert (got == want_big).all(), (key, v)
             capi.check(lib.btb_set_option(key, reset if reset is not None else before.value))
-        capi.check(lib.btb_set_option(b"umma_fp4_general", 0))   # the CTA-pair variants are int8 kernels
-        capi.check(lib.btb_set_option(b"umma_dense_simplex", 0))
-        for variant in (0, 1, 2, 3):
-            capi.check(lib.btb_set_option(b"umma_cg2_variant", variant))
-            _, got = gpu_matrix(capi, general, 1, 2)
-            assert (got == want_g).all(), variant
-            _, got = gpu_matrix(capi, dense, 1, 2)
-            assert (got == want_d).all(), variant
     finally:
         capi.check(lib.btb_set_option(b"umma_dense_simplex", 2))
         capi.check(lib.btb_set_option(b"umma_fp4", 1))
         capi.check(lib.btb_set_option(b"umma_fp4_general", 1))
         capi.check(lib.btb_set_option(b"umma_tile_mode", 1))
-        capi.check(lib.btb_set_option(b"umma_cg2_variant", 0))
-        capi.check(lib.btb_set_option(b"umma_cta_group", 1))
+        capi.check(lib.btb_set_option(b"umma_fp4_pair", 1))
 
 
 def test_golden_c1_matrix(capi, oracle):
@@ -162,7 +151,7 @@ def test_tile_packed_rank_shares_assemble(capi, oracle, name, engine, cg):
     n, L = 1100, 700
     seqs = synth.snp_alignment(n, L, seed=8, heavy_n=0.1)
     if cg:
-        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+        capi.check(capi.lib().btb_set_option(b"umma_fp4_pair", 1 if cg == 2 else 0))
     plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
     plan.encode()
     shares, packed = [], []
@@ -188,7 +177,7 @@ def test_block_row_shares_cover_the_matrix(capi, oracle, name, engine, cg, n, L,
     if dense:
         seqs = np.where(np.isin(seqs, list(b"ACGT")), seqs, ord("A")).astype(np.uint8)
     if cg:
-        capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+        capi.check(capi.lib().btb_set_option(b"umma_fp4_pair", 1 if cg == 2 else 0))
     plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
     assert (plan.sigma == capi.SIGMA_DENSE4) == dense
     plan.encode()
@@ -219,7 +208,7 @@ def test_block_rows_without_mirror_and_arbitrary_ranges(capi, oracle):
     want = oracle.snp_dists_rows(seqs, threads=8)
     for _, engine, cg in ENGINES:
         if cg:
-            capi.check(capi.lib().btb_set_option(b"umma_cta_group", cg))
+            capi.check(capi.lib().btb_set_option(b"umma_fp4_pair", 1 if cg == 2 else 0))
         plan = device.DistancePlan(to_device(seqs), length=L, engine=engine)
         plan.encode()
         for lo, hi in [(0, 7), (2, 5), (6, 7), (3, 3)]:
