@@ -171,10 +171,11 @@ int64_t walk_record(const FileBytes &fb, const FastaRecord &r, uint8_t *out) {
         const void *nl = memchr(d + p, '\n', R - p);
         size_t e = nl ? size_t(static_cast<const uint8_t *>(nl) - d) : R;
         size_t n = e - p;
+        // one trailing CR per line is dropped (whole-string test, as the parser the tools share does).  It is not
+        // copied either: `out` may be a slot of exactly seq_len bytes next to another thread's slot.
+        if (len + int64_t(n) > 1 && d[e - 1] == '\r') --n;
         if (out) memcpy(out + len, d + p, n);
         len += int64_t(n);
-        // one trailing CR per line is dropped (whole-string test, as the parser the tools share does)
-        if (len > 1 && d[e - 1] == '\r') --len;
         p = e + 1;
     }
     return len;
