@@ -251,6 +251,28 @@ def e2e_single(lib, _capi, torch, seqs, plan, n, L, local, steps):
     e2e_s = (time.perf_counter() - t0) / steps
     info = {"call": "btb_dist_matrix_host (C-ABI level 2): pinned host alignment -> H2D -> encode -> distance kernels -> D2H band by band -> pinned host matrix",
             "h2d_bytes_per_step": int(n * L), "d2h_bytes_per_step": int(n * n * plan.elem)}
+    # the same call delivering every unique pair once (upper triangle only): half the D2H bytes.  A second figure,
+    # not the headline: `e2e` above is the full square snp-dists prints.
+    h_up = torch.zeros((n, ld), dtype=plan.out_dtype, pin_memory=True)
+
+    def call_upper():
+        _capi.check(lib.btb_dist_matrix_host_upper(ctypes.c_void_p(h_seqs.data_ptr()), n, L, h_seqs.stride(0), 0, 0,
+                                                   _capi.ENGINE_UMMA, local, 0, 1, ctypes.c_void_p(h_up.data_ptr()),
+                                                   plan.elem, ld), "btb_dist_matrix_host_upper")
+    call_upper()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call_upper()
+    torch.cuda.synchronize()
+    up_s = (time.perf_counter() - t0) / steps
+    import numpy as np
+    rows = slice(0, min(n, 2048))
+    same = bool((np.triu(h_up.numpy()[rows, :n]) == np.triu(h_out.numpy()[rows, :n])).all())
+    info["upper_triangle_only"] = {"call": "btb_dist_matrix_host_upper: cells (r, c >= r) only", "seconds_per_step": up_s,
+                                   "value": unique_pairs(n) / up_s, "unit": "pairs/s", "d2h_bytes_per_step": int(n * (n + 1) // 2 * plan.elem),
+                                   "equals_full_matrix_on_first_rows": same}
+    del h_up
     return e2e_s, info, h_seqs.numpy()[:, :L], h_out.numpy()[:, :n], (h_seqs, h_out)
 
 
@@ -287,6 +309,20 @@ def e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, l
                                                   ctypes.c_void_p(h_out.ctypes.data), plan.elem, n), "btb_dist_matrix_host_comm")
     call()
     torch.cuda.synchronize()
+    # what the box gives when every rank copies its share of the matrix to the host at the same time (plain
+    # cudaMemcpy from a device buffer into the shared page-locked matrix): the ceiling of the D2H phase
+    share = n * n * plan.elem // world
+    d_probe = torch.empty(share, dtype=torch.uint8, device=seqs.device)
+    h_probe = torch.from_numpy(h_out.reshape(-1).view(np.uint8)[rank * share:(rank + 1) * share])
+    torch.cuda.synchronize()
+    dist.barrier(group=host_pg)
+    tc = time.perf_counter()
+    h_probe.copy_(d_probe, non_blocking=True)
+    torch.cuda.synchronize()
+    copy_s = torch.tensor([time.perf_counter() - tc], dtype=torch.float64)
+    dist.all_reduce(copy_s, op=dist.ReduceOp.MAX, group=host_pg)
+    d2h_all = n * n * plan.elem / float(copy_s[0]) / 1e9
+    del d_probe, h_probe
     dist.barrier(group=host_pg)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -306,6 +342,7 @@ def e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, l
             "h2d_bytes_per_step": int(n * L), "d2h_bytes_per_step": int(n * n * plan.elem),
             "bytes_are": "summed over all ranks (each rank moves about 1/N of both)",
             "path": "sharded" if path.value == 1 else "replicated-upload fallback",
+            "plain_d2h_all_ranks_GBps": d2h_all,
             "rank0_phase_ms": {k: round(phases[i] * 1e3, 3) for i, k in enumerate(names)}}
 
     def cleanup():
@@ -381,15 +418,35 @@ def gpu_arm(args):
 
     seqs = make_alignment_cuda(n, L, device)                      # identical on every rank (operands are replicated)
     plan = dev.DistancePlan(seqs, length=L, engine=_capi.ENGINE_UMMA)
-    # The path shards by block rows of the matrix: each rank owns a contiguous range of 256-row blocks
-    # holding (nearly) equal numbers of upper-triangle tiles; no data-path collective.
-    row_lo, row_hi = dev.row_share(n, rank, world)
+    # The path shards by block rows of the matrix: each rank owns a contiguous range of 256-row blocks; no
+    # data-path collective.  A rank only encodes the rows its block rows meet (from its first row on), and the
+    # ranges are cut so that  tiles + encode share  is the same for every rank (btb_dist_row_share_weighted).
     T = dev.block_rows(n)
-    my_tiles = sum(T - i for i in range(row_lo, row_hi))
     out = plan.alloc_matrix()
+    encode_tiles = 0.0
+    if world > 1:
+        def _ms(fn, reps=3):
+            best = 1e30
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            return best
+        plan.encode()
+        probe_lo = max(0, T - 64) // 2 * 2
+        plan.compute_rows(out, probe_lo, T)
+        torch.cuda.synchronize()
+        t_enc = _ms(plan.encode)
+        t_tile = _ms(lambda: plan.compute_rows(out, probe_lo, T)) / max(1, sum(T - i for i in range(probe_lo, T)))
+        ratio = torch.tensor([t_enc / max(t_tile, 1e-9)], dtype=torch.float64, device=device)
+        dist.broadcast(ratio, src=0)                                 # every rank must cut the same ranges
+        encode_tiles = float(ratio[0])
+    row_lo, row_hi = dev.row_share_weighted(n, rank, world, encode_tiles) if world > 1 else (0, T)
+    enc_row0 = max(0, row_lo * 256 - 256)                            # the 240-column units of the first block row start up to 239 rows early
+    my_tiles = sum(T - i for i in range(row_lo, row_hi))
 
     def step():
-        plan.encode()
+        plan.encode(enc_row0, n)
         plan.compute_rows(out, row_lo, row_hi)
 
     def sync_all():
@@ -410,7 +467,7 @@ def gpu_arm(args):
     t_timed0 = time.perf_counter()
     ev[0].record()
     for s in range(args.steps):
-        plan.encode()
+        plan.encode(enc_row0, n)
         ev[2 * s + 1].record()
         plan.compute_rows(out, row_lo, row_hi)
         ev[2 * s + 2].record()
@@ -556,7 +613,8 @@ def gpu_arm(args):
         "details": {"engine": "tcgen05 %s, cta_group::%d" % ("kind::mxf4 (e2m1 0/1 operands)" if _query(lib, b"umma_fp4") else "kind::i8", 2 if pair else _query(lib, b"umma_cta_group")),
                     "options": os.environ.get("BTB_OPTIONS", ""), "tiles_total": multirank.tile_count(n), "tiles_this_rank": my_tiles,
                     "block_rows_this_rank": [row_lo, row_hi],
-                    "sharding": "contiguous 256-row blocks with equal upper-triangle tile counts per rank, no collective on the compute path",
+                    "sharding": "contiguous 256-row blocks per rank, cut so that tiles + operand encode (rows from the rank's first row on) are equal; "
+                                "no collective on the compute path", "encode_cost_in_tiles": encode_tiles, "rows_encoded_this_rank": [enc_row0, n],
                     "l2_policy": "operands (2.25 GB) and output (5 GB) exceed the 126 MB L2; no flush needed",
                     "timed_region": "operand encode + distance kernels per step, CUDA events on the launching stream, max over ranks"},
     }

@@ -31,6 +31,8 @@ SIGNATURES = {
                               c_int, c_int, c_int, p_i64, p_i64]),
     "btb_dist_matrix_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_vp, c_int, c_i64]),
+    "btb_dist_matrix_host_upper": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           c_vp, c_int, c_i64]),
     "btb_release_workspace": (c_int, []),
     "btb_comm_create": (c_int, [ctypes.c_char_p, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "btb_comm_destroy": (c_int, [c_vp]),
@@ -46,11 +48,13 @@ SIGNATURES = {
     "btb_dist_alphabet": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, ctypes.POINTER(c_int), c_vp]),
     "btb_dist_operand_bytes": (c_i64, [c_int, c_i64, c_i64, c_int]),
     "btb_dist_encode": (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
+    "btb_dist_encode_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_i64, c_i64, c_vp]),
     "btb_dist_tile_count": (c_i64, [c_i64]),
     "btb_dist_tile_coords": (c_int, [c_i64, c_i64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "btb_distance_tiles": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_int, c_vp]),
     "btb_dist_block_rows": (c_i64, [c_i64]),
     "btb_dist_row_share": (c_int, [c_i64, c_int, c_int, p_i64, p_i64]),
+    "btb_dist_row_share_weighted": (c_int, [c_i64, c_int, c_int, ctypes.c_double, p_i64, p_i64]),
     "btb_distance_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp]),
     "btb_format_csv_rows": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(ctypes.c_char_p),
                                     ctypes.c_char, c_int, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),

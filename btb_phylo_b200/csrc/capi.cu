@@ -252,6 +252,44 @@ extern "C" int btb_dist_row_share(int64_t n, int rank, int world, int64_t *lo, i
     return BTB_OK;
 }
 
+// The same with the cost of preparing the operands counted in: a rank whose block rows start at `lo` encodes
+// the rows from lo on (btb_dist_encode_rows), i.e. (T - lo) / T of what encoding all rows costs, `encode_tiles`
+// (in units of one tile of distance work).  Rank 0 reads every row, the last rank a third of them: contiguous
+// ranges whose  tiles + encode share  are (nearly) equal, found by bisection on the largest cost.
+extern "C" int btb_dist_row_share_weighted(int64_t n, int rank, int world, double encode_tiles, int64_t *lo, int64_t *hi) {
+    if (n <= 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi || encode_tiles < 0) return fail(BTB_EINVAL, "btb_dist_row_share_weighted: bad argument");
+    const int64_t T = tiles_per_dim(n);
+    auto cost = [&](int64_t a, int64_t b) -> double {     // block rows [a, b)
+        const double tiles = double(b - a) * double(T - a) - double(b - a) * double(b - a - 1) / 2.0;
+        return tiles + encode_tiles * double(T - a) / double(T);
+    };
+    std::vector<int64_t> bound(size_t(world) + 1, T);
+    auto fits = [&](double cap, std::vector<int64_t> *out) -> bool {
+        int64_t a = 0;
+        for (int r = 0; r < world; ++r) {
+            int64_t b = a;
+            while (b < T && cost(a, b + 1) <= cap) ++b;
+            if (b == a && a < T) return false;             // not even one block row fits
+            // ranks start on even block rows when there is room (512-row units of the CTA-pair kernel)
+            if ((b & 1) && b < T && T >= 4 * int64_t(world) && b - 1 > a) --b;
+            if (out) (*out)[size_t(r)] = a;
+            a = b;
+        }
+        if (out) (*out)[size_t(world)] = T;
+        return a >= T;
+    };
+    double lo_c = 0, hi_c = cost(0, T);
+    for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo_c + hi_c);
+        if (fits(mid, nullptr)) hi_c = mid; else lo_c = mid;
+    }
+    fits(hi_c, &bound);
+    bound[size_t(world)] = T;
+    *lo = bound[size_t(rank)];
+    *hi = rank + 1 == world ? T : bound[size_t(rank) + 1];
+    return BTB_OK;
+}
+
 extern "C" int btb_distance_rows(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
                                  int64_t row_block_lo, int64_t row_block_hi, void *d_out, int out_elem_bytes,
                                  int64_t out_ld, int mirror, void *stream) {
@@ -410,9 +448,9 @@ int streamed_matrix(Workspace &ws, const uint8_t *seqs, int64_t n, int64_t len, 
 }
 }  // namespace
 
-extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
-                                    int allchars, int keepcase, int engine, int device, int rank, int world,
-                                    void *out, int out_elem_bytes, int64_t out_ld) {
+static int dist_matrix_host_impl(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                                 int allchars, int keepcase, int engine, int device, int rank, int world,
+                                 void *out, int out_elem_bytes, int64_t out_ld, bool upper_only) {
     if (!seqs || !out || n <= 0 || len < 0 || row_stride < len || out_ld < n || world < 1 || rank < 0 || rank >= world)
         return fail(BTB_EINVAL, "btb_dist_matrix_host: bad argument");
     if (out_elem_bytes != 2 && out_elem_bytes != 4) return fail(BTB_EINVAL, "out_elem_bytes must be 2 or 4");
@@ -425,7 +463,7 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
     cudaStream_t st = ws.st;
     int rc = BTB_OK;
     g_host_stream_last = 0;
-    if (world == 1 && g_host_stream && !allchars && !keepcase && engine != BTB_ENGINE_POPC && len > 0 &&
+    if (world == 1 && g_host_stream && !upper_only && !allchars && !keepcase && engine != BTB_ENGINE_POPC && len > 0 &&
         umma_fp4_dense(BTB_SIGMA_DENSE4, len) && tiles_per_dim(n) >= 2 * kBand) {
         size_t free_b = 0, total_b = 0;
         const size_t need = size_t(btb_dist_operand_bytes(BTB_ENGINE_UMMA, n, len, BTB_SIGMA_DENSE4)) + size_t(n) * size_t((len + 15) / 16 * 16) +
@@ -471,12 +509,13 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         int64_t first = 0;
         for (int64_t r0 = 0; r0 < T; r0 += kBand) {
             const int64_t w = std::min<int64_t>(kBand, T - r0), cnt = band_tiles(T, r0, w);
-            L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, first, first + cnt, d_out, out_elem_bytes, d_ld, 0, 1, st));
+            L2_TRY(btb_distance_tiles(eng, d_ops, n, len, sigma, first, first + cnt, d_out, out_elem_bytes, d_ld, 0, upper_only ? 0 : 1, st));
             L2_CUDA(cudaEventRecord(ws.ev, st));
             L2_CUDA(cudaStreamWaitEvent(ws.st2, ws.ev, 0));
             const int64_t row0 = r0 * BTB_TILE, row1 = std::min<int64_t>(n, (r0 + w) * BTB_TILE);
-            L2_CUDA(cudaMemcpy2DAsync(static_cast<char *>(out) + size_t(row0 * out_ld) * eb, size_t(out_ld) * eb,
-                                      d_out + size_t(row0 * d_ld) * eb, size_t(d_ld) * eb, size_t(n) * eb,
+            const int64_t col0 = upper_only ? row0 : 0;                // upper triangle only: nothing left of the band's diagonal block
+            L2_CUDA(cudaMemcpy2DAsync(static_cast<char *>(out) + size_t(row0 * out_ld + col0) * eb, size_t(out_ld) * eb,
+                                      d_out + size_t(row0 * d_ld + col0) * eb, size_t(d_ld) * eb, size_t(n - col0) * eb,
                                       size_t(row1 - row0), cudaMemcpyDeviceToHost, ws.st2));
             first += cnt;
         }
@@ -486,7 +525,7 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         // back as two wide 2-D copies (the rows from their first column on, and the mirrored strip below)
         int64_t lo = 0, hi = 0;
         L2_TRY(btb_dist_row_share(n, rank, world, &lo, &hi));
-        L2_TRY(btb_distance_rows(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, 1, st));
+        L2_TRY(btb_distance_rows(eng, d_ops, n, len, sigma, lo, hi, d_out, out_elem_bytes, d_ld, upper_only ? 0 : 1, st));
         char *ho = static_cast<char *>(out);
         auto copy2d = [&](int64_t r0, int64_t r1, int64_t c0, int64_t c1) -> cudaError_t {
             if (r1 <= r0 || c1 <= c0) return cudaSuccess;
@@ -495,13 +534,25 @@ extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len,
         };
         const int64_t row0 = std::min<int64_t>(n, lo * BTB_TILE), row1 = std::min<int64_t>(n, hi * BTB_TILE);
         L2_CUDA(copy2d(row0, row1, row0, n));
-        L2_CUDA(copy2d(row1, n, row0, row1));
+        if (!upper_only) L2_CUDA(copy2d(row1, n, row0, row1));
     }
     L2_CUDA(cudaStreamSynchronize(st));
     cleanup();
     return BTB_OK;
 #undef L2_CUDA
 #undef L2_TRY
+}
+
+extern "C" int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                                    int allchars, int keepcase, int engine, int device, int rank, int world,
+                                    void *out, int out_elem_bytes, int64_t out_ld) {
+    return dist_matrix_host_impl(seqs, n, len, row_stride, allchars, keepcase, engine, device, rank, world, out, out_elem_bytes, out_ld, false);
+}
+
+extern "C" int btb_dist_matrix_host_upper(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                                          int allchars, int keepcase, int engine, int device, int rank, int world,
+                                          void *out, int out_elem_bytes, int64_t out_ld) {
+    return dist_matrix_host_impl(seqs, n, len, row_stride, allchars, keepcase, engine, device, rank, world, out, out_elem_bytes, out_ld, true);
 }
 
 // =============================================================================== level 1: snp-dists

@@ -686,6 +686,42 @@ extern "C" int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, in
     return -1;
 }
 
+// Operand rows [row0, row1) only, at their place in the operand of all n rows: a rank of a multi-GPU job whose
+// block rows start at row r never reads the rows before r - 256 (btb_distance_rows), so it need not encode them.
+// FP4 layouts; anything else encodes everything.
+extern "C" int btb_dist_encode_rows(int engine, const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                                    const uint8_t table[256], int sigma, void *d_operands, int64_t row0, int64_t row1,
+                                    void *stream_) {
+    if (n <= 0 || len < 0 || !d_operands || !table || !d_seqs || row0 < 0 || row1 > n || row0 > row1)
+        return fail(BTB_EINVAL, "btb_dist_encode_rows: bad argument");
+    if (engine != BTB_ENGINE_UMMA || !umma_use_fp4(sigma, len) || (row0 == 0 && row1 == n))
+        return btb_dist_encode(engine, d_seqs, n, len, row_stride, table, sigma, d_operands, stream_);
+    if (row0 == row1) return BTB_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t kb = umma_k_bytes(len, sigma), rows = row1 - row0;
+    uint8_t *A = static_cast<uint8_t *>(d_operands);
+    const uint8_t *seqs = d_seqs + row0 * row_stride;
+    const bool dense = sigma_dense(sigma), use_major = dense && g_umma_major_zero && n >= 64;
+    const int64_t padded = (len + 31) / 32 * 32;
+    uint8_t *d_small = nullptr;                          // table 256 | major (padded) | counts (len x 16)
+    const size_t counts_off = size_t(256 + padded + 255) & ~size_t(255);
+    BTB_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_small), counts_off + (use_major ? size_t(len) * 16 : 0) + 16, stream));
+    BTB_CUDA(cudaMemcpyAsync(d_small, table, 256, cudaMemcpyHostToDevice, stream));
+    uint8_t *d_major = nullptr;
+    if (use_major) {                                     // any choice of the zero-coded symbol per site is exact: these rows decide
+        d_major = d_small + 256;
+        uint32_t *d_counts = reinterpret_cast<uint32_t *>(d_small + counts_off);
+        BTB_CUDA(cudaMemsetAsync(d_major, 0, size_t(padded), stream));
+        BTB_TRY(dist_site_counts(seqs, rows, len, row_stride, d_small, d_counts, stream));
+        site_major_kernel<<<(unsigned)((len + 255) / 256), 256, 0, stream>>>(d_counts, len, d_major);
+    }
+    int32_t *rowsum = reinterpret_cast<int32_t *>(A + n * kb);
+    if (dense) BTB_CUDA(cudaMemsetAsync(rowsum + row0, 0, size_t(rows) * 4, stream));
+    BTB_TRY(dist_encode_fp4_rows(seqs, rows, len, row_stride, table, d_small, sigma, A + row0 * kb, dense ? rowsum + row0 : nullptr, d_major, stream));
+    BTB_CUDA(cudaFreeAsync(d_small, stream));
+    return BTB_OK;
+}
+
 extern "C" int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int64_t len,
                                int64_t row_stride, const uint8_t table[256], int sigma,
                                void *d_operands, void *stream_) {

@@ -45,6 +45,14 @@ def row_share(n, rank, world):
     return lo.value, hi.value
 
 
+def row_share_weighted(n, rank, world, encode_tiles):
+    """row_share with the operand encode counted in (btb_dist_row_share_weighted)."""
+    lo, hi = ctypes.c_int64(0), ctypes.c_int64(0)
+    _capi.check(_capi.lib().btb_dist_row_share_weighted(n, rank, world, float(encode_tiles), ctypes.byref(lo), ctypes.byref(hi)),
+                "btb_dist_row_share_weighted")
+    return lo.value, hi.value
+
+
 class DistancePlan:
     """Operands + output of the distance stage for one alignment resident in HBM.
 
@@ -74,10 +82,17 @@ class DistancePlan:
         self.elem = 2 if out_dtype == torch.uint16 else 4
         self.tiles = tile_count(self.n)
 
-    def encode(self):
-        _capi.check(self.lib.btb_dist_encode(self.engine, _ptr(self.seqs), self.n, self.len, self.row_stride,
-                                             self.table, self.sigma, _ptr(self.operands), _stream()),
-                    "btb_dist_encode")
+    def encode(self, row0=0, row1=None):
+        """All rows, or only the rows [row0, row1) (what a rank whose block rows start later needs)."""
+        row1 = self.n if row1 is None else row1
+        if row0 == 0 and row1 == self.n:
+            _capi.check(self.lib.btb_dist_encode(self.engine, _ptr(self.seqs), self.n, self.len, self.row_stride,
+                                                 self.table, self.sigma, _ptr(self.operands), _stream()),
+                        "btb_dist_encode")
+        else:
+            _capi.check(self.lib.btb_dist_encode_rows(self.engine, _ptr(self.seqs), self.n, self.len, self.row_stride,
+                                                      self.table, self.sigma, _ptr(self.operands), row0, row1, _stream()),
+                        "btb_dist_encode_rows")
 
     def alloc_matrix(self):
         ld = (self.n + 7) // 8 * 8
@@ -103,15 +118,15 @@ class DistancePlan:
 
 
 def distance_matrix_host(seqs, allchars=False, keepcase=False, engine=_capi.ENGINE_AUTO, device=0,
-                         rank=0, world=1, out=None, dtype=np.uint32):
-    """Level-2 call on numpy buffers: n x L uint8 -> n x n distances (btb_dist_matrix_host)."""
+                         rank=0, world=1, out=None, dtype=np.uint32, upper_only=False):
+    """Level-2 call on numpy buffers: n x L uint8 -> n x n distances (btb_dist_matrix_host; with
+    upper_only only the cells (r, c >= r) are written: btb_dist_matrix_host_upper)."""
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     n, L = seqs.shape
     if out is None:
         out = np.zeros((n, n), dtype=dtype)
     elem = out.dtype.itemsize
-    _capi.check(_capi.lib().btb_dist_matrix_host(seqs.ctypes.data, n, L, seqs.strides[0], int(allchars), int(keepcase),
-                                                 engine, device, rank, world, out.ctypes.data, elem,
-                                                 out.strides[0] // elem),
-                "btb_dist_matrix_host")
+    fn = _capi.lib().btb_dist_matrix_host_upper if upper_only else _capi.lib().btb_dist_matrix_host
+    _capi.check(fn(seqs.ctypes.data, n, L, seqs.strides[0], int(allchars), int(keepcase), engine, device, rank, world,
+                   out.ctypes.data, elem, out.strides[0] // elem), "btb_dist_matrix_host")
     return out

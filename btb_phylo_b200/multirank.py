@@ -67,6 +67,39 @@ def row_share(n, rank, world):
     return boundary(rank), boundary(rank + 1)
 
 
+def row_share_weighted(n, rank, world, encode_tiles):
+    """Same rule as btb_dist_row_share_weighted: contiguous block-row ranges whose  tiles + encode share  are
+    (nearly) equal, where a rank starting at block row lo pays encode_tiles * (T - lo) / T for its operands."""
+    T = tiles_per_dim(n)
+
+    def cost(a, b):
+        return float(b - a) * float(T - a) - float(b - a) * float(b - a - 1) / 2.0 + encode_tiles * float(T - a) / float(T)
+
+    def fits(cap):
+        a, bounds = 0, []
+        for _ in range(world):
+            b = a
+            while b < T and cost(a, b + 1) <= cap:
+                b += 1
+            if b == a and a < T:
+                return None
+            if b % 2 == 1 and b < T and T >= 4 * world and b - 1 > a:
+                b -= 1
+            bounds.append(a)
+            a = b
+        return bounds + [T] if a >= T else None
+
+    lo_c, hi_c = 0.0, cost(0, T)
+    for _ in range(60):
+        mid = 0.5 * (lo_c + hi_c)
+        if fits(mid) is not None:
+            hi_c = mid
+        else:
+            lo_c = mid
+    bounds = fits(hi_c)
+    return bounds[rank], (T if rank + 1 == world else bounds[rank + 1])
+
+
 def assemble_rows(n, shares, mats, out=None):
     """shares: list of block-row ranges (lo, hi); mats: per-rank n x n matrices in which the rank has
     written the cells (r, c >= r) of its rows and their mirrors.  Returns the merged matrix."""

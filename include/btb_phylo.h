@@ -128,6 +128,16 @@ int btb_dist_matrix_host(const uint8_t *seqs, int64_t n, int64_t len, int64_t ro
                          int rank, int world,
                          void *out, int out_elem_bytes, int64_t out_ld);
 
+/* The same, upper triangle only: the cells (r, c >= r) are written (every unique pair once, the diagonal
+ * zero), cells below the diagonal are left as they were or unspecified.  Half the device-to-host bytes --
+ * the call is bound by that copy -- for consumers that take a symmetric matrix as its upper triangle.
+ * (Measured: mirroring on the host instead, 16 threads transposing 256 x 256 tiles, is slower than copying
+ * both triangles over PCIe, so the full matrix of btb_dist_matrix_host is mirrored on the device.) */
+int btb_dist_matrix_host_upper(const uint8_t *seqs, int64_t n, int64_t len, int64_t row_stride,
+                               int allchars, int keepcase, int engine, int device,
+                               int rank, int world,
+                               void *out, int out_elem_bytes, int64_t out_ld);
+
 /* btb_dist_matrix_host keeps its device buffers between calls; this frees them. */
 int btb_release_workspace(void);
 
@@ -227,6 +237,12 @@ int64_t btb_dist_operand_bytes(int engine, int64_t n, int64_t len, int sigma);
 int btb_dist_encode(int engine, const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
                     const uint8_t table[256], int sigma, void *d_operands, void *stream);
 
+/* btb_dist_encode for the rows [row0, row1) only, written at their place in the operand of all n rows (the other
+ * rows of d_operands are left as they are).  FP4 operand layouts; other layouts encode all rows. */
+int btb_dist_encode_rows(int engine, const uint8_t *d_seqs, int64_t n, int64_t len, int64_t row_stride,
+                         const uint8_t table[256], int sigma, void *d_operands, int64_t row0, int64_t row1,
+                         void *stream);
+
 /* number of BTB_TILE x BTB_TILE tiles in the upper triangle (diagonal included) */
 int64_t btb_dist_tile_count(int64_t n);
 /* tile index -> (block row I, block column J), I <= J; the order is L2-friendly bands */
@@ -249,6 +265,11 @@ int btb_distance_tiles(int engine, const void *d_operands, int64_t n, int64_t le
  * cells as well (so the rows are complete once every earlier block row has been computed too). */
 int64_t btb_dist_block_rows(int64_t n);
 int btb_dist_row_share(int64_t n, int rank, int world, int64_t *row_block_lo, int64_t *row_block_hi);
+/* btb_dist_row_share with the operand encode counted in: rank r only has to encode the rows from its first block
+ * row on (btb_dist_encode_rows with row0 = max(0, lo * BTB_TILE - BTB_TILE)), which is (T - lo) / T of
+ * encode_tiles, the cost of encoding all rows in units of one tile of distance work.  Equalises tiles + encode. */
+int btb_dist_row_share_weighted(int64_t n, int rank, int world, double encode_tiles,
+                                int64_t *row_block_lo, int64_t *row_block_hi);
 int btb_distance_rows(int engine, const void *d_operands, int64_t n, int64_t len, int sigma,
                       int64_t row_block_lo, int64_t row_block_hi,
                       void *d_out, int out_elem_bytes, int64_t out_ld, int mirror, void *stream);

@@ -266,6 +266,49 @@ def test_level2_host_call(capi, oracle):
     assert (out == want).all()
 
 
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("world", [2, 3])
+def test_partial_encode_and_weighted_shares(capi, oracle, dense, world):
+    """A rank encodes only the rows from (one block before) its first block row on -- everything before stays
+    garbage -- and the block-row ranges are cut with the encode cost counted in: the assembled matrix is exact."""
+    from btb_phylo_b200 import device
+    n, L = 5000, 700
+    seqs = synth.snp_alignment(n, L, seed=61, heavy_n=0.0 if dense else 0.1)
+    want = oracle.snp_dists_rows(seqs, threads=8).astype(np.int64)
+    shares, mats = [], []
+    for rank in range(world):
+        lo, hi = device.row_share_weighted(n, rank, world, 40.0)
+        assert (lo, hi) == multirank.row_share_weighted(n, rank, world, 40.0)
+        plan = device.DistancePlan(to_device(seqs), length=L, engine=capi.ENGINE_UMMA)
+        assert (plan.sigma == capi.SIGMA_DENSE4) == dense
+        plan.operands.fill_(0xA7)                                     # rows that are not encoded hold garbage
+        plan.encode(max(0, lo * 256 - 256), n)
+        out = plan.alloc_matrix()
+        plan.compute_rows(out, lo, hi)
+        torch.cuda.synchronize()
+        shares.append((lo, hi))
+        mats.append(out[:, :n].cpu().numpy().astype(np.int64))
+    assert shares[0][0] == 0 and shares[-1][1] == multirank.tiles_per_dim(n)
+    assert (multirank.assemble_rows(n, shares, mats) == want).all()
+
+
+def test_level2_upper_triangle_only(capi, oracle):
+    """btb_dist_matrix_host_upper: every cell on or above the diagonal, nothing below it is touched --
+    one GPU (band by band) and the two shares of a 2-rank job, dense and general alphabets, both engines."""
+    from btb_phylo_b200 import device
+    for seqs in (synth.snp_alignment(4700, 900, seed=52), synth.snp_alignment(2300, 1300, seed=53, heavy_n=0.1)):
+        n = seqs.shape[0]
+        want = np.triu(oracle.snp_dists_rows(seqs, threads=8))
+        for engine in (capi.ENGINE_UMMA, capi.ENGINE_POPC):
+            out = np.full((n, n), 0xFFFF, dtype=np.uint16)
+            device.distance_matrix_host(seqs, engine=engine, out=out, upper_only=True)
+            assert (np.triu(out) == want).all() and (np.tril(out, -1 * 256 * 8) == np.tril(np.full((n, n), 0xFFFF, np.uint16), -1 * 256 * 8)).all()
+        out = np.zeros((n, n), dtype=np.uint32)
+        device.distance_matrix_host(seqs, rank=0, world=2, out=out, upper_only=True)
+        device.distance_matrix_host(seqs, rank=1, world=2, out=out, upper_only=True)
+        assert (np.triu(out) == want).all()
+
+
 def test_level2_streamed_path(capi, oracle):
     """n >= 16 block rows, default mode, dense input: the level-2 call uploads / computes / downloads
     band by band in reverse order; a non-dense band sends the call down the general path.  Same

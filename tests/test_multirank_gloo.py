@@ -65,7 +65,7 @@ def test_two_rank_tile_sharding_assembles_full_matrix():
     assert ret["equal"] and ret["max_ms"] == 11.0 and ret["tiles"] == multirank.tile_count(n)
 
 
-def _row_worker(rank, world, port, n, L, ret):
+def _row_worker(rank, world, port, n, L, ret, encode_tiles=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -73,8 +73,12 @@ def _row_worker(rank, world, port, n, L, ret):
     from btb_phylo_b200 import device, multirank, synth
     from oracle import oracle
     seqs = synth.snp_alignment(n, L, seed=12, heavy_n=0.05)
-    lo, hi = device.row_share(n, rank, world)                        # C-ABI: btb_dist_row_share (host only)
-    assert (lo, hi) == multirank.row_share(n, rank, world)
+    if encode_tiles is None:
+        lo, hi = device.row_share(n, rank, world)                    # C-ABI: btb_dist_row_share (host only)
+        assert (lo, hi) == multirank.row_share(n, rank, world)
+    else:                                                            # shares with the operand encode counted in
+        lo, hi = device.row_share_weighted(n, rank, world, encode_tiles)
+        assert (lo, hi) == multirank.row_share_weighted(n, rank, world, encode_tiles)
     full = oracle.snp_dists_rows(seqs, threads=2)
     r0, r1 = min(n, lo * 256), min(n, hi * 256)
     mine = np.zeros((n, n), dtype=np.uint32)                         # stands in for btb_distance_rows(mirror=1)
@@ -95,3 +99,31 @@ def test_two_rank_block_row_sharding_assembles_full_matrix():
     ret = mgr.dict()
     mp.spawn(_row_worker, args=(world, _free_port(), n, L, ret), nprocs=world, join=True)
     assert ret["equal"]
+
+
+def test_two_rank_weighted_block_rows_assemble_full_matrix():
+    n, L, world = 2300, 60, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_row_worker, args=(world, _free_port(), n, L, ret, 12.5), nprocs=world, join=True)
+    assert ret["equal"]
+
+
+@pytest.mark.parametrize("n", [300, 6400, 50000, 100000])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("encode_tiles", [0.0, 40.0, 675.0, 1e5])
+def test_weighted_row_shares_partition_the_block_rows(n, world, encode_tiles):
+    """btb_dist_row_share_weighted (C) == multirank.row_share_weighted (numpy mirror); the ranges are contiguous,
+    cover every block row once, and the costliest rank is no worse than with the unweighted rule."""
+    sys.path.insert(0, ROOT)
+    from btb_phylo_b200 import device, multirank
+    T = multirank.tiles_per_dim(n)
+    shares = [device.row_share_weighted(n, r, world, encode_tiles) for r in range(world)]
+    assert shares == [multirank.row_share_weighted(n, r, world, encode_tiles) for r in range(world)]
+    assert shares[0][0] == 0 and shares[-1][1] == T and all(shares[r][1] == shares[r + 1][0] for r in range(world - 1))
+
+    def cost(a, b):
+        return sum(T - i for i in range(a, b)) + encode_tiles * (T - a) / T
+    plain = [multirank.row_share(n, r, world) for r in range(world)]
+    if T >= 4 * world:
+        assert max(cost(a, b) for a, b in shares) <= max(cost(a, b) for a, b in plain) + (T + 1)    # within one block row of work
