@@ -441,8 +441,12 @@ def gpu_arm(args):
         ratio = torch.tensor([t_enc / max(t_tile, 1e-9)], dtype=torch.float64, device=device)
         dist.broadcast(ratio, src=0)                                 # every rank must cut the same ranges
         encode_tiles = float(ratio[0])
-    row_lo, row_hi = dev.row_share_weighted(n, rank, world, encode_tiles) if world > 1 else (0, T)
-    enc_row0 = max(0, row_lo * 256 - 256)                            # the 240-column units of the first block row start up to 239 rows early
+    if os.environ.get("BTB_BENCH_SHARE") == "plain":                 # (diagnosis) equal tile counts, every rank encodes every row
+        row_lo, row_hi = dev.row_share(n, rank, world)
+        enc_row0 = 0
+    else:
+        row_lo, row_hi = dev.row_share_weighted(n, rank, world, encode_tiles) if world > 1 else (0, T)
+        enc_row0 = max(0, row_lo * 256 - 256)                        # the 240-column units of the first block row start up to 239 rows early
     my_tiles = sum(T - i for i in range(row_lo, row_hi))
 
     def step():
@@ -475,6 +479,10 @@ def gpu_arm(args):
     clocks = sampler.stop(t_timed0, time.perf_counter())
     total_ms = ev[0].elapsed_time(ev[2 * args.steps])
     kern_ms = [ev[2 * s + 1].elapsed_time(ev[2 * s + 2]) for s in range(args.steps)]
+    if os.environ.get("BTB_BENCH_VERBOSE"):
+        enc_ms = [ev[2 * s].elapsed_time(ev[2 * s + 1]) for s in range(args.steps)]
+        sys.stderr.write("[bench] rank %d block rows [%d, %d) tiles %d: encode %.3f ms, kernel %.3f ms, step %.3f ms\n"
+                         % (rank, row_lo, row_hi, my_tiles, statistics.mean(enc_ms), statistics.mean(kern_ms), total_ms / args.steps))
     t = torch.tensor([total_ms, statistics.mean(kern_ms)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
