@@ -56,12 +56,17 @@ int open_output_temp(const char *final_path, std::string &tmp_path, int *fd) {
 }
 
 int commit_output(const std::string &tmp_path, const char *final_path, bool unlink_first) {
+    // The file that is being replaced stays open across the rename and is closed by a detached thread: giving
+    // back the pages of a 12 GB snps.csv takes half a second (tmpfs and ext4 alike) and nobody has to wait for it.
+    const int old_fd = open(final_path, O_RDONLY | O_CLOEXEC);
     if (unlink_first) unlink(final_path);
     if (rename(tmp_path.c_str(), final_path) != 0) {
         const int e = errno;
+        if (old_fd >= 0) close(old_fd);
         unlink(tmp_path.c_str());
         return fail(BTB_EIO, "cannot rename to '%s': %s", final_path, strerror(e));
     }
+    if (old_fd >= 0) std::thread([old_fd] { close(old_fd); }).detach();
     return BTB_OK;
 }
 

@@ -3,10 +3,13 @@
 // per-base decision is taken by the kernels in extract.cu.
 //
 // Reference call site: btbphylo/phylogeny.py:133  `snp-sites <multi_fasta> -c -o <snps.fas>`.
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <chrono>
 #include <cstring>
 #include <functional>
@@ -423,36 +426,75 @@ int extract_pipeline(const ByteSource &src, std::vector<FastaRecord> &recs, cons
     if (n_snps) *n_snps = L;
     if (L == 0) return no_snps();
 
-    // phase 3: gather the kept columns of every sample into one pinned host matrix
+    // phase 3 + write: every record (">name\n" + L bases + "\n", one line per sequence) has its place in the
+    // file before anything is copied: each device compacts its samples, sends them to the host in chunks
+    // through the pinned staging buffers the ingest already owns (no n x L pinned matrix is allocated:
+    // page-locking 0.7 GB costs more than the whole stage), and its host threads put the rows, with their
+    // headers, straight where they belong -- into a mapping of the output file on tmpfs, else into one image
+    // in memory that a single write() pushes out.
     const int64_t ld = (L + 15) / 16 * 16;
-    PinnedBuf h_rows;
-    BTB_TRY(h_rows.alloc(size_t(n * ld)));
-    BTB_TRY(for_each_device([&](ExtractCtx &c) -> int {
+    std::vector<size_t> rec_at(size_t(n) + 1, 0);
+    for (int64_t r = 0; r < n; ++r) rec_at[size_t(r) + 1] = rec_at[size_t(r)] + recs[size_t(r)].name.size() + 2 + size_t(L) + 1;
+    const size_t total = rec_at[size_t(n)];
+    std::string tmp_path;
+    int tfd = -1;
+    BTB_TRY(open_output_temp(out_fasta, tmp_path, &tfd));
+    char *image = nullptr;
+    bool mapped = false;
+    if (on_memory_fs(out_fasta) && ftruncate(tfd, off_t(total)) == 0) {
+        if (fallocate(tfd, 0, 0, off_t(total)) != 0) { /* sparse is fine too */ }
+        void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, tfd, 0);
+        if (m != MAP_FAILED) { image = static_cast<char *>(m); mapped = true; }
+    }
+    if (!image) image = static_cast<char *>(malloc(std::max<size_t>(total, 1)));
+    auto drop_image = [&]() { if (mapped) munmap(image, total); else free(image); image = nullptr; };
+    if (!image) { close(tfd); discard_output(tmp_path); return fail(BTB_ENOMEM, "out of host memory"); }
+    int rc = for_each_device([&](ExtractCtx &c) -> int {
         if (c.s1 <= c.s0) return BTB_OK;
         BTB_TRY(require_device(c.dev));
         BTB_TRY(c.snps.alloc(size_t(c.nloc * ld)));
         BTB_TRY(btb_compact_columns(c.planes.as<uint32_t>(), 0, c.nloc, c.nloc, G, c.idx.as<uint32_t>(), L, c.snps.as<uint8_t>(), ld, c.st.s));
-        BTB_CUDA(cudaMemcpyAsync(h_rows.as<uint8_t>() + c.s0 * ld, c.snps.p, size_t(c.nloc * ld), cudaMemcpyDeviceToHost, c.st.s));
-        BTB_CUDA(cudaStreamSynchronize(c.st.s));
+        const int64_t chunk_rows = std::max<int64_t>(1, int64_t(c.chunk_cap) / ld);
+        auto fetch = [&](int64_t r0, int b) -> cudaError_t {         // rows [r0, r0 + chunk_rows) of this device -> staging buffer b
+            const int64_t rows = std::min(chunk_rows, c.nloc - r0);
+            cudaError_t e = cudaMemcpyAsync(c.h_text[b].p, c.snps.as<uint8_t>() + r0 * ld, size_t(rows * ld), cudaMemcpyDeviceToHost, c.st.s);
+            return e != cudaSuccess ? e : cudaEventRecord(c.done[b], c.st.s);
+        };
+        BTB_CUDA(fetch(0, 0));
+        int b = 0;
+        for (int64_t r0 = 0; r0 < c.nloc; r0 += chunk_rows, b ^= 1) {
+            const int64_t rows = std::min(chunk_rows, c.nloc - r0);
+            BTB_CUDA(cudaEventSynchronize(c.done[b]));
+            if (r0 + chunk_rows < c.nloc) BTB_CUDA(fetch(r0 + chunk_rows, b ^ 1));     // the next chunk travels while this one is placed
+            const char *src = c.h_text[b].as<char>();
+            parallel_for(rows, c.threads, [&](int64_t lo, int64_t hi) {
+                for (int64_t k = lo; k < hi; ++k) {
+                    const int64_t r = c.s0 + r0 + k;
+                    const std::string &nm = recs[size_t(r)].name;
+                    char *q = image + rec_at[size_t(r)];
+                    *q++ = '>';
+                    memcpy(q, nm.data(), nm.size());
+                    q += nm.size();
+                    *q++ = '\n';
+                    memcpy(q, src + k * ld, size_t(L));
+                    q[L] = '\n';
+                }
+            });
+        }
         return BTB_OK;
-    }));
-    timer.mark("k3 compact + D2H");
-
-    // ---- write: >name\n + L bases + \n per sample, one line per sequence --------------------------
-    std::string tmp_path;
-    int tfd = -1;
-    BTB_TRY(open_output_temp(out_fasta, tmp_path, &tfd));
-    FILE *fo = fdopen(tfd, "wb");
-    if (!fo) { close(tfd); discard_output(tmp_path); return fail(BTB_EIO, "cannot open '%s' for writing", tmp_path.c_str()); }
-    setvbuf(fo, nullptr, _IOFBF, 1 << 22);
-    int rc = BTB_OK;
-    for (int64_t r = 0; r < n && rc == BTB_OK; ++r) {
-        const std::string &nm = recs[size_t(r)].name;
-        if (fputc('>', fo) == EOF || fwrite(nm.data(), 1, nm.size(), fo) != nm.size() || fputc('\n', fo) == EOF ||
-            fwrite(h_rows.as<char>() + r * ld, 1, size_t(L), fo) != size_t(L) || fputc('\n', fo) == EOF)
-            rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str());
+    });
+    timer.mark("k3 compact + D2H + records placed");
+    if (rc == BTB_OK && !mapped) {
+        size_t off = 0;
+        while (off < total) {
+            const ssize_t k = write(tfd, image + off, total - off);
+            if (k < 0 && errno == EINTR) continue;
+            if (k <= 0) { rc = fail(BTB_EIO, "write to '%s' failed", tmp_path.c_str()); break; }
+            off += size_t(k);
+        }
     }
-    if (fclose(fo) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
+    drop_image();
+    if (close(tfd) != 0 && rc == BTB_OK) rc = fail(BTB_EIO, "closing '%s' failed", tmp_path.c_str());
     timer.mark("write snps.fas");
     if (rc != BTB_OK) { discard_output(tmp_path); return rc; }
     return commit_output(tmp_path, out_fasta, g_replace_unlink_first != 0);
