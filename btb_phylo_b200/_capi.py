@@ -27,6 +27,7 @@ SIGNATURES = {
     "btb_snp_sites": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int, p_i64, p_i64, p_i64]),
     "btb_snp_sites_files": (c_int, [ctypes.POINTER(ctypes.c_char_p), c_i64, ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int,
                                     p_i64, p_i64, p_i64]),
+    "btb_fasta_frame_files": (c_int, [ctypes.POINTER(ctypes.c_char_p), c_i64, p_i64, c_i64, ctypes.c_char_p, ctypes.c_size_t, p_i64]),
     "btb_snp_dists": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_int, c_int, c_int, ctypes.c_char, c_int, c_int,
                               c_int, c_int, c_int, p_i64, p_i64]),
     "btb_dist_matrix_host": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -569,6 +569,41 @@ extern "C" int btb_snp_sites(const char *in_fasta, const char *out_fasta, int pu
     return btb_snp_sites_files(&in_fasta, 1, in_fasta, out_fasta, pure_mode, n_gpus, host_threads, n_samples, genome_len, n_snps);
 }
 
+// Framing of a list of FASTA files taken as if concatenated, by prediction (host_io.h): for callers that stage the
+// record bytes themselves (btb_phylo_b200/plane_store.py).  out[6 r + 0..5] = file index, offset of the first
+// sequence byte in that file, bytes of the sequence region, bases, bases per line (0 = one line), terminator bytes;
+// names = the record names joined by '\n'.  *n_records = -1 when the files are not predictable (gzip, FASTQ, mixed
+// or irregular layouts): the caller then has to go through btb_snp_sites_files, which parses anything.
+extern "C" int btb_fasta_frame_files(const char *const *in_fastas, int64_t n_files, int64_t *out, int64_t cap_records,
+                                     char *names, size_t names_cap, int64_t *n_records) {
+    if (!in_fastas || n_files <= 0 || !n_records) return fail(BTB_EINVAL, "btb_fasta_frame_files: bad argument");
+    *n_records = -1;
+    std::vector<SourceFile> files;
+    BTB_TRY(open_sources(in_fastas, n_files, files));
+    std::vector<FastaRecord> recs;
+    bool fast = false;
+    BTB_TRY(frame_predicted(files, recs, &fast));
+    if (!fast) return BTB_OK;
+    size_t need = 1;
+    for (auto &r : recs) need += r.name.size() + 1;
+    if (int64_t(recs.size()) > cap_records || (names && need > names_cap) || !out)
+        return fail(BTB_EINVAL, "btb_fasta_frame_files: %zu records / %zu name bytes do not fit the buffers", recs.size(), need);
+    char *p = names;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const FastaRecord &r = recs[i];
+        int64_t *o = out + 6 * int64_t(i);
+        o[0] = r.file; o[1] = int64_t(r.seq_off); o[2] = int64_t(r.raw_len); o[3] = r.seq_len; o[4] = r.line_w; o[5] = r.eol;
+        if (names) {
+            if (i) *p++ = '\n';
+            memcpy(p, r.name.data(), r.name.size());
+            p += r.name.size();
+        }
+    }
+    if (names) *p = 0;
+    *n_records = int64_t(recs.size());
+    return BTB_OK;
+}
+
 namespace btb {
 void set_ingest_predict(int v) { g_ingest_predict = v ? 1 : 0; }
 int get_ingest_predict() { return g_ingest_predict; }

@@ -53,7 +53,7 @@ def _raise_like_run(cmd, err):
           *****""" % (cmd, 1, err))
 
 
-def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None):
+def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None, plane_store=None):
     """Run the snp-sites stage on consensus files (reference: phylogeny.py:128-141).
 
     Writes `snp_sites_outpath` (one unwrapped record per sample) and returns
@@ -64,6 +64,11 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None):
     `multi_fasta_path` may also be a list / tuple of per-sample consensus FASTA paths: they are
     taken as if concatenated in that order -- the file build_multi_fasta (phylogeny.py:48-88) would
     have written -- without writing or re-reading it.
+
+    `plane_store` (a directory; only with a list of per-sample files) makes the call incremental
+    (the weekly run): the bit-planes of every file are kept there, keyed by path,
+    size and modification time, and a later call reads the text of new or changed files only --
+    see plane_store.py.  Same snps.fas, byte for byte.
     """
     n = ctypes.c_int64(0)
     g = ctypes.c_int64(0)
@@ -75,6 +80,18 @@ def snp_sites(snp_sites_outpath, multi_fasta_path, threads=None):
             return os.path.getsize(path)
         except OSError:
             return 0                                       # the library reports the unreadable file
+    if plane_store and isinstance(multi_fasta_path, (list, tuple)) and len(multi_fasta_path) > 0:
+        from . import plane_store as _store
+        try:
+            _, _, n_snps, _ = _store.snp_sites_cached(_capi.lib(), snp_sites_outpath, [os.fspath(x) for x in multi_fasta_path],
+                                                      threads, os.fspath(plane_store))
+        except _store.NotPredictable:
+            n_snps = None                                  # inputs that need the exact parser: the plain path below
+        if n_snps is not None:
+            if n_snps == 0:
+                _raise_like_run("snp-sites <%d consensus files> -c -o %s" % (len(multi_fasta_path), snp_sites_outpath),
+                                "Warning: No SNPs were detected so there is nothing to output.")
+            return {"number_of_snps": n_snps}
     if isinstance(multi_fasta_path, (list, tuple)):
         paths = [os.fsencode(x) for x in multi_fasta_path]
         shown = "<%d consensus files>" % len(paths)

@@ -105,6 +105,15 @@ int btb_snp_sites_files(const char *const *in_fastas, int64_t n_files, const cha
                         const char *out_fasta, int pure_mode, int n_gpus, int host_threads,
                         int64_t *n_samples, int64_t *genome_len, int64_t *n_snps);
 
+/* Framing of a list of FASTA files taken as if concatenated, by prediction (equal-layout records: what consensus
+ * files are), for callers that stage the record bytes themselves -- the plane store of
+ * btb_phylo_b200/plane_store.py.  out[6 r + 0..5] = file index, offset of the first sequence byte
+ * in that file, bytes of the sequence region, bases, bases per line (0 = one line), terminator bytes; names = the
+ * record names joined by '\n'.  *n_records = -1 when the files are not predictable (gzip, FASTQ, mixed or
+ * irregular layouts): go through btb_snp_sites_files then, which parses anything. */
+int btb_fasta_frame_files(const char *const *in_fastas, int64_t n_files, int64_t *out, int64_t cap_records,
+                          char *names, size_t names_cap, int64_t *n_records);
+
 /* snp-dists [-a] [-k] [-m] [-c] [-b] [-q] -j T <in_fasta> > <out_path>   (phylogeny.py:149).
  * sep is ',' for -c else '\t'; corner = 0 is -b; the three banner lines go to stderr unless
  * quiet.  The file holds the full square, byte-identical with snp-dists 0.8.2. */

@@ -1,0 +1,94 @@
+"""GPU (-m gpu): the incremental snp-sites stage (btb_phylo_b200/plane_store.py).  With a plane
+store the call reads the text of new or changed consensus files only and takes the bit-planes of all others
+from the store; snps.fas must be what the uncached call -- and the oracle -- write, byte for byte."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from btb_phylo_b200 import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+@pytest.fixture
+def ph(capi):
+    from btb_phylo_b200 import phylogeny
+    return phylogeny
+
+
+def write_samples(tmp_path, names, aln, wrap=60):
+    paths = []
+    for nm, row in zip(names, aln):
+        p = tmp_path / (nm + ".fas")
+        p.write_bytes(synth.fasta_bytes([nm], row[None, :], wrap=wrap))
+        paths.append(str(p))
+    return paths
+
+
+def oracle_snps(oracle, tmp_path, paths):
+    mf = tmp_path / "multi.fas"
+    with open(mf, "wb") as out:
+        for p in paths:
+            out.write(open(p, "rb").read())
+    o = tmp_path / "oracle.fas"
+    assert oracle.run_snp_sites(str(mf), str(o)).returncode == 0
+    return o.read_bytes()
+
+
+def test_weekly_growth_same_bytes_as_the_uncached_call(ph, oracle, tmp_path):
+    n, G = 60, 123457
+    names = synth.sample_names(n)
+    aln = synth.genome_alignment(n, G, 1500, seed=77, n_frac=0.02)
+    paths = write_samples(tmp_path, names, aln)
+    store = tmp_path / "store"
+    out = tmp_path / "snps.fas"
+    # week 1: 40 samples, empty store
+    meta = ph.snp_sites(str(out), paths[:40], plane_store=str(store))
+    want = oracle_snps(oracle, tmp_path, paths[:40])
+    assert out.read_bytes() == want and meta["number_of_snps"] == len(want.split(b"\n")[1])
+    assert len(os.listdir(store)) == 40
+    # week 2: 20 more samples -- 40 come from the store.  The new samples change the kept-column set.
+    before = {f: os.stat(store / f).st_mtime_ns for f in os.listdir(store)}
+    meta = ph.snp_sites(str(out), paths, plane_store=str(store))
+    want = oracle_snps(oracle, tmp_path, paths)
+    assert out.read_bytes() == want
+    assert len(os.listdir(store)) == 60 and all(os.stat(store / f).st_mtime_ns == t for f, t in before.items())
+    plain = tmp_path / "plain.fas"
+    ph.snp_sites(str(plain), paths)
+    assert plain.read_bytes() == want
+    # a sample is re-sequenced: its file changes (size or mtime) and is read again; another order of the files
+    aln[7, 1000:1100] = ord("N")
+    time.sleep(0.01)
+    open(paths[7], "wb").write(synth.fasta_bytes([names[7]], aln[7][None, :], wrap=60))
+    order = list(reversed(range(n)))
+    meta = ph.snp_sites(str(out), [paths[i] for i in order], plane_store=str(store))
+    assert out.read_bytes() == oracle_snps(oracle, tmp_path, [paths[i] for i in order])
+    # everything from the store
+    meta2 = ph.snp_sites(str(out), [paths[i] for i in order], plane_store=str(store))
+    assert meta2 == meta and out.read_bytes() == oracle_snps(oracle, tmp_path, [paths[i] for i in order])
+
+
+def test_store_is_ignored_for_inputs_that_need_the_exact_parser(ph, oracle, tmp_path):
+    n, G = 12, 5003
+    names = synth.sample_names(n)
+    aln = synth.genome_alignment(n, G, 300, seed=78, n_frac=0.0)
+    paths = write_samples(tmp_path, names, aln)
+    # one file with two wrap widths inside its record (irregular) and one with two records
+    open(paths[3], "wb").write(b">" + names[3].encode() + b"\n" + aln[3][:100].tobytes() + b"\n" + aln[3][100:].tobytes() + b"\n")
+    both = synth.fasta_bytes(names[5:7], aln[5:7], wrap=60)
+    open(paths[5], "wb").write(both)
+    files = paths[:6] + paths[7:]
+    out = tmp_path / "snps.fas"
+    ph.snp_sites(str(out), files, plane_store=str(tmp_path / "store"))
+    assert out.read_bytes() == oracle_snps(oracle, tmp_path, files)
+
+
+def test_no_snps_raises_like_the_tool(ph, tmp_path):
+    names = synth.sample_names(3)
+    aln = np.repeat(np.frombuffer(b"ACGT" * 50, dtype=np.uint8)[None, :], 3, axis=0)
+    paths = write_samples(tmp_path, names, aln, wrap=0)
+    with pytest.raises(Exception, match="No SNPs were detected"):
+        ph.snp_sites(str(tmp_path / "snps.fas"), paths, plane_store=str(tmp_path / "store"))
+    assert not (tmp_path / "snps.fas").exists()
