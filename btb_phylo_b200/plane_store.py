@@ -209,9 +209,24 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
 
     # ---- the new samples' planes go to the store (also when no SNP was found: the planes are what they are) -------
     if nU:
-        for k0 in range(0, nU, max(1, CHUNK_BYTES // (3 * words * 4))):
-            k1 = min(nU, k0 + max(1, CHUNK_BYTES // (3 * words * 4)))
-            host = [planes[p, k0:k1].cpu().numpy() for p in range(3)]
+        per_chunk = max(1, need // blob_bytes)
+        pinned = [s_[:per_chunk * blob_bytes].view(torch.int32).view(3, per_chunk, words) for s_ in staging]
+        torch.cuda.synchronize()
+        chunks = [(k0, min(nU, k0 + per_chunk)) for k0 in range(0, nU, per_chunk)]
+        done = [None, None]
+
+        def fetch(c):                                                 # device -> page-locked chunk c & 1, asynchronously
+            k0, k1 = chunks[c]
+            for p in range(3):
+                pinned[c & 1][p, :k1 - k0].copy_(planes[p, k0:k1], non_blocking=True)
+            done[c & 1] = torch.cuda.Event()
+            done[c & 1].record()
+        fetch(0)
+        for c, (k0, k1) in enumerate(chunks):
+            done[c & 1].synchronize()
+            if c + 1 < len(chunks):
+                fetch(c + 1)                                          # (its buffer was written out one iteration ago)
+            host = pinned[c & 1].numpy()
 
             def save_one(k, host=host, k0=k0):
                 i = new_idx[k]
@@ -222,7 +237,7 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
                     f.write(HEADER.pack(MAGIC, G, words, stats[i].st_size, stats[i].st_mtime_ns, len(nm)))
                     f.write(nm)
                     for p in range(3):
-                        f.write(host[p][k - k0].tobytes())
+                        f.write(memoryview(host[p, k - k0]).cast("B"))
                 os.replace(part, blob)
             list(pool.map(save_one, range(k0, k1)))
     pool.shutdown()
