@@ -28,6 +28,7 @@ constexpr int kMinLineW = 32;                            // shorter lines go thr
 // is given.  250 x WPT words = 8000 x WPT columns: with 60..80-column lines the CTA's text span is just under
 // 2 x WPT x 4096 bytes, so the 256 threads classify it in 2 x WPT rounds of 16-byte chunks with next to no idle lanes.
 constexpr int kPackThreadsB = 250;                       // threads that own plane words
+constexpr uint32_t kNone = 0xFFFFFFFFu;
 template <int WPT> struct PackCfg {
     static constexpr int kWords = kPackThreadsB * WPT;
     static constexpr int kCols = kWords * 32;
@@ -156,12 +157,11 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     const uint32_t G32 = uint32_t(G), cb = uint32_t(c0);          // genome lengths fit 32 bits (the tools use int)
     const int64_t per = (n_chunk + gridDim.y - 1) / gridDim.y;
     const int64_t s_lo = int64_t(blockIdx.y) * per, s_hi = s_lo + per < n_chunk ? s_lo + per : n_chunk;
-    uint32_t *const plane0 = planes + (0 * n_total + first) * words + w;      // this thread's words of sample `first`, plane 0
-    const int64_t plane_stride = n_total * words;
-    auto store_words = [&](int64_t i, const uint32_t (&x0)[WPT], const uint32_t (&x1)[WPT], const uint32_t (&xv)[WPT]) {
-        uint32_t *p0 = plane0 + i * words;
-        uint32_t *p1 = p0 + plane_stride;
-        uint32_t *pv = p1 + plane_stride;
+    // this thread's words of the CTA's first sample in the three planes; the pointers move on by one sample per iteration
+    uint32_t *p0 = planes + (first + s_lo) * words + w;
+    uint32_t *p1 = p0 + n_total * words;
+    uint32_t *pv = p1 + n_total * words;
+    auto store_words = [&](const uint32_t (&x0)[WPT], const uint32_t (&x1)[WPT], const uint32_t (&xv)[WPT]) {
         if constexpr (WPT == 4) {
             *reinterpret_cast<uint4 *>(p0) = make_uint4(x0[0], x0[1], x0[2], x0[3]);
             *reinterpret_cast<uint4 *>(p1) = make_uint4(x1[0], x1[1], x1[2], x1[3]);
@@ -174,10 +174,11 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             *p0 = x0[0]; *p1 = x1[0]; *pv = xv[0];
         }
     };
+    auto next_sample = [&]() { p0 += words; p1 += words; pv += words; };
     const uint32_t zeros[WPT] = {};
     if (c0 >= G) {                                                  // a block of padding words only
         if (owns)
-            for (int64_t i = s_lo; i < s_hi; ++i) store_words(i, zeros, zeros, zeros);
+            for (int64_t i = s_lo; i < s_hi; ++i, next_sample()) store_words(zeros, zeros, zeros);
         return;
     }
     const uint32_t ce = G32 - cb < uint32_t(Cfg::kCols) ? G32 : cb + uint32_t(Cfg::kCols);   // end of this CTA's columns
@@ -186,24 +187,33 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     // layout-dependent values, recomputed when (W, e) changes
     uint32_t W_cur = 0xFFFFFFFFu, e_cur = 0;
     uint32_t rel_cb = 0, span_len = 0;                              // text offset of column cb relative to the record; bytes to its end
-    uint32_t d_k[WPT], M_k[WPT], cm_k[WPT], rem_k[WPT];            // per word: bit offset - a15, columns before the line end, columns < G, bases left on the line
+    uint32_t d_k[WPT], M_k[WPT], cm_k[WPT];                        // per word: bit offset - a15, columns before the line end, columns < G
+    uint32_t end_k[WPT], ls_k[WPT], lsoff_k[WPT];                  // text offset of the line end in the word (kNone: none); line-start bit, its text offset
+    uint32_t eol_first = '\n', eol_last_at = 0;                    // first terminator byte; offset of the last one ('\n') from it
     auto relayout = [&](uint32_t W, uint32_t e) {
         W_cur = W; e_cur = e;
+        eol_first = e == 2u ? uint32_t('\r') : uint32_t('\n');
+        eol_last_at = e ? e - 1u : 0u;
         rel_cb = cb + (W ? cb / W : 0u) * e;
         span_len = (ce - 1) + (W ? (ce - 1) / W : 0u) * e + 1 + e - rel_cb;    // incl. the terminator after the last column
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const uint32_t ck = c + 32u * k;
+            d_k[k] = 0; M_k[k] = 0xFFFFFFFFu; cm_k[k] = 0u; end_k[k] = kNone; ls_k[k] = 0u; lsoff_k[k] = 0u;   // a padding word: all zero
             if (ck < ce) {
                 const uint32_t ncols = ce - ck < 32u ? ce - ck : 32u;
                 const uint32_t line = W ? ck / W : 0u;
                 const uint32_t pos = W ? ck - line * W : 0u;
-                rem_k[k] = W ? W - pos : 0xFFFFu;
+                const uint32_t rem = W ? W - pos : 0xFFFFu;         // bases left on the line at column ck
                 d_k[k] = ck + line * e - rel_cb;
-                M_k[k] = rem_k[k] >= 32u ? 0xFFFFFFFFu : (1u << rem_k[k]) - 1u;
+                M_k[k] = rem >= 32u ? 0xFFFFFFFFu : (1u << rem) - 1u;
                 cm_k[k] = ncols >= 32u ? 0xFFFFFFFFu : (1u << ncols) - 1u;
-            } else {
-                rem_k[k] = 0xFFFFu; d_k[k] = 0; M_k[k] = 0xFFFFFFFFu; cm_k[k] = 0u;      // a padding word: all zero
+                // a line ends inside (or at the end of) this word and more bases follow: its terminator is checked here
+                // (inside the staged span, which includes the terminator after the CTA's last column)
+                if (rem <= ncols && ck + rem < G32) end_k[k] = d_k[k] + rem;
+                // Every line start is a column of exactly one word: its first one, or the one after a line end inside it.
+                if ((W && rem == W) || ck == 0u) { ls_k[k] = 1u; lsoff_k[k] = d_k[k]; }
+                else if (rem < ncols) { ls_k[k] = 1u << rem; lsoff_k[k] = d_k[k] + rem + e; }
             }
         }
     };
@@ -240,8 +250,9 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     for (int64_t i = s_lo; i < s_hi; ++i) {
         const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
         if (W && W < uint32_t(kMinLineW)) {                 // a layout the host must re-stage
-            if (owns) store_words(i, zeros, zeros, zeros);
+            if (owns) store_words(zeros, zeros, zeros);
             if (threadIdx.x == 0) atomicOr(&flags[i], 1);
+            next_sample();
             continue;                                       // (uniform for the CTA: no barrier is skipped by a part of it)
         }
         if (W != W_cur || e != e_cur) relayout(W, e);
@@ -276,7 +287,8 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         }
         // ---- phase B: this thread's words, taken from the bit arrays
         uint32_t o0[WPT], o1[WPT], ov[WPT];
-        bool irregular = false, marker = false;
+        uint32_t irregular = 0;                             // != 0: the record is not laid out as promised
+        bool marker = false;
 #pragma unroll
         for (int k = 0; k < WPT; ++k) {
             const uint32_t o = a15 + d_k[k];               // bit index in the arrays = byte index in the stage buffer
@@ -287,29 +299,23 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
                 return ((x0 & M) | (__funnelshift_r(x0, x1, e) & ~M)) & cm;
             };
             const uint32_t fv = take(buf), g0 = take(buf + kBitWords), f1 = take(buf + 2 * kBitWords);
-            irregular |= (g0 & ~fv) != 0;                  // a control character among the bases
-            const uint32_t ck = c + 32u * k, rem = rem_k[k];
-            if (cm) {
-                const uint32_t ncols = ce - ck < 32u ? ce - ck : 32u;
-                // A line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser
-                // the tools share (it opens the next record / a quality block): the host must re-index.  Every line
-                // start is a column of exactly one word -- its first one, or the one after a line end inside it -- and
-                // a marker is never a base: the byte is only looked at when that column is not valid.
-                const bool starts_line = (W && rem == W) || ck == 0;
-                const uint32_t j = starts_line ? 0u : rem;                 // column (bit) of the line start in this word, if < ncols
-                if ((starts_line || rem < ncols) && !((fv >> j) & 1u)) marker |= is_marker(stg[o + j + (starts_line ? 0u : e)]);
-                if (rem <= ncols && ck + rem < G32) {      // a line ends inside (or at the end of) this word and more bases follow
-                    const uint32_t t = o + rem;            // (inside the staged span: it includes the terminator after the last column)
-                    if (e == 1) irregular |= stg[t] != '\n';
-                    else irregular |= (stg[t] != '\r') | (stg[t + 1] != '\n');
-                }
-            }
+            irregular |= g0 & ~fv;                         // a control character among the bases
+            // the terminator of the line that ends in this word must be the expected bytes ('\n', or '\r' '\n')
+            const bool has_end = end_k[k] != kNone;
+            const uint32_t t = has_end ? a15 + end_k[k] : 0u;
+            const uint32_t t_first = stg[t], t_last = stg[t + eol_last_at];
+            irregular |= has_end ? ((t_first ^ eol_first) | (t_last ^ uint32_t('\n'))) : 0u;
+            // A line of the sequence region that starts with '>', '@' or '+' is not sequence at all for the parser the
+            // tools share (it opens the next record / a quality block): the host must re-index.  A marker is never a
+            // base: the byte is only looked at when the line's first column is not valid.
+            if (ls_k[k] & ~fv) marker |= is_marker(stg[a15 + lsoff_k[k]]);
             o0[k] = g0 & fv; o1[k] = f1; ov[k] = fv;
             const uint32_t lo2 = fv & ~f1, hi2 = fv & f1;   // codes 0/1 (A, C) and 2/3 (T, G)
             sA[k] |= lo2 & ~g0; sC[k] |= lo2 & g0; sT[k] |= hi2 & ~g0; sG[k] |= hi2 & g0;
             sInv[k] |= ~fv & cm;
         }
-        if (owns) store_words(i, o0, o1, ov);
+        if (owns) store_words(o0, o1, ov);
+        next_sample();
         if (irregular) atomicOr(&flags[i], 1);
         if (marker) atomicOr(&flags[i], 2);
         ++k_act;
