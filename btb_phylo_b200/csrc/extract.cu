@@ -111,6 +111,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "PACK_DONE:\n\t}"
         ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -217,15 +220,19 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             }
         }
     };
-    uint32_t full_bar[kRing];
+    uint32_t full_bar[kRing], empty_bar[kRing];                    // text landed / every thread is done with the buffer
 #pragma unroll
-    for (int k = 0; k < kRing; ++k) full_bar[k] = smem_u32(&full[k]);
+    for (int k = 0; k < kRing; ++k) { full_bar[k] = smem_u32(&full[k]); empty_bar[k] = smem_u32(&full[kRing + k]); }
     const int64_t text_padded = (text_bytes + 15) & ~int64_t(15);  // the allocation is padded to a 16-byte boundary
     auto issue = [&](int64_t i, int k) {                            // one thread: bulk copy of sample i's span into stage[k]
         const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
-        const int64_t lo = rec_off[i] + int64_t(cb) + int64_t(W ? cb / W : 0u) * e;
-        const int64_t len = int64_t(ce - 1) + int64_t(W ? (ce - 1) / W : 0u) * e + 1 + e - (int64_t(cb) + int64_t(W ? cb / W : 0u) * e);
-        int64_t hi = lo + len;
+        uint32_t rel = rel_cb, span = span_len;                     // (the layout registers hold them for the current layout)
+        if (W != W_cur || e != e_cur) {
+            rel = cb + (W ? cb / W : 0u) * e;
+            span = (ce - 1) + (W ? (ce - 1) / W : 0u) * e + 1 + e - rel;
+        }
+        const int64_t lo = rec_off[i] + int64_t(rel);
+        int64_t hi = lo + int64_t(span);
         if (hi > text_bytes) hi = text_bytes;
         const int64_t alo = lo & ~int64_t(15);
         int64_t bytes = (((hi - alo + 15) >> 4) + 1) * 16;          // + 1 chunk: phase B may look one word beyond
@@ -236,12 +243,10 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     int64_t nxt = s_lo;                                             // next sample whose text has not been requested (thread 0)
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < kRing; ++k) mbar_init(full_bar[k], 1);
+        for (int k = 0; k < kRing; ++k) { mbar_init(full_bar[k], 1); mbar_init(empty_bar[k], kPackThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int k = 0; k < kRing - 1; ++k) {               // the buffer of the sample before the current one is refilled in the loop
-            while (nxt < s_hi && !active(nxt)) ++nxt;
-            if (nxt < s_hi) issue(nxt++, k);
-        }
+        while (nxt < s_hi && !active(nxt)) ++nxt;           // the first active sample; the following ones are requested in the loop
+        if (nxt < s_hi) issue(nxt++, 0);
     }
     __syncthreads();
     uint32_t sA[WPT] = {}, sC[WPT] = {}, sG[WPT] = {}, sT[WPT] = {}, sInv[WPT] = {};
@@ -259,32 +264,44 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         // per sample only the record's start is new; everything below is 32-bit arithmetic relative to it
         const int64_t rec = rec_off[i];
         const uint32_t a15 = (uint32_t(rec) + rel_cb) & 15u;        // misalignment of the span's first byte
-        const int64_t room64 = text_bytes - (rec + int64_t(rel_cb)); // bytes from there to the end of the text (matters for the last record only)
-        const uint32_t room = room64 > int64_t(1 << 30) ? (1u << 30) : (room64 > 0 ? uint32_t(room64) : 0u);
-        const uint32_t len = span_len < room ? span_len : room;
-        const int nchunk = int((a15 + len + 15u) >> 4) + 1;         // + 1: phase B may look one word beyond
-        const int live = int((a15 + room + 15u) >> 4);              // chunks that hold text at all
+        // The span may run beyond the end of the text in the last record only (a truncated file): then fewer bytes were
+        // staged, and the chunks past them count as blanks.
+        int nchunk = int((a15 + span_len + 15u) >> 4) + 1;          // + 1: phase B may look one word beyond
+        int live = nchunk;                                          // chunks that hold text at all
+        if (rec + int64_t(rel_cb) + int64_t(span_len) + 48 > text_bytes) {      // (48: every chunk below lies inside the text)
+            const int64_t room64 = text_bytes - (rec + int64_t(rel_cb));
+            const uint32_t room = room64 > int64_t(1 << 30) ? (1u << 30) : (room64 > 0 ? uint32_t(room64) : 0u);
+            const uint32_t len = span_len < room ? span_len : room;
+            nchunk = int((a15 + len + 15u) >> 4) + 1;
+            live = int((a15 + room + 15u) >> 4);
+        }
+        const int nload = nchunk < live ? nchunk : live;
         uint32_t *buf = bits + (k_act & 1u) * 3 * kBitWords;
         const uint8_t *stg = stage + ring * Cfg::kStageBytes;
+        if (threadIdx.x == 0) {     // the text of the NEXT active sample is requested a whole sample ahead: into the other
+            while (nxt < s_hi && !active(nxt)) ++nxt;       // buffer, once every thread is done with the sample before this one
+            if (nxt < s_hi) {
+                const uint32_t nb = ring + 1u == uint32_t(kRing) ? 0u : ring + 1u;
+                if (k_act + 1u >= uint32_t(kRing)) mbar_wait(empty_bar[nb], ((k_act + 1u - uint32_t(kRing)) / uint32_t(kRing)) & 1u);
+                issue(nxt++, int(nb));
+            }
+        }
         mbar_wait(full_bar[ring], ring_phase);
         // ---- phase A: classify the text, 16 bytes per thread and step
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stg);
         uint16_t *hvp = reinterpret_cast<uint16_t *>(buf), *h0p = reinterpret_cast<uint16_t *>(buf + kBitWords);
         uint16_t *h1p = reinterpret_cast<uint16_t *>(buf + 2 * kBitWords);
 #pragma unroll 2
-        for (int j = threadIdx.x; j < nchunk; j += kPackThreads) {
-            uint4 t4 = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
-            if (j < live) t4 = st4[j];
+        for (int j = threadIdx.x; j < nload; j += kPackThreads) {
+            const uint4 t4 = st4[j];
             const Class4 g0 = classify4(t4.x), g1 = classify4(t4.y), g2 = classify4(t4.z), g3 = classify4(t4.w);
             hvp[j] = uint16_t(gather16(g0.v, g1.v, g2.v, g3.v));
             h0p[j] = uint16_t(gather16(g0.f0, g1.f0, g2.f0, g3.f0));
             h1p[j] = uint16_t(gather16(g0.f1, g1.f1, g2.f1, g3.f1));
         }
-        __syncthreads();            // this sample's bit arrays are complete; the stage buffer of the PREVIOUS sample is free
-        if (threadIdx.x == 0) {     // ... and takes the text of the active sample after next
-            while (nxt < s_hi && !active(nxt)) ++nxt;
-            if (nxt < s_hi) issue(nxt++, int(ring == 0 ? uint32_t(kRing - 1) : ring - 1u));
-        }
+        if (nload < nchunk)                                          // blanks: not a base, not a control character
+            for (int j = nload + threadIdx.x; j < nchunk; j += kPackThreads) hvp[j] = h0p[j] = h1p[j] = 0;
+        __syncthreads();            // this sample's bit arrays are complete
         // ---- phase B: this thread's words, taken from the bit arrays
         uint32_t o0[WPT], o1[WPT], ov[WPT];
         uint32_t irregular = 0;                             // != 0: the record is not laid out as promised
@@ -314,6 +331,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             sA[k] |= lo2 & ~g0; sC[k] |= lo2 & g0; sT[k] |= hi2 & ~g0; sG[k] |= hi2 & g0;
             sInv[k] |= ~fv & cm;
         }
+        mbar_arrive(empty_bar[ring]);                       // (the checks above were this thread's last look at the staged text)
         if (owns) store_words(o0, o1, ov);
         next_sample();
         if (irregular) atomicOr(&flags[i], 1);

@@ -70,7 +70,8 @@ int         btb_device_count(int *count);                 /* number of usable sm
  *     "umma_lockstep" [1]      0 off, k >= 1: TMA producers of all CTAs start a unit at most k-1 rounds apart
  *     "umma_coop" [1]          0: CTA-pair kernel without the cooperative launch attribute (set automatically when
  *                              a profiler is attached: ncu cannot replay a cooperative cluster launch)
- *   extraction: "pack_wpt" [2] plane words per thread of k1 (1, 2, 4); "ingest_predict" [1] predicted FASTA framing
+ *   extraction: "pack_wpt" [2] plane words per thread of k1 (1, 2, 4); "pack_gy" [0 = automatic] sample groups per launch;
+ *               "ingest_predict" [1] predicted FASTA framing
  *   level 1/2:  "dense_pageable" [1] large snps.fas into pageable host memory; "host_stream" [0] +
  *               "host_stream_rows" [64] streamed level-2 call;
  *               "comm_band_rows" [16] block rows per launch + copy band of a rank's share (btb_dist_matrix_host_comm);
