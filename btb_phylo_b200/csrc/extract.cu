@@ -220,30 +220,30 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             }
         }
     };
-    uint32_t full_bar[kRing], empty_bar[kRing];                    // text landed / every thread is done with the buffer
-#pragma unroll
-    for (int k = 0; k < kRing; ++k) { full_bar[k] = smem_u32(&full[k]); empty_bar[k] = smem_u32(&full[kRing + k]); }
+    const uint32_t bar0 = smem_u32(full);
+    auto full_bar_at = [&](uint32_t k) { return bar0 + 8u * k; };                  // the text of buffer k has landed
+    auto empty_bar_at = [&](uint32_t k) { return bar0 + 8u * (uint32_t(kRing) + k); };   // every thread is done with buffer k
     const int64_t text_padded = (text_bytes + 15) & ~int64_t(15);  // the allocation is padded to a 16-byte boundary
-    auto issue = [&](int64_t i, int k) {                            // one thread: bulk copy of sample i's span into stage[k]
-        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+    auto issue_at = [&](uint32_t W, uint32_t e, int64_t rec, int k) {   // one thread: bulk copy of a sample's span into stage[k]
         uint32_t rel = rel_cb, span = span_len;                     // (the layout registers hold them for the current layout)
         if (W != W_cur || e != e_cur) {
             rel = cb + (W ? cb / W : 0u) * e;
             span = (ce - 1) + (W ? (ce - 1) / W : 0u) * e + 1 + e - rel;
         }
-        const int64_t lo = rec_off[i] + int64_t(rel);
+        const int64_t lo = rec + int64_t(rel);
         int64_t hi = lo + int64_t(span);
         if (hi > text_bytes) hi = text_bytes;
         const int64_t alo = lo & ~int64_t(15);
         int64_t bytes = (((hi - alo + 15) >> 4) + 1) * 16;          // + 1 chunk: phase B may look one word beyond
         if (alo + bytes > text_padded) bytes = text_padded - alo;   // (chunks beyond the text read as blanks in phase A)
-        mbar_expect_tx(full_bar[k], uint32_t(bytes));
-        bulk_g2s(smem_u32(stage + k * Cfg::kStageBytes), text + alo, uint32_t(bytes), full_bar[k]);
+        mbar_expect_tx(full_bar_at(uint32_t(k)), uint32_t(bytes));
+        bulk_g2s(smem_u32(stage + k * Cfg::kStageBytes), text + alo, uint32_t(bytes), full_bar_at(uint32_t(k)));
     };
+    auto issue = [&](int64_t i, int k) { issue_at(uint32_t(line_w[i]), uint32_t(eol_len[i]), rec_off[i], k); };
     int64_t nxt = s_lo;                                             // next sample whose text has not been requested (thread 0)
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < kRing; ++k) { mbar_init(full_bar[k], 1); mbar_init(empty_bar[k], kPackThreads); }
+        for (int k = 0; k < kRing; ++k) { mbar_init(full_bar_at(uint32_t(k)), 1); mbar_init(empty_bar_at(uint32_t(k)), kPackThreads); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         while (nxt < s_hi && !active(nxt)) ++nxt;           // the first active sample; the following ones are requested in the loop
         if (nxt < s_hi) issue(nxt++, 0);
@@ -252,8 +252,15 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
     uint32_t sA[WPT] = {}, sC[WPT] = {}, sG[WPT] = {}, sT[WPT] = {}, sInv[WPT] = {};
     uint32_t k_act = 0, ring = 0, ring_phase = 0;                   // active samples done; their stage buffer and its mbarrier phase
     auto is_marker = [](uint32_t b) { return b == '>' || b == '@' || b == '+'; };
+    // the record table entry of a sample is read one iteration ahead: no thread waits for it, and thread 0 has what the
+    // next request needs at hand
+    uint32_t W_n = 0, e_n = 0;
+    int64_t rec_n = 0;
+    if (s_lo < s_hi) { W_n = uint32_t(line_w[s_lo]); e_n = uint32_t(eol_len[s_lo]); rec_n = rec_off[s_lo]; }
     for (int64_t i = s_lo; i < s_hi; ++i) {
-        const uint32_t W = uint32_t(line_w[i]), e = uint32_t(eol_len[i]);
+        const uint32_t W = W_n, e = e_n;
+        const int64_t rec = rec_n;
+        if (i + 1 < s_hi) { W_n = uint32_t(line_w[i + 1]); e_n = uint32_t(eol_len[i + 1]); rec_n = rec_off[i + 1]; }
         if (W && W < uint32_t(kMinLineW)) {                 // a layout the host must re-stage
             if (owns) store_words(zeros, zeros, zeros);
             if (threadIdx.x == 0) atomicOr(&flags[i], 1);
@@ -262,7 +269,6 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         }
         if (W != W_cur || e != e_cur) relayout(W, e);
         // per sample only the record's start is new; everything below is 32-bit arithmetic relative to it
-        const int64_t rec = rec_off[i];
         const uint32_t a15 = (uint32_t(rec) + rel_cb) & 15u;        // misalignment of the span's first byte
         // The span may run beyond the end of the text in the last record only (a truncated file): then fewer bytes were
         // staged, and the chunks past them count as blanks.
@@ -279,14 +285,16 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
         uint32_t *buf = bits + (k_act & 1u) * 3 * kBitWords;
         const uint8_t *stg = stage + ring * Cfg::kStageBytes;
         if (threadIdx.x == 0) {     // the text of the NEXT active sample is requested a whole sample ahead: into the other
-            while (nxt < s_hi && !active(nxt)) ++nxt;       // buffer, once every thread is done with the sample before this one
-            if (nxt < s_hi) {
+            const bool follows = nxt == i + 1 && nxt < s_hi && !(W_n && W_n < uint32_t(kMinLineW));   // (the usual case)
+            if (!follows) while (nxt < s_hi && !active(nxt)) ++nxt;
+            if (nxt < s_hi) {       // buffer, once every thread is done with the sample before this one
                 const uint32_t nb = ring + 1u == uint32_t(kRing) ? 0u : ring + 1u;
-                if (k_act + 1u >= uint32_t(kRing)) mbar_wait(empty_bar[nb], ((k_act + 1u - uint32_t(kRing)) / uint32_t(kRing)) & 1u);
-                issue(nxt++, int(nb));
+                if (k_act + 1u >= uint32_t(kRing)) mbar_wait(empty_bar_at(uint32_t(nb)), ((k_act + 1u - uint32_t(kRing)) / uint32_t(kRing)) & 1u);
+                if (follows) issue_at(W_n, e_n, rec_n, int(nb)); else issue(nxt, int(nb));
+                ++nxt;
             }
         }
-        mbar_wait(full_bar[ring], ring_phase);
+        mbar_wait(full_bar_at(uint32_t(ring)), ring_phase);
         // ---- phase A: classify the text, 16 bytes per thread and step
         const uint4 *st4 = reinterpret_cast<const uint4 *>(stg);
         uint16_t *hvp = reinterpret_cast<uint16_t *>(buf), *h0p = reinterpret_cast<uint16_t *>(buf + kBitWords);
@@ -331,7 +339,7 @@ pack_planes_kernel(const uint8_t *__restrict__ text, int64_t text_bytes, const i
             sA[k] |= lo2 & ~g0; sC[k] |= lo2 & g0; sT[k] |= hi2 & ~g0; sG[k] |= hi2 & g0;
             sInv[k] |= ~fv & cm;
         }
-        mbar_arrive(empty_bar[ring]);                       // (the checks above were this thread's last look at the staged text)
+        mbar_arrive(empty_bar_at(uint32_t(ring)));                       // (the checks above were this thread's last look at the staged text)
         if (owns) store_words(o0, o1, ov);
         next_sample();
         if (irregular) atomicOr(&flags[i], 1);
@@ -526,7 +534,7 @@ int pack_planes(const uint8_t *d_text, int64_t text_bytes, const int64_t *d_rec_
     const int64_t cta_words = int64_t(kPackThreadsB) * wpt;
     const int64_t gx = (words + cta_words - 1) / cta_words;
     // sample groups: about 14 CTAs per SM in all (four are resident at a time; measured best on 48 records of
-    // 4.35 Mb: 3.05 TB/s with 8 groups against 2.4 with 1), but no fewer than four samples per CTA -- its set-up
+    // 4.35 Mb: 3.3 TB/s with 8 groups against 2.4 with 1), but no fewer than four samples per CTA -- its set-up
     // and the merge of its column state (one coalesced atomicOr per state word and group) have to be worth it
     int sms = 148;
     { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
