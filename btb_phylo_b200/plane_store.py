@@ -10,7 +10,8 @@ can be reused is k1's output: the three bit-planes of every sample (3 bits per b
     snp_sites(snps.fas, [consensus files ...], plane_store="/path/to/store")
 
 keeps one blob per input file, keyed by the file's absolute path and validated by its size and
-modification time (the rule `make` uses).  A later call packs only the files that are new or have
+modification time (the rule `make` uses), plus a small index of what the blob headers say (a hint that
+saves one open per blob; every header is still read and compared when its planes are).  A later call packs only the files that are new or have
 changed (k1, with the column state fused in), loads the planes of all others from the store (their
 column state comes from the stand-alone k2 over those planes), and then selects and compacts exactly
 as the uncached call does: the result is the same snps.fas, byte for byte -- tests/test_gpu_store.py.
@@ -23,6 +24,7 @@ btb_snp_sites_files, which parses anything, and leaves the store alone.
 """
 import ctypes
 import hashlib
+import json
 import os
 import struct
 from concurrent.futures import ThreadPoolExecutor
@@ -36,8 +38,36 @@ HEADER = struct.Struct("<8sqqqqi")      # magic, G, words, source size, source m
 CHUNK_BYTES = 64 << 20
 
 
+INDEX = "index.json"           # blob file name -> [G, words, source size, source mtime (ns), record name]: what the blob headers say
+
+
 def _blob_path(store, path):
     return os.path.join(store, hashlib.sha1(os.path.abspath(path).encode()).hexdigest() + ".planes")
+
+
+def _load_index(store):
+    """The store's index: one small file instead of one open + read per blob (0.75 s for 16,000 blobs).  It is only a
+    hint -- every blob's header is read together with its planes and must say the same -- and it heals itself: blobs
+    it does not list are looked at directly, entries whose blob turns out stale are dropped."""
+    try:
+        with open(os.path.join(store, INDEX)) as f:
+            d = json.load(f)
+        if d.get("magic") == MAGIC.decode() and isinstance(d.get("blobs"), dict):
+            return d["blobs"]
+    except (OSError, ValueError):
+        pass
+    return {}
+
+
+def _save_index(store, blobs):
+    part = os.path.join(store, "%s.%d.tmp" % (INDEX, os.getpid()))
+    with open(part, "w") as f:
+        json.dump({"magic": MAGIC.decode(), "blobs": blobs}, f)
+    os.replace(part, os.path.join(store, INDEX))
+
+
+class _StaleBlob(Exception):
+    """A blob the index vouched for is not what its header should say: drop it and start over."""
 
 
 def _read_header(blob, st):
@@ -68,14 +98,49 @@ class NotPredictable(Exception):
 
 def snp_sites_cached(lib, out_path, paths, threads, store):
     """-> (n_samples, G, L, n_from_store).  Raises NotPredictable for inputs this path does not take."""
+    with ThreadPoolExecutor(max_workers=max(1, min(int(threads), 64))) as pool:
+        for _ in range(4):
+            try:
+                return _snp_sites_cached(lib, out_path, paths, store, pool)
+            except _StaleBlob as stale:
+                blobs = _load_index(store)
+                for b in stale.args[0]:
+                    blobs.pop(os.path.basename(b), None)
+                    try:
+                        os.unlink(b)
+                    except OSError:
+                        pass
+                _save_index(store, blobs)
+    raise NotPredictable("the plane store keeps changing under this call")
+
+
+def _snp_sites_cached(lib, out_path, paths, store, pool):
+    import sys
+    import time
     import torch
+    marks = [("start", time.perf_counter())]                         # BTB_STORE_VERBOSE=1: phase timers on stderr
     os.makedirs(store, exist_ok=True)
     n = len(paths)
     stats = [os.stat(p) for p in paths]
-    heads = [_read_header(_blob_path(store, p), st) for p, st in zip(paths, stats)]
+    index = _load_index(store)
+    blob_of = [_blob_path(store, p) for p in paths]
+    index_dirty = False
+
+    def head_of(k):
+        e = index.get(os.path.basename(blob_of[k]))
+        if e is not None and e[2] == stats[k].st_size and e[3] == stats[k].st_mtime_ns:
+            return e[0], e[1], e[4]
+        return _read_header(blob_of[k], stats[k])                     # not listed (or listed for an older source): look
+    heads = [head_of(k) for k in range(n)]
+    for k in range(n):
+        key = os.path.basename(blob_of[k])
+        if heads[k] is not None and key not in index:
+            index[key] = [heads[k][0], heads[k][1], stats[k].st_size, stats[k].st_mtime_ns, heads[k][2]]
+            index_dirty = True
     new_idx = [i for i in range(n) if heads[i] is None]
     old_idx = [i for i in range(n) if heads[i] is not None]
 
+    marks.append(("store headers", time.perf_counter()))
     # ---- frame the new files (one record each, equal layout: what consensus files are) ------------------
     frames, names = None, [None] * n
     if new_idx:
@@ -102,16 +167,17 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
     if any(heads[i][1] != words for i in old_idx):
         raise NotPredictable("store written for another plane layout")
 
+    marks.append(("frame new files", time.perf_counter()))
     dev = torch.device("cuda", torch.cuda.current_device())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     nU = len(new_idx)
     planes = torch.empty((3, n, words), dtype=torch.int32, device=dev)        # plane rows: the new samples, then the stored ones
     state = torch.zeros(5 * words, dtype=torch.int32, device=dev)
     flags = torch.zeros(max(1, nU), dtype=torch.int32, device=dev)
-    pool = ThreadPoolExecutor(max_workers=max(1, min(int(threads), 64)))
-    # two page-locked staging buffers serve both the text of new files and the planes of stored ones
+    # two page-locked staging buffers serve both the text of new files and the planes of stored ones; larger ones
+    # for large sample sets (fewer, better filled rounds of the reader threads)
     blob_bytes = 3 * words * 4
-    need = CHUNK_BYTES
+    need = min(max(CHUNK_BYTES, n * blob_bytes // 64), 4 * CHUNK_BYTES)
     if nU:
         need = max(need, int((frames[:, 2].max() + 15) // 16 * 16) + 64)
     if old_idx:
@@ -159,6 +225,7 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
         if int(flags[:nU].max().item()) != 0:
             raise NotPredictable("a record is not laid out as its first line promised")
 
+    marks.append(("pack new files", time.perf_counter()))
     # ---- stored samples: planes from the store, their column state from k2 --------------------------------------
     if old_idx:
         per_chunk = max(1, need // blob_bytes)
@@ -174,12 +241,37 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
 
             def load_one(k, hostv=hostv, k0=k0):
                 i = old_idx[k]
-                with open(_blob_path(store, paths[i]), "rb") as f:
-                    f.seek(HEADER.size + len(heads[i][2].encode()))
-                    for p in range(3):
-                        if f.readinto(memoryview(hostv[p, k - k0]).cast("B")) != words * 4:
-                            raise OSError("short plane blob for %s" % paths[i])
-            list(pool.map(load_one, range(k0, k1)))
+                nm = heads[i][2].encode()
+                want = HEADER.pack(MAGIC, G, words, stats[i].st_size, stats[i].st_mtime_ns, len(nm)) + nm
+                head = bytearray(len(want))
+                try:
+                    fd = os.open(blob_of[i], os.O_RDONLY)
+                except OSError:
+                    return blob_of[i]
+                try:                                                  # one scatter read: header, then the planes to their rows
+                    bufs = [memoryview(head)] + [memoryview(hostv[p, k - k0]).cast("B") for p in range(3)]
+                    total, got = len(want) + blob_bytes, 0
+                    while got < total:
+                        rest, skip = [], got
+                        for b in bufs:
+                            if skip >= len(b):
+                                skip -= len(b)
+                            else:
+                                rest.append(b[skip:])
+                                skip = 0
+                        more = os.preadv(fd, rest, got)
+                        if more <= 0:
+                            return blob_of[i]
+                        got += more
+                    if bytes(head) != want or os.fstat(fd).st_size != total:
+                        return blob_of[i]
+                finally:
+                    os.close(fd)
+                return None
+            stale = [b for b in pool.map(load_one, range(k0, k1)) if b is not None]
+            if stale:
+                torch.cuda.synchronize()
+                raise _StaleBlob(stale)
             for p in range(3):
                 planes[p, nU + k0:nU + k1].copy_(pinned[b][p, :k1 - k0], non_blocking=True)
             busy[b] = torch.cuda.Event()
@@ -187,6 +279,7 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
         stored = planes[:, nU:, :]                                   # (k2 walks rows nU .. n-1 of each plane: stride n * words)
         _capi.check(lib.btb_column_mask(_ptr(stored), n - nU, n, G, _ptr(state), 1, st), "btb_column_mask")
 
+    marks.append(("load stored planes", time.perf_counter()))
     # ---- k3: select, compact ----------------------------------------------------------------------------------------
     keep = torch.empty(words, dtype=torch.int32, device=dev)
     idx = torch.empty(words * 32, dtype=torch.int32, device=dev)
@@ -203,10 +296,12 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
         row_of[old_idx] = nU + np.arange(len(old_idx))
         tmp = "%s.%d.tmp" % (out_path, os.getpid())
         with open(tmp, "wb") as f:
-            for i in range(n):
-                f.write(b">" + names[i].encode() + b"\n" + rows[row_of[i]].tobytes() + b"\n")
+            for i0 in range(0, n, 512):
+                f.write(b"".join(b">" + names[i].encode() + b"\n" + rows[row_of[i]].tobytes() + b"\n"
+                                 for i in range(i0, min(n, i0 + 512))))
         os.replace(tmp, out_path)
 
+    marks.append(("select, compact, snps.fas", time.perf_counter()))
     # ---- the new samples' planes go to the store (also when no SNP was found: the planes are what they are) -------
     if nU:
         per_chunk = max(1, need // blob_bytes)
@@ -230,7 +325,7 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
 
             def save_one(k, host=host, k0=k0):
                 i = new_idx[k]
-                blob = _blob_path(store, paths[i])
+                blob = blob_of[i]
                 nm = names[i].encode()
                 part = "%s.%d.tmp" % (blob, os.getpid())
                 with open(part, "wb") as f:
@@ -240,5 +335,13 @@ def snp_sites_cached(lib, out_path, paths, threads, store):
                         f.write(memoryview(host[p, k - k0]).cast("B"))
                 os.replace(part, blob)
             list(pool.map(save_one, range(k0, k1)))
-    pool.shutdown()
+        for i in new_idx:
+            index[os.path.basename(blob_of[i])] = [G, words, stats[i].st_size, stats[i].st_mtime_ns, names[i]]
+        index_dirty = True
+    if index_dirty:
+        _save_index(store, index)
+    marks.append(("save new planes", time.perf_counter()))
+    if os.environ.get("BTB_STORE_VERBOSE"):
+        print("plane store: %d samples, %d from the store; " % (n, len(old_idx)) +
+              ", ".join("%s %.3f s" % (marks[k][0], marks[k][1] - marks[k - 1][1]) for k in range(1, len(marks))), file=sys.stderr)
     return n, G, L, len(old_idx)

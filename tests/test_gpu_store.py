@@ -27,6 +27,10 @@ def write_samples(tmp_path, names, aln, wrap=60):
     return paths
 
 
+def blobs_of(store):
+    return sorted(f for f in os.listdir(store) if f.endswith(".planes"))
+
+
 def oracle_snps(oracle, tmp_path, paths):
     mf = tmp_path / "multi.fas"
     with open(mf, "wb") as out:
@@ -48,13 +52,13 @@ def test_weekly_growth_same_bytes_as_the_uncached_call(ph, oracle, tmp_path):
     meta = ph.snp_sites(str(out), paths[:40], plane_store=str(store))
     want = oracle_snps(oracle, tmp_path, paths[:40])
     assert out.read_bytes() == want and meta["number_of_snps"] == len(want.split(b"\n")[1])
-    assert len(os.listdir(store)) == 40
+    assert len(blobs_of(store)) == 40
     # week 2: 20 more samples -- 40 come from the store.  The new samples change the kept-column set.
-    before = {f: os.stat(store / f).st_mtime_ns for f in os.listdir(store)}
+    before = {f: os.stat(store / f).st_mtime_ns for f in blobs_of(store)}
     meta = ph.snp_sites(str(out), paths, plane_store=str(store))
     want = oracle_snps(oracle, tmp_path, paths)
     assert out.read_bytes() == want
-    assert len(os.listdir(store)) == 60 and all(os.stat(store / f).st_mtime_ns == t for f, t in before.items())
+    assert len(blobs_of(store)) == 60 and all(os.stat(store / f).st_mtime_ns == t for f, t in before.items())
     plain = tmp_path / "plain.fas"
     ph.snp_sites(str(plain), paths)
     assert plain.read_bytes() == want
@@ -104,7 +108,7 @@ def test_damaged_or_foreign_blobs_are_packed_again(ph, oracle, tmp_path):
     ph.snp_sites(str(out), paths, plane_store=str(store))
     want = oracle_snps(oracle, tmp_path, paths)
     assert out.read_bytes() == want
-    blobs = sorted(os.listdir(store))
+    blobs = blobs_of(store)
     assert len(blobs) == n
     raw = (store / blobs[0]).read_bytes()
     (store / blobs[0]).write_bytes(raw[:-8])                          # truncated
@@ -133,17 +137,17 @@ def test_crlf_files_and_a_flagged_record(ph, oracle, tmp_path):
     out = tmp_path / "snps.fas"
     ph.snp_sites(str(out), paths[:7], plane_store=str(store))
     assert out.read_bytes() == oracle_snps(oracle, tmp_path, paths[:7])
-    assert len(os.listdir(store)) == 7
+    assert len(blobs_of(store)) == 7
     ph.snp_sites(str(out), paths, plane_store=str(store))
     assert out.read_bytes() == oracle_snps(oracle, tmp_path, paths)
-    assert len(os.listdir(store)) == n
+    assert len(blobs_of(store)) == n
     # a new file with a tab among its bases: the kernel flags the record, the call goes through the exact parser
     extra = aln[0].copy()
     extra[1234] = 9
     files = paths + [write("tabbed", extra)]
     ph.snp_sites(str(out), files, plane_store=str(store))
     assert out.read_bytes() == oracle_snps(oracle, tmp_path, files)
-    assert len(os.listdir(store)) == n                                # nothing was stored for the fallback call
+    assert len(blobs_of(store)) == n                                # nothing was stored for the fallback call
     # new files of another layout than the first new one (other wrap, LF): not what the predicted framing takes
     # -- same bytes through the exact parser, whatever the store holds
     more = [write("w60", aln[1], wrap=60, crlf=False), write("w0", aln[2], wrap=0, crlf=False), write("w80", aln[3], wrap=80)]

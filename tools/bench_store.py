@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--snps", type=int, default=20000)
     ap.add_argument("--threads", type=int, default=min(64, os.cpu_count() or 1))
     ap.add_argument("--dir", default="/dev/shm/btb_store_bench")
+    ap.add_argument("--store-dir", default=None, help="where the plane store goes (default: under --dir)")
     a = ap.parse_args()
     import torch
     import bench_northstar as ns
@@ -33,8 +34,9 @@ def main():
     g = argparse.Namespace(samples=a.samples, genome=a.genome, snps=a.snps, files=a.samples, writers=8, dir=a.dir, seed=5,
                            n_frac=0.01, private_n=None)
     paths, names, _, nbytes, gen_s = ns.generate(g, torch, torch.device("cuda", 0))
-    store = os.path.join(a.dir, "store")
-    out = {"n_samples": a.samples, "genome": a.genome, "fasta_bytes": nbytes, "files": len(paths), "host_threads": a.threads}
+    store = os.path.join(a.store_dir or a.dir, "store")
+    out = {"n_samples": a.samples, "genome": a.genome, "fasta_bytes": nbytes, "files": len(paths), "host_threads": a.threads,
+           "inputs_dir": a.dir, "store_dir": store, "generate_s": gen_s}
     res = {}
 
     def run(label, **kw):
@@ -47,16 +49,17 @@ def main():
         run("warmup")                                              # CUDA context, library load
         plain = run("plain")
         cold = run("store_empty", plane_store=store)
-        res["store_empty"]["store_bytes"] = sum(os.path.getsize(os.path.join(store, f)) for f in os.listdir(store))
+        res["store_empty"]["store_bytes"] = sum(os.path.getsize(os.path.join(store, f)) for f in os.listdir(store) if f.endswith(".planes"))
         warm = run("store_full", plane_store=store)
-        blobs = sorted(os.listdir(store))
-        for f in blobs[:: 100]:                                    # 1 % of the samples are "new this week"
-            os.unlink(os.path.join(store, f))
+        for f in paths[:: 100]:                                    # 1 % of the samples are "new this week": another mtime
+            st = os.stat(f)
+            os.utime(f, ns=(st.st_atime_ns, st.st_mtime_ns + 1000000000))
         weekly = run("store_1pct_new", plane_store=store)
         out["runs"] = res
         out["identical_snps_fas"] = plain == cold == warm == weekly
     finally:
         shutil.rmtree(a.dir, ignore_errors=True)
+        shutil.rmtree(store, ignore_errors=True)
     print(json.dumps(out), flush=True)
 
 
