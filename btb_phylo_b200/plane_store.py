@@ -42,7 +42,7 @@ INDEX = "index.json"           # blob file name -> [G, words, source size, sourc
 
 
 def _blob_path(store, path):
-    return os.path.join(store, hashlib.sha1(os.path.abspath(path).encode()).hexdigest() + ".planes")
+    return os.path.join(store, hashlib.sha1(os.fsencode(os.path.abspath(path))).hexdigest() + ".planes")
 
 
 def _load_index(store):
@@ -83,7 +83,7 @@ def _read_header(blob, st):
             name = f.read(nl)
             if len(name) != nl or os.fstat(f.fileno()).st_size != HEADER.size + nl + 3 * words * 4:
                 return None
-            return G, words, name.decode()
+            return G, words, name.decode("utf-8", "surrogateescape")
     except OSError:
         return None
 
@@ -155,7 +155,7 @@ def _snp_sites_cached(lib, out_path, paths, store, pool):
         frames = np.frombuffer(out, dtype=np.int64).reshape(-1, 6).copy()
         if not (frames[:, 0] == np.arange(len(new_idx))).all():
             raise NotPredictable("a record spans files")
-        for k, nm in enumerate(nbuf.value.decode().split("\n")):
+        for k, nm in enumerate(nbuf.value.decode("utf-8", "surrogateescape").split("\n")):
             names[new_idx[k]] = nm
     for i in old_idx:
         names[i] = heads[i][2]
@@ -241,7 +241,7 @@ def _snp_sites_cached(lib, out_path, paths, store, pool):
 
             def load_one(k, hostv=hostv, k0=k0):
                 i = old_idx[k]
-                nm = heads[i][2].encode()
+                nm = heads[i][2].encode("utf-8", "surrogateescape")
                 want = HEADER.pack(MAGIC, G, words, stats[i].st_size, stats[i].st_mtime_ns, len(nm)) + nm
                 head = bytearray(len(want))
                 try:
@@ -297,7 +297,7 @@ def _snp_sites_cached(lib, out_path, paths, store, pool):
         tmp = "%s.%d.tmp" % (out_path, os.getpid())
         with open(tmp, "wb") as f:
             for i0 in range(0, n, 512):
-                f.write(b"".join(b">" + names[i].encode() + b"\n" + rows[row_of[i]].tobytes() + b"\n"
+                f.write(b"".join(b">" + names[i].encode("utf-8", "surrogateescape") + b"\n" + rows[row_of[i]].tobytes() + b"\n"
                                  for i in range(i0, min(n, i0 + 512))))
         os.replace(tmp, out_path)
 
@@ -326,8 +326,8 @@ def _snp_sites_cached(lib, out_path, paths, store, pool):
             def save_one(k, host=host, k0=k0):
                 i = new_idx[k]
                 blob = blob_of[i]
-                nm = names[i].encode()
-                part = "%s.%d.tmp" % (blob, os.getpid())
+                nm = names[i].encode("utf-8", "surrogateescape")
+                part = "%s.%d.%d.tmp" % (blob, os.getpid(), k)        # (the same file may be listed twice)
                 with open(part, "wb") as f:
                     f.write(HEADER.pack(MAGIC, G, words, stats[i].st_size, stats[i].st_mtime_ns, len(nm)))
                     f.write(nm)

@@ -154,3 +154,19 @@ def test_crlf_files_and_a_flagged_record(ph, oracle, tmp_path):
     files = paths + more
     ph.snp_sites(str(out), files, plane_store=str(store))
     assert out.read_bytes() == oracle_snps(oracle, tmp_path, files)
+
+
+def test_a_file_listed_twice_and_a_name_that_is_not_utf8(ph, oracle, tmp_path):
+    n, G = 6, 7001
+    names = synth.sample_names(n)
+    aln = synth.genome_alignment(n, G, 200, seed=81, n_frac=0.0)
+    paths = write_samples(tmp_path, names, aln)
+    odd = tmp_path / "odd.fas"
+    odd.write_bytes(synth.fasta_bytes(["x"], aln[0][None, :], wrap=60).replace(b">x\n", b">s\xff\xfe 1\n", 1))
+    files = paths + [str(odd), paths[2]]
+    store = tmp_path / "store"
+    out = tmp_path / "snps.fas"
+    for _ in range(2):                                                 # empty store, then everything from it
+        ph.snp_sites(str(out), files, plane_store=str(store))
+        assert out.read_bytes() == oracle_snps(oracle, tmp_path, files)
+    assert len(blobs_of(store)) == n + 1
