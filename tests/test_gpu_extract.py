@@ -84,3 +84,68 @@ def test_level3_pack_wrapped_text(capi, oracle):
         assert (bits(pl[2, i]) == valid).all(), i
         assert (bits(pl[0, i]) == (valid & (code & 1).astype(bool))).all(), i
         assert (bits(pl[1, i]) == (valid & (code >> 1).astype(bool))).all(), i
+
+
+@pytest.mark.parametrize("groups", [0, 1, 3])
+def test_level3_pack_skips_short_line_records_anywhere(capi, groups):
+    """Records whose lines are shorter than 32 columns are flagged and skipped by k1 (the host walks them); they
+    may stand first, in a row, or last in a CTA's share of the samples.  The text of the next record that IS packed
+    is requested a sample ahead -- by its table entry when it follows directly, by a scan otherwise -- and the
+    column state fused into the same pass must equal k2's over the packed planes."""
+    G = 9973
+    wraps = [8, 60, 16, 16, 16, 70, 0, 24, 61, 60, 8, 8, 33, 60, 12]
+    n = len(wraps)
+    aln = synth.genome_alignment(n, G, 400, seed=91, n_frac=0.02, lower=0.02)
+    names = synth.sample_names(n)
+    text = bytearray()
+    offs, lws, els = [], [], []
+    for i in range(n):
+        eol = b"\r\n" if i % 4 == 1 else b"\n"
+        rec = synth.fasta_bytes([names[i]], aln[i:i + 1], wrap=wraps[i], eol=eol)
+        offs.append(len(text) + rec.index(eol) + len(eol))
+        lws.append(wraps[i] if wraps[i] and wraps[i] < G else 0)
+        els.append(len(eol) if lws[-1] else 0)
+        text += rec
+    nbytes = len(text)
+    text += b"\0" * 64
+    lib = capi.lib()
+    capi.check(lib.btb_set_option(b"pack_gy", groups))
+    try:
+        words = lib.btb_plane_words(G)
+        d_text = torch.frombuffer(bytes(text), dtype=torch.uint8).cuda()
+        d_off = torch.tensor(offs, dtype=torch.int64).cuda()
+        d_lw = torch.tensor(lws, dtype=torch.int32).cuda()
+        d_el = torch.tensor(els, dtype=torch.int32).cuda()
+        planes = torch.full((3 * n * words,), -1, dtype=torch.int32).cuda()
+        flags = torch.zeros(n, dtype=torch.int32).cuda()
+        state = torch.zeros(5 * words, dtype=torch.int32).cuda()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        capi.check(lib.btb_pack_planes_state(P(d_text), nbytes, P(d_off), P(d_lw), P(d_el), n, 0, n, G, P(planes), P(flags),
+                                             P(state), st))
+        torch.cuda.synchronize()
+    finally:
+        capi.check(lib.btb_set_option(b"pack_gy", 0))
+    short = np.array([0 < w < 32 for w in wraps])
+    assert (flags.cpu().numpy() == short.astype(np.int32)).all()
+    pl = planes.cpu().numpy().view(np.uint32).reshape(3, n, words)
+    order = np.arange(32, dtype=np.uint32)
+    bits = lambda w: ((w[:, None] >> order[None, :]) & 1).reshape(-1)[:G]
+    for i in range(n):
+        if short[i]:
+            assert not pl[:, i].any(), i                               # skipped records leave all-zero planes
+            continue
+        valid = np.isin(aln[i], np.frombuffer(b"ACGTacgt", dtype=np.uint8))
+        code = (aln[i] >> 1) & 3
+        assert (bits(pl[2, i]) == valid).all(), i
+        assert (bits(pl[0, i]) == (valid & (code & 1).astype(bool))).all(), i
+        assert (bits(pl[1, i]) == (valid & (code >> 1).astype(bool))).all(), i
+    # k2 over the same planes (the skipped records' zero planes count as invalid everywhere, in both)
+    ref = torch.zeros(5 * words, dtype=torch.int32).cuda()
+    capi.check(lib.btb_column_mask(P(planes), n, n, G, P(ref), 0, st))
+    torch.cuda.synchronize()
+    got, want = state.cpu().numpy().view(np.uint32).reshape(5, words), ref.cpu().numpy().view(np.uint32).reshape(5, words)
+    tail = np.uint32((1 << (G % 32)) - 1) if G % 32 else np.uint32(0xFFFFFFFF)
+    last = (G - 1) // 32
+    for plane in range(4):
+        assert (got[plane, :last] == want[plane, :last]).all() and (got[plane, last] & tail) == (want[plane, last] & tail)
