@@ -297,6 +297,10 @@ def e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, l
     dist.barrier(group=host_pg)
     h_seqs = _shared_array(p_seqs, (n, stride), np.uint8, False)
     h_out = _shared_array(p_mat, (n, n), out_np, False)
+    dist.barrier(group=host_pg)
+    if rank == 0:                       # every rank has its mappings: the names can go now (nothing is left behind if a step fails)
+        os.unlink(p_seqs)
+        os.unlink(p_mat)
     lo, hi = n * rank // world, n * (rank + 1) // world
     h_out[lo:hi] = 0                                               # first touch of "my" rows next to my GPU
     _page_lock(h_seqs)
@@ -349,9 +353,6 @@ def e2e_multi(lib, _capi, torch, dist, host_pg, seqs, plan, n, L, rank, world, l
         _page_unlock(h_seqs)
         _page_unlock(h_out)
         dist.barrier(group=host_pg)
-        if rank == 0:
-            os.unlink(p_seqs)
-            os.unlink(p_mat)
     return e2e_s, info, h_seqs[:, :L], h_out, cleanup
 
 
