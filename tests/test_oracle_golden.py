@@ -125,3 +125,26 @@ def test_oracle_file_and_memory_forms_agree(oracle, tmp_path):
         assert r.returncode == 0 and fas == want
     r, csv = run_dists(oracle, tmp_path, fas, flags=("-c",))
     assert csv == oracle.format_matrix(names, oracle.snp_dists_rows(aln[:, keep]))
+
+
+def test_oracle_matches_third_party_hamming_on_dense_alignments(oracle):
+    """An implementation nobody here wrote: on an alignment of A/C/G/T only, snp-dists' distance (SURVEY.md App. A.3:
+    positions where both symbols count and differ) is the plain Hamming distance -- scipy's pdist x L.  With N, gaps
+    and lower case the tools' rule is Hamming over the positions where both rows hold one of ACGT (after upper-casing),
+    which scipy gives per pair on the masked columns."""
+    from scipy.spatial.distance import hamming, pdist, squareform
+    n, L = 41, 777
+    dense = synth.snp_alignment(n, L, seed=11)
+    assert set(np.unique(dense)) <= set(b"ACGT")
+    want = np.rint(squareform(pdist(dense, metric="hamming")) * L).astype(np.int64)
+    assert (oracle.snp_dists_rows(dense, threads=2) == want).all()
+    mixed = synth.snp_alignment(19, 400, seed=12, heavy_n=0.15, iupac=0.03, lower=0.1)
+    up = mixed.copy()
+    up[(up >= 97) & (up <= 122)] -= 32
+    counts = np.isin(up, np.frombuffer(b"ACGT", dtype=np.uint8))
+    got = oracle.snp_dists_rows(mixed, threads=2)
+    for i in range(len(mixed)):
+        for j in range(len(mixed)):
+            both = counts[i] & counts[j]
+            d = int(round(hamming(up[i][both], up[j][both]) * both.sum())) if both.any() else 0
+            assert got[i, j] == d, (i, j)
